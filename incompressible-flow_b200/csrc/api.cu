@@ -1,0 +1,1014 @@
+// api.cu -- C ABI (include/impes_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// Replaces, behind plain-C entry points, the bodies of
+//   PressureSolver   [REF src/pressure_solver.cpp:7-125]
+//   SaturationSolver [REF src/saturation_solver.cpp:19-112]
+// (and their MPI analogues [REF src/par_pressure_solver.cpp] [REF src/par_saturation_solver.cpp]).
+// Nothing is assembled: the state a solve needs (coefficients, Krylov vectors, halo buffers,
+// the NCCL communicator) lives in the handle.  No CPU fallback exists in this file.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/impes_b200.h"
+#include "kernels.cuh"
+#include "nccl_shim.h"
+
+using namespace impes;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+std::string g_create_error;
+
+enum { KC_DARCY = 0, KC_MINRES = 1, KC_PREC = 2, KC_SAT = 3, KC_COEFF = 4, KC_DOT = 5, KC_MISC = 6, KC_COMM = 7, KC_N = 8 };
+
+}  // namespace
+
+struct impes_ctx {
+  impes_desc d;
+  Lay L;
+  Phys ph;
+  SatParam sp;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  // global (all-rank) sizes in native host layout
+  long g_ncell = 0, g_nvx = 0, g_nvy = 0, g_nvz = 0, g_nv = 0, g_np = 0;
+  double h[3] = {1, 1, 1}, vol = 1, geo[3] = {0, 0, 0};  // internal directions
+  // device arrays
+  double* K[3] = {nullptr, nullptr, nullptr};
+  double* phi = nullptr;
+  double* S[2] = {nullptr, nullptr};
+  int scur = 0;
+  double* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // RK stage buffers (lazy)
+  double* m[3] = {nullptr, nullptr, nullptr};
+  double *Md = nullptr, *T = nullptr, *rhs = nullptr;
+  double *x = nullptr, *v0 = nullptr, *v1 = nullptr, *w0 = nullptr, *w1 = nullptr, *q = nullptr, *u1 = nullptr;
+  double* tmpv = nullptr;  // scratch dvec for operator-level entry points
+  double* partial = nullptr;
+  double* scal = nullptr;  // [0] alpha, [1] beta^2
+  unsigned* ticket = nullptr;
+  MinresState* st = nullptr;  // [2]
+  unsigned long long* guard = nullptr;
+  double* flushbuf = nullptr;
+  long flush_n = 0;
+  bool coeff_valid = false;
+  // launch geometry
+  int grid_cells = 0, grid_vec = 0, grid_sgs = 0, num_sms = 0;
+  // graphs
+  bool use_graph = true;
+  cudaGraphExec_t minres_exec = nullptr;
+  int graph_iters = 0;
+  // multi-GPU
+  NcclShim nccl;
+  ncclComm_t comm = nullptr;
+  // accounting
+  long long launches = 0;
+  bool profiling = false;
+  double prof_ms[KC_N] = {0};
+  long long prof_n[KC_N] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof b_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      h->err = b_;                                                                                 \
+      return IMPES_ERR_CUDA;                                                                       \
+    }                                                                                              \
+  } while (0)
+
+#define NK(call)                                                                  \
+  do {                                                                            \
+    int r_ = (call);                                                              \
+    if (r_ != 0) {                                                                \
+      char b_[512];                                                               \
+      snprintf(b_, sizeof b_, "%s:%d: %s -> nccl error %d", __FILE__, __LINE__, #call, r_); \
+      h->err = b_;                                                                \
+      return IMPES_ERR_NCCL;                                                      \
+    }                                                                             \
+  } while (0)
+
+#define RET_IF(x)            \
+  do {                       \
+    int rc_ = (x);           \
+    if (rc_) return rc_;     \
+  } while (0)
+
+long pad32(long n) { return (n + 31) / 32 * 32; }
+
+// Launch accounting (+ optional per-class device timing when profiling is on).
+struct Scope {
+  impes_ctx* h;
+  int cls;
+  int n;
+  Scope(impes_ctx* h_, int cls_, int n_ = 1) : h(h_), cls(cls_), n(n_) {
+    h->launches += n;
+    h->prof_n[cls] += n;
+    if (h->profiling) cudaEventRecord(h->ev0, h->stream);
+  }
+  ~Scope() {
+    if (h->profiling) {
+      cudaEventRecord(h->ev1, h->stream);
+      cudaEventSynchronize(h->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      h->prof_ms[cls] += ms;
+    }
+  }
+};
+
+int dev_alloc(impes_ctx* h, double** p, long n) {
+  CK(cudaMalloc((void**)p, sizeof(double) * (size_t)std::max<long>(n, 1)));
+  CK(cudaMemsetAsync(*p, 0, sizeof(double) * (size_t)std::max<long>(n, 1), h->stream));
+  return 0;
+}
+
+// ---- host (global, native) <-> device (slab local) transfers -------------------------------
+
+// cvec (cell array with ghost planes) from a global cell array
+int upload_cells(impes_ctx* h, const double* host, double* dev) {
+  const Lay& L = h->L;
+  const int k0 = std::max(L.zlo - 1, 0), k1 = std::min(L.zhi + 1, L.NZ);
+  CK(cudaMemcpyAsync(dev + L.plane * (k0 - L.zlo + 1), host + L.plane * k0, sizeof(double) * L.plane * (k1 - k0),
+                     cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+int download_cells_owned(impes_ctx* h, const double* dev, double* host) {
+  const Lay& L = h->L;
+  CK(cudaMemcpyAsync(host + L.plane * L.zlo, dev + L.plane, sizeof(double) * L.plane * L.nzl, cudaMemcpyDeviceToHost,
+                     h->stream));
+  return 0;
+}
+
+// dvec from / to a global native Darcy vector [ux|uy|uz|p]; which: bit0 = velocity, bit1 = pressure.
+// Uploads fill the ghost planes from the (global) host array as well.
+int upload_dvec(impes_ctx* h, const double* host_v, const double* host_p, double* dev) {
+  const Lay& L = h->L;
+  if (host_v) {
+    const long px = (long)(L.NX + 1) * L.NY, py = (long)L.NX * (L.NY + 1);
+    CK(cudaMemcpyAsync(dev + L.off_x, host_v + px * L.zlo, sizeof(double) * px * L.nzl, cudaMemcpyHostToDevice, h->stream));
+    if (L.has_y)
+      CK(cudaMemcpyAsync(dev + L.off_y, host_v + h->g_nvx + py * L.zlo, sizeof(double) * py * L.nzl,
+                         cudaMemcpyHostToDevice, h->stream));
+    const int f0 = std::max(L.zlo - 1, 0), f1 = L.zhi + 1;  // face planes [f0, f1)
+    CK(cudaMemcpyAsync(dev + L.off_z + L.plane * (f0 - L.zlo + 1), host_v + h->g_nvx + h->g_nvy + L.plane * f0,
+                       sizeof(double) * L.plane * (f1 - f0), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (host_p) {
+    const int k0 = std::max(L.zlo - 1, 0), k1 = std::min(L.zhi + 1, L.NZ);
+    CK(cudaMemcpyAsync(dev + L.off_p + L.plane * (k0 - L.zlo + 1), host_p + L.plane * k0,
+                       sizeof(double) * L.plane * (k1 - k0), cudaMemcpyHostToDevice, h->stream));
+  }
+  return 0;
+}
+int download_dvec_owned(impes_ctx* h, const double* dev, double* host_v, double* host_p) {
+  const Lay& L = h->L;
+  if (host_v) {
+    const long px = (long)(L.NX + 1) * L.NY, py = (long)L.NX * (L.NY + 1);
+    CK(cudaMemcpyAsync(host_v + px * L.zlo, dev + L.off_x, sizeof(double) * px * L.nzl, cudaMemcpyDeviceToHost, h->stream));
+    if (L.has_y)
+      CK(cudaMemcpyAsync(host_v + h->g_nvx + py * L.zlo, dev + L.off_y, sizeof(double) * py * L.nzl,
+                         cudaMemcpyDeviceToHost, h->stream));
+    const int nf = L.nzl + (L.zhi == L.NZ ? 1 : 0);  // owned face planes (+ top boundary on the last rank)
+    CK(cudaMemcpyAsync(host_v + h->g_nvx + h->g_nvy + L.plane * L.zlo, dev + L.off_z + L.plane, sizeof(double) * L.plane * nf,
+                       cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (host_p)
+    CK(cudaMemcpyAsync(host_p + L.plane * L.zlo, dev + L.off_p + L.plane, sizeof(double) * L.plane * L.nzl,
+                       cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+// ---- halo exchange (world_size > 1): grouped ncclSend/Recv of whole planes ---------------------
+// up = towards rank+1.  Each (ptr, plane index) pair names a plane inside a (nzl+2)-plane region.
+int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool send_down_bottom_owned) {
+  // send_up_top_owned:   my plane index nzl   (top owned)    -> upper rank's plane 0      (ghost below)
+  // send_down_bottom_owned: my plane index 1 (bottom owned)  -> lower rank's plane nzl+1  (ghost above)
+  if (h->L.nranks == 1) return 0;
+  const Lay& L = h->L;
+  const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
+  Scope sc(h, KC_COMM, 1);
+  NK(h->nccl.GroupStart());
+  if (send_up_top_owned) {
+    if (up >= 0) NK(h->nccl.Send(base + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
+    if (dn >= 0) NK(h->nccl.Recv(base, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
+  }
+  if (send_down_bottom_owned) {
+    if (dn >= 0) NK(h->nccl.Send(base + L.plane, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
+    if (up >= 0) NK(h->nccl.Recv(base + L.plane * (L.nzl + 1), (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
+  }
+  NK(h->nccl.GroupEnd());
+  return 0;
+}
+// halo of a Darcy vector before K1: p ghost-below, uz ghost-below (from the lower rank's top owned
+// face plane) and uz ghost-above (the upper rank's bottom owned face plane).
+int halo_darcy(impes_ctx* h, double* v) {
+  if (h->L.nranks == 1) return 0;
+  const Lay& L = h->L;
+  const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
+  Scope sc(h, KC_COMM, 1);
+  NK(h->nccl.GroupStart());
+  if (up >= 0) {
+    NK(h->nccl.Send(v + L.off_p + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
+    NK(h->nccl.Send(v + L.off_z + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
+    NK(h->nccl.Recv(v + L.off_z + L.plane * (L.nzl + 1), (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
+  }
+  if (dn >= 0) {
+    NK(h->nccl.Recv(v + L.off_p, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
+    NK(h->nccl.Recv(v + L.off_z, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
+    NK(h->nccl.Send(v + L.off_z + L.plane, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
+  }
+  NK(h->nccl.GroupEnd());
+  return 0;
+}
+int allreduce_scalar(impes_ctx* h, double* p) {
+  if (h->L.nranks == 1) return 0;
+  Scope sc(h, KC_COMM, 1);
+  NK(h->nccl.AllReduce(p, p, 1, ncclFloat64, ncclSum, h->comm, h->stream));
+  return 0;
+}
+
+// ---- coefficient update (K4) -------------------------------------------------------------------
+int update_coeff(impes_ctx* h) {
+  const Lay& L = h->L;
+  RET_IF(exchange_planes(h, h->S[h->scur], true, true));
+  {
+    Scope sc(h, KC_COEFF, 2);
+    const int g = (int)((L.ncv + BLK - 1) / BLK);
+    k_cell_coeff<<<g, BLK, 0, h->stream>>>(L, h->ph, h->S[h->scur], h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1],
+                                           h->geo[2], h->m[0], h->m[1], h->m[2]);
+    k_face_coeff<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->m[0], h->m[1], h->m[2], h->Md, h->T);
+  }
+  CK(cudaGetLastError());
+  h->coeff_valid = true;
+  return 0;
+}
+
+// ---- K1 ----------------------------------------------------------------------------------------
+int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState* st) {
+  RET_IF(halo_darcy(h, x));
+  {
+    Scope sc(h, KC_DARCY, 1);
+    if (dot)
+      k_darcy_apply<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->m[0], h->m[1], h->m[2], x, y, h->partial,
+                                                                h->scal + 0, h->ticket, st);
+    else
+      k_darcy_apply<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->m[0], h->m[1], h->m[2], x, y, h->partial,
+                                                                 h->scal + 0, h->ticket, st);
+  }
+  if (dot) RET_IF(allreduce_scalar(h, h->scal + 0));
+  return 0;
+}
+
+// ---- K3: Schur block --------------------------------------------------------------------------
+int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const MinresState* st) {
+  Scope sc(h, KC_PREC, 1);
+  Lay L = h->L;
+  const double* T = h->T;
+  const double* Md = h->Md;
+  void* args[] = {(void*)&L, (void*)&T, (void*)&Md, (void*)&r, (void*)&y, (void*)&fwd, (void*)&bwd, (void*)&st};
+  CK(cudaLaunchCooperativeKernel((void*)k_sgs_wavefront, dim3(h->grid_sgs), dim3(BLK), args, 0, h->stream));
+  return 0;
+}
+
+// y_p = SchurPrec(r_p).  Parity mode: lexicographic symmetric GS; across slabs the sweep is pipelined
+// rank by rank (exact global ordering, so results do not depend on the number of GPUs).
+int schur_prec(impes_ctx* h, const double* r, double* y, const MinresState* st) {
+  const Lay& L = h->L;
+  if (h->d.schur_prec != IMPES_SCHUR_SGS_LEX) {
+    h->err = "schur_prec: only IMPES_SCHUR_SGS_LEX is implemented";
+    return IMPES_ERR_UNSUPPORTED;
+  }
+  if (L.nranks == 1) return launch_sgs(h, r, y, 1, 1, st);
+  const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
+  double* yp = y + L.off_p;
+  // forward: wait for the plane below, sweep, hand my top plane up
+  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream)); }
+  RET_IF(launch_sgs(h, r, y, 1, 0, st));
+  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream)); }
+  // backward: wait for the plane above, sweep, hand my bottom plane down
+  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp + L.plane * (L.nzl + 1), (size_t)L.plane, ncclFloat64, up, h->comm, h->stream)); }
+  RET_IF(launch_sgs(h, r, y, 0, 1, st));
+  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + L.plane, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream)); }
+  return 0;
+}
+
+int dot_owned(impes_ctx* h, const double* a, const double* b, double* out, const MinresState* st) {
+  {
+    Scope sc(h, KC_DOT, 1);
+    k_dot_owned<<<h->grid_cells, BLK, 0, h->stream>>>(h->L, a, b, h->partial, out, h->ticket, st);
+  }
+  return allreduce_scalar(h, out);
+}
+
+// one MINRES iteration with the given vector roles; reads st_cur, writes st_next
+int minres_iteration(impes_ctx* h, double* u1, double* q, double* v0, double* v1, double* w0, double* w1,
+                     const MinresState* st_cur, MinresState* st_next) {
+  const Lay& L = h->L;
+  RET_IF(darcy_apply(h, u1, q, true, st_cur));
+  {
+    Scope sc(h, KC_MINRES, 1);
+    k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, L.off_p, q, v0, v1, h->Md, q, h->scal + 0, st_cur);
+  }
+  RET_IF(schur_prec(h, v0, q, st_cur));
+  RET_IF(dot_owned(h, v0, q, h->scal + 1, st_cur));
+  {
+    Scope sc(h, KC_MINRES, 1);
+    k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, w0, w1, u1, h->x, v0, q, h->scal + 0, h->scal + 1, st_cur,
+                                                   st_next, h->d.darcy_maxiter);
+  }
+  return 0;
+}
+
+int minres_pair(impes_ctx* h) {
+  RET_IF(minres_iteration(h, h->u1, h->q, h->v0, h->v1, h->w0, h->w1, h->st + 0, h->st + 1));
+  RET_IF(minres_iteration(h, h->q, h->u1, h->v1, h->v0, h->w1, h->w0, h->st + 1, h->st + 0));
+  return 0;
+}
+
+int build_minres_graph(impes_ctx* h) {
+  if (h->minres_exec || !h->use_graph || h->L.nranks > 1 || h->profiling) return 0;
+  const int pairs = 8;
+  cudaGraph_t g = nullptr;
+  const long long l0 = h->launches;
+  long long n0[KC_N];
+  memcpy(n0, h->prof_n, sizeof n0);
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    h->use_graph = false;
+    return 0;
+  }
+  int rc = 0;
+  for (int p = 0; p < pairs && !rc; ++p) rc = minres_pair(h);
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  h->launches = l0;  // capture is not execution
+  memcpy(h->prof_n, n0, sizeof n0);
+  if (rc || e != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    h->use_graph = false;  // e.g. cooperative launch not capturable: fall back to direct launches
+    return 0;
+  }
+  if (cudaGraphInstantiate(&h->minres_exec, g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    h->minres_exec = nullptr;
+    h->use_graph = false;
+  }
+  cudaGraphDestroy(g);
+  h->graph_iters = 2 * pairs;
+  return 0;
+}
+
+int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
+  const Lay& L = h->L;
+  auto t0 = std::chrono::steady_clock::now();
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, h->stream));
+  RET_IF(update_coeff(h));
+  const size_t nb = sizeof(double) * (size_t)L.ntot;
+  CK(cudaMemsetAsync(h->x, 0, nb, h->stream));   // x = 0  [REF src/pressure_solver.cpp:101]
+  CK(cudaMemsetAsync(h->v0, 0, nb, h->stream));
+  CK(cudaMemsetAsync(h->w0, 0, nb, h->stream));
+  CK(cudaMemsetAsync(h->w1, 0, nb, h->stream));
+  CK(cudaMemsetAsync(h->q, 0, nb, h->stream));
+  CK(cudaMemsetAsync(h->u1, 0, nb, h->stream));
+  CK(cudaMemcpyAsync(h->v1, h->rhs, nb, cudaMemcpyDeviceToDevice, h->stream));  // v1 = b - A*0
+  {
+    Scope sc(h, KC_PREC, 1);
+    k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(L.off_p, h->v1, h->Md, h->u1);
+  }
+  RET_IF(schur_prec(h, h->v1, h->u1, nullptr));
+  RET_IF(dot_owned(h, h->u1, h->v1, h->scal + 1, nullptr));
+  {
+    Scope sc(h, KC_MINRES, 1);
+    k_minres_init<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, h->v1, h->u1, h->scal + 1, h->st + 0, h->d.darcy_rtol,
+                                                      h->d.darcy_atol);
+  }
+  CK(cudaGetLastError());
+  RET_IF(build_minres_graph(h));
+  MinresState hs;
+  for (;;) {
+    CK(cudaMemcpyAsync(&hs, h->st + 0, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (hs.done) break;
+    if (h->d.darcy_print_level == 1 && h->L.rank == 0)
+      printf("MINRES: iteration %3d: ||r||_B = %g\n", hs.it, fabs(hs.eta));
+    if (h->minres_exec) {
+      CK(cudaGraphLaunch(h->minres_exec, h->stream));
+      const long long per_iter = 5;
+      h->launches += per_iter * h->graph_iters;
+      h->prof_n[KC_DARCY] += h->graph_iters;
+      h->prof_n[KC_MINRES] += 2 * h->graph_iters;
+      h->prof_n[KC_PREC] += h->graph_iters;
+      h->prof_n[KC_DOT] += h->graph_iters;
+    } else {
+      for (int p = 0; p < 4; ++p) RET_IF(minres_pair(h));
+    }
+    CK(cudaGetLastError());
+  }
+  RET_IF(halo_darcy(h, h->x));  // ghosts of the result (velocity ghost faces feed the saturation step)
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (stats) {
+    stats->iterations = hs.it;
+    stats->converged = hs.done == 1;
+    stats->final_norm = fabs(hs.eta);
+    stats->initial_norm = hs.eta0;
+    stats->device_ms = ms;
+    stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  if (hs.done != 1) {
+    char b[256];
+    snprintf(b, sizeof b, "Darcy solver DIDN'T converge. Iter = %d. Final norm = %g", hs.it, fabs(hs.eta));
+    h->err = b;
+    return IMPES_ERR_NOT_CONVERGED;
+  }
+  return 0;
+}
+
+// ---- K6 driver ---------------------------------------------------------------------------------
+int n_substeps(const impes_ctx* h, double global_dt, double dt) {
+  if (h->d.substep_rule == IMPES_SUBSTEPS_PARALLEL) {
+    int n = 0;
+    double t = 0.0;
+    while (!(t >= global_dt - dt / 2)) { t += dt; ++n; }  // [REF src/par_saturation_solver.cpp:149-155]
+    return n;
+  }
+  return (int)(global_dt / dt);  // [REF src/saturation_solver.cpp:74-75]
+}
+
+int sat_rate(impes_ctx* h, double* Sin, double* out) {  // out = M_phi^-1 (Kt f(Sin) + b)
+  RET_IF(exchange_planes(h, Sin, true, true));
+  Scope sc(h, KC_SAT, 1);
+  k_sat_substep<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->ph, h->sp, h->x, h->phi, Sin, out);
+  return 0;
+}
+int axpby(impes_ctx* h, double a, const double* x, double b, const double* y, double* out) {
+  Scope sc(h, KC_SAT, 1);
+  k_axpby<<<h->grid_vec, BLK, 0, h->stream>>>(h->L.ncv, a, x, b, y, out);
+  return 0;
+}
+int xpby(impes_ctx* h, const double* x, double b, const double* y, double* out) {
+  Scope sc(h, KC_SAT, 1);
+  k_xpby<<<h->grid_vec, BLK, 0, h->stream>>>(h->L.ncv, x, b, y, out);
+  return 0;
+}
+
+int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
+  const int nt = n_substeps(h, global_dt, dt);
+  if (nsub) *nsub = nt;
+  h->sp.dt = dt;
+  const int ode = h->d.substep_rule == IMPES_SUBSTEPS_SERIAL ? 1 : h->d.ode_solver_type;  // serial ignores -ode
+  if (ode != 1 && ode != 2 && ode != 3 && ode != 4) {
+    char b[128];
+    snprintf(b, sizeof b, "Uknown ODE solver: type %d", ode);  // [REF src/par_saturation_solver.cpp:121-123]
+    h->err = b;
+    return IMPES_ERR_UNSUPPORTED;
+  }
+  if (ode != 1)
+    for (int s = 0; s < 4; ++s)
+      if (!h->stage[s]) RET_IF(dev_alloc(h, &h->stage[s], h->L.ncv));
+  for (int ti = 1; ti <= nt; ++ti) {
+    double* S = h->S[h->scur];
+    double* Sn = h->S[h->scur ^ 1];
+    if (ode == 1) {
+      RET_IF(exchange_planes(h, S, true, true));
+      {
+        Scope sc(h, KC_SAT, 1);
+        k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->ph, h->sp, h->x, h->phi, S, Sn);
+      }
+      h->scur ^= 1;
+    } else if (ode == 2) {  // RK2Solver(a = 1)
+      const double a = 1.0, bb = 0.5 / a;
+      double *k = h->stage[0], *x1 = h->stage[1];
+      RET_IF(sat_rate(h, S, k));
+      RET_IF(xpby(h, S, (1. - bb) * dt, k, x1));
+      RET_IF(xpby(h, S, a * dt, k, Sn));
+      RET_IF(sat_rate(h, Sn, k));
+      RET_IF(xpby(h, x1, bb * dt, k, S));
+    } else if (ode == 3) {  // RK3SSPSolver
+      double *k = h->stage[0], *y = h->stage[1];
+      RET_IF(sat_rate(h, S, k));
+      RET_IF(xpby(h, S, dt, k, y));
+      RET_IF(sat_rate(h, y, k));
+      RET_IF(xpby(h, y, dt, k, y));
+      RET_IF(axpby(h, 0.75, S, 0.25, y, y));
+      RET_IF(sat_rate(h, y, k));
+      RET_IF(xpby(h, y, dt, k, y));
+      RET_IF(axpby(h, 1. / 3, S, 2. / 3, y, S));
+    } else {  // RK4Solver
+      double *k = h->stage[0], *y = h->stage[1], *z = h->stage[2];
+      RET_IF(sat_rate(h, S, k));
+      RET_IF(xpby(h, S, dt / 2, k, y));
+      RET_IF(xpby(h, S, dt / 6, k, z));
+      RET_IF(sat_rate(h, y, k));
+      RET_IF(xpby(h, S, dt / 2, k, y));
+      RET_IF(xpby(h, z, dt / 3, k, z));
+      RET_IF(sat_rate(h, y, k));
+      RET_IF(xpby(h, S, dt, k, y));
+      RET_IF(xpby(h, z, dt / 3, k, z));
+      RET_IF(sat_rate(h, y, k));
+      RET_IF(xpby(h, z, dt / 6, k, S));
+    }
+  }
+  CK(cudaGetLastError());
+  h->coeff_valid = false;
+  return 0;
+}
+
+// RHS: block 0 = 0, block 1 = -(Q, psi) with the cell-centre rule (P0)  [REF src/pressure_solver.cpp:35-45]
+// WellFunctionCoefficient::eval2D/eval3D [REF src/param.hpp:306-345].  Static: built once on the host.
+double well_Q(const impes_desc& d, const double* p) {
+  const impes_well &in = d.injection, &pr = d.production;
+  if (d.dim == 2) {
+    if (fabs(p[0] - in.center[0]) <= in.radius && fabs(p[1] - in.center[1]) <= in.radius) return d.inflow;
+    if (fabs(p[0] - pr.center[0]) <= pr.radius && fabs(p[1] - pr.center[1]) <= pr.radius) return d.outflow;
+    return 0.;
+  }
+  if (fabs(p[0] - in.center[0]) <= in.radius && fabs(p[2] - in.center[2]) <= in.radius && p[1] >= in.center[1] &&
+      p[1] <= in.center[1] + in.height)
+    return d.inflow;
+  if (fabs(p[0] - pr.center[0]) <= pr.radius && fabs(p[2] - pr.center[2]) <= pr.radius && p[1] >= pr.center[1] &&
+      p[1] <= pr.center[1] + pr.height)
+    return d.outflow;
+  return 0.;
+}
+
+int check_handle(impes_ctx* h) {
+  if (!h) return IMPES_ERR_BAD_ARG;
+  if (cudaSetDevice(h->dev) != cudaSuccess) {
+    h->err = "cudaSetDevice failed";
+    return IMPES_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported C ABI
+// =================================================================================================
+
+API int impes_abi_version(void) { return IMPES_ABI_VERSION; }
+
+API void impes_desc_defaults(impes_desc* d) {
+  // Param::Param() / DarcySolverParam() / Well()  [REF src/param.cpp:8-13,26-30,35-68]
+  memset(d, 0, sizeof *d);
+  d->struct_size = (int32_t)sizeof(impes_desc);
+  d->dim = 2;
+  d->nx = d->ny = d->nz = 100;
+  d->sx = d->sy = d->sz = 100.;
+  d->order_v = 1; d->order_p = 1; d->order_s = 0;
+  d->two_phase = 0;
+  d->ode_solver_type = 1;
+  d->mu_w = 1.0; d->mu_o = 1.0;  // MU_W, MU_O [REF config.hpp.in:37,43]
+  d->injection.radius = d->production.radius = 1.;
+  d->injection.height = d->production.height = 1.;
+  d->inflow = 1.; d->outflow = -1.; d->saturation_source = 1.;
+  d->darcy_maxiter = 1000; d->darcy_rtol = 1e-6; d->darcy_atol = 1e-10; d->darcy_print_level = 0;
+  d->schur_prec = IMPES_SCHUR_SGS_LEX;
+  d->substep_rule = IMPES_SUBSTEPS_SERIAL;
+  d->rank = 0; d->world_size = 1; d->device = 0;
+}
+
+API const char* impes_last_error(impes_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+API void impes_destroy(impes_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->dev);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->minres_exec) cudaGraphExecDestroy(h->minres_exec);
+  if (h->comm) h->nccl.CommDestroy(h->comm);
+  double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->stage[0], h->stage[1], h->stage[2],
+                    h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf};
+  for (double* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->ticket) cudaFree(h->ticket);
+  if (h->st) cudaFree(h->st);
+  if (h->guard) cudaFree(h->guard);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const double* Kz, const double* phi) {
+  const impes_desc& d = h->d;
+  if (d.dim != 2 && d.dim != 3) { h->err = "dim must be 2 or 3"; return IMPES_ERR_BAD_ARG; }
+  if (d.nx < 1 || d.ny < 1 || (d.dim == 3 && d.nz < 1)) { h->err = "grid sizes must be >= 1"; return IMPES_ERR_BAD_ARG; }
+  if (!Kx || !Ky || (d.dim == 3 && !Kz)) { h->err = "permeability arrays missing"; return IMPES_ERR_BAD_ARG; }
+  if (d.order_v != 0 || d.order_p != 0 || d.order_s != 0) {
+    h->err = "only RT0/P0/P0 (-ov 0 -op 0 -os 0) is implemented on the GPU path so far";
+    return IMPES_ERR_UNSUPPORTED;
+  }
+  if (d.world_size < 1 || d.rank < 0 || d.rank >= d.world_size) { h->err = "bad rank/world_size"; return IMPES_ERR_BAD_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    h->err = "no CUDA device available (the IMPES hot path has no CPU fallback)";
+    return IMPES_ERR_CUDA;
+  }
+  h->dev = d.device;
+  CK(cudaSetDevice(h->dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->dev));
+  h->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  if (const char* e = getenv("IMPES_NO_GRAPH")) h->use_graph = !(e[0] == '1');
+
+  Lay& L = h->L;
+  L.NX = d.nx;
+  L.has_y = d.dim == 3;
+  L.NY = d.dim == 3 ? d.ny : 1;
+  L.NZ = d.dim == 3 ? d.nz : d.ny;
+  const double H[3] = {d.sx / d.nx, d.sy / d.ny, d.dim == 3 ? d.sz / d.nz : 1.0};
+  h->vol = H[0] * H[1] * (d.dim == 3 ? H[2] : 1.0);
+  if (d.dim == 3) { h->h[0] = H[0]; h->h[1] = H[1]; h->h[2] = H[2]; }
+  else { h->h[0] = H[0]; h->h[1] = 1.0; h->h[2] = H[1]; }
+  for (int c = 0; c < 3; ++c) h->geo[c] = h->h[c] * h->h[c] / h->vol;
+  if (d.world_size > L.NZ) { h->err = "more ranks than cell planes"; return IMPES_ERR_BAD_ARG; }
+  L.rank = d.rank;
+  L.nranks = d.world_size;
+  {  // balanced slabs: the first (NZ % P) ranks get one extra plane
+    const int base = L.NZ / L.nranks, rem = L.NZ % L.nranks;
+    L.zlo = d.rank * base + std::min(d.rank, rem);
+    L.nzl = base + (d.rank < rem ? 1 : 0);
+    L.zhi = L.zlo + L.nzl;
+  }
+  L.plane = (long)L.NX * L.NY;
+  L.ncl = L.plane * L.nzl;
+  L.ncv = L.plane * (L.nzl + 2);
+  L.off_x = 0;
+  L.off_y = pad32(L.off_x + (long)(L.NX + 1) * L.NY * L.nzl);
+  L.off_z = L.has_y ? pad32(L.off_y + (long)L.NX * (L.NY + 1) * L.nzl) : L.off_y;
+  L.off_p = pad32(L.off_z + L.plane * (L.nzl + 2));
+  L.ntot = pad32(L.off_p + L.plane * (L.nzl + 2));
+  L.nblk = (int)((L.ncl + BLK - 1) / BLK);
+  h->g_ncell = L.plane * L.NZ;
+  h->g_nvx = (long)(L.NX + 1) * L.NY * L.NZ;
+  h->g_nvy = L.has_y ? (long)L.NX * (L.NY + 1) * L.NZ : 0;
+  h->g_nvz = L.plane * (L.NZ + 1);
+  h->g_nv = h->g_nvx + h->g_nvy + h->g_nvz;
+  h->g_np = h->g_ncell;
+  h->ph.two_phase = d.two_phase; h->ph.Sor = d.Sor; h->ph.Swc = d.Swc; h->ph.mu_w = d.mu_w; h->ph.mu_o = d.mu_o;
+  SatParam& sp = h->sp;
+  sp.two_phase = d.two_phase; sp.dt = 0; sp.vol = h->vol;
+  sp.hx = h->h[0]; sp.hy = h->h[1]; sp.hz = h->h[2];
+  sp.well_2d = d.dim == 2;
+  sp.inj_c0 = d.injection.center[0]; sp.inj_c1 = d.injection.center[1]; sp.inj_c2 = d.injection.center[2];
+  sp.inj_r = d.injection.radius; sp.inj_h = d.injection.height; sp.src = d.saturation_source;
+
+  h->grid_cells = L.nblk;
+  h->grid_vec = (int)std::min<long>((L.ntot + BLK - 1) / BLK, (long)h->num_sms * 8);
+  {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_wavefront, BLK, 0));
+    const long want = ((long)L.NY * L.nzl + BLK - 1) / BLK;
+    h->grid_sgs = (int)std::max<long>(1, std::min<long>(want, (long)per_sm * h->num_sms));
+  }
+
+  // device arrays
+  const double* Kin[3] = {Kx, d.dim == 3 ? Ky : nullptr, d.dim == 3 ? Kz : Ky};
+  for (int c = 0; c < 3; ++c) {
+    RET_IF(dev_alloc(h, &h->K[c], L.ncv));
+    RET_IF(dev_alloc(h, &h->m[c], L.ncv));
+    if (Kin[c]) RET_IF(upload_cells(h, Kin[c], h->K[c]));
+  }
+  RET_IF(dev_alloc(h, &h->phi, L.ncv));
+  {
+    std::vector<double> ph(h->g_ncell, 1.0);
+    if (phi) memcpy(ph.data(), phi, sizeof(double) * h->g_ncell);
+    RET_IF(upload_cells(h, ph.data(), h->phi));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  RET_IF(dev_alloc(h, &h->S[0], L.ncv));
+  RET_IF(dev_alloc(h, &h->S[1], L.ncv));
+  double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
+  for (double** v : vecs) RET_IF(dev_alloc(h, v, L.ntot));
+  {  // Md = 1 everywhere first (padding and ghost entries must stay harmless under division)
+    k_fill<<<h->grid_vec, BLK, 0, h->stream>>>(h->Md, L.ntot, 1.0);
+    h->launches++;
+  }
+  RET_IF(dev_alloc(h, &h->partial, L.nblk + 8));
+  RET_IF(dev_alloc(h, &h->scal, 8));
+  CK(cudaMalloc((void**)&h->ticket, sizeof(unsigned) * 4));
+  CK(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned) * 4, h->stream));
+  CK(cudaMalloc((void**)&h->st, sizeof(MinresState) * 4));  // [0,1] solver, [2] timing state, [3] sink
+  CK(cudaMemsetAsync(h->st, 0, sizeof(MinresState) * 4, h->stream));
+  {
+    MinresState bs;
+    memset(&bs, 0, sizeof bs);
+    bs.beta = 1.0; bs.eta = 1.0; bs.gamma0 = bs.gamma1 = 1.0;
+    const double sc[4] = {0.0, 0.0, 0.5, 1.0};
+    CK(cudaMemcpyAsync(h->st + 2, &bs, sizeof bs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->scal, sc, sizeof sc, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaMalloc((void**)&h->guard, sizeof(unsigned long long) * 2));
+  {  // rhs (global, native) built on the host, uploaded slab-wise
+    std::vector<double> g(h->g_np);
+    for (int kz = 0; kz < (d.dim == 3 ? d.nz : 1); ++kz)
+      for (int jy = 0; jy < d.ny; ++jy)
+        for (int ix = 0; ix < d.nx; ++ix) {
+          const double p[3] = {(ix + 0.5) * H[0], (jy + 0.5) * H[1], (kz + 0.5) * H[2]};
+          const double s = h->vol * well_Q(d, p);
+          g[ix + (long)d.nx * (jy + (long)d.ny * kz)] = -s;
+        }
+    RET_IF(upload_dvec(h, nullptr, g.data(), h->rhs));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+API int impes_create(const impes_desc* d, const double* Kx, const double* Ky, const double* Kz, const double* phi,
+                     impes_handle* out) {
+  if (!out) return IMPES_ERR_BAD_ARG;
+  *out = nullptr;
+  if (!d || d->struct_size != (int32_t)sizeof(impes_desc)) {
+    g_create_error = "impes_create: null descriptor or struct_size mismatch";
+    return IMPES_ERR_BAD_ARG;
+  }
+  impes_ctx* h = new impes_ctx();
+  h->d = *d;
+  const int rc = create_impl(h, Kx, Ky, Kz, phi);
+  if (rc) {
+    g_create_error = h->err;
+    impes_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+API int impes_get_dims(impes_handle h, impes_dims* out) {
+  if (!h || !out) return IMPES_ERR_BAD_ARG;
+  memset(out, 0, sizeof *out);
+  out->n_cells = h->g_ncell;
+  out->n_v = h->g_nv; out->n_p = h->g_np; out->n_s = h->g_ncell;
+  out->n_v_comp[0] = h->g_nvx;
+  if (h->d.dim == 3) { out->n_v_comp[1] = h->g_nvy; out->n_v_comp[2] = h->g_nvz; }
+  else { out->n_v_comp[1] = h->g_nvz; out->n_v_comp[2] = 0; }
+  out->slab_lo = h->L.zlo; out->slab_hi = h->L.zhi;
+  return 0;
+}
+
+API int impes_comm_unique_id(void* id128) {
+  NcclShim sh;
+  if (!sh.load()) return IMPES_ERR_NCCL;
+  ncclUniqueId id;
+  if (sh.GetUniqueId(&id) != 0) return IMPES_ERR_NCCL;
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+API int impes_comm_init(impes_handle h, const void* id128) {
+  RET_IF(check_handle(h));
+  if (h->L.nranks == 1) return 0;
+  if (!h->nccl.load()) { h->err = "cannot dlopen libnccl.so.2"; return IMPES_ERR_NCCL; }
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NK(h->nccl.CommInitRank(&h->comm, h->L.nranks, id, h->L.rank));
+  return 0;
+}
+
+API int impes_set_field(impes_handle h, int which, const double* host) {
+  RET_IF(check_handle(h));
+  if (!host) return IMPES_ERR_BAD_ARG;
+  switch (which) {
+    case IMPES_FIELD_SATURATION: RET_IF(upload_cells(h, host, h->S[h->scur])); h->coeff_valid = false; break;
+    case IMPES_FIELD_VELOCITY: RET_IF(upload_dvec(h, host, nullptr, h->x)); break;
+    case IMPES_FIELD_PRESSURE: RET_IF(upload_dvec(h, nullptr, host, h->x)); break;
+    case IMPES_FIELD_DARCY_X: RET_IF(upload_dvec(h, host, host + h->g_nv, h->x)); break;
+    default: h->err = "unknown field"; return IMPES_ERR_BAD_ARG;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_get_field(impes_handle h, int which, double* host) {
+  RET_IF(check_handle(h));
+  if (!host) return IMPES_ERR_BAD_ARG;
+  switch (which) {
+    case IMPES_FIELD_SATURATION: RET_IF(download_cells_owned(h, h->S[h->scur], host)); break;
+    case IMPES_FIELD_VELOCITY: RET_IF(download_dvec_owned(h, h->x, host, nullptr)); break;
+    case IMPES_FIELD_PRESSURE: RET_IF(download_dvec_owned(h, h->x, nullptr, host)); break;
+    case IMPES_FIELD_DARCY_X: RET_IF(download_dvec_owned(h, h->x, host, host + h->g_nv)); break;
+    default: h->err = "unknown field"; return IMPES_ERR_BAD_ARG;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_update_coefficients(impes_handle h) {
+  RET_IF(check_handle(h));
+  RET_IF(update_coeff(h));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_pressure_solve(impes_handle h, const double* S_host, double* x_host, impes_solve_stats* stats) {
+  RET_IF(check_handle(h));
+  impes_solve_stats loc;
+  if (!stats) stats = &loc;
+  memset(stats, 0, sizeof *stats);
+  auto t0 = std::chrono::steady_clock::now();
+  if (S_host) RET_IF(upload_cells(h, S_host, h->S[h->scur]));
+  const int rc = pressure_solve_device(h, stats);
+  if (rc && rc != IMPES_ERR_NOT_CONVERGED) return rc;
+  if (x_host) {
+    RET_IF(download_dvec_owned(h, h->x, x_host, x_host + h->g_nv));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+API int impes_saturation_advance(impes_handle h, const double* V_host, double* S_inout, int global_ti, double global_dt,
+                                 double dt_local, int* n_substeps_out) {
+  (void)global_ti;  // only names output files in the reference [REF src/saturation_solver.cpp:93-108]
+  RET_IF(check_handle(h));
+  if (!(dt_local > 0)) { h->err = "dt_local must be > 0"; return IMPES_ERR_BAD_ARG; }
+  if (V_host) RET_IF(upload_dvec(h, V_host, nullptr, h->x));
+  if (S_inout) RET_IF(upload_cells(h, S_inout, h->S[h->scur]));
+  RET_IF(saturation_device(h, global_dt, dt_local, n_substeps_out));
+  if (S_inout) RET_IF(download_cells_owned(h, h->S[h->scur], S_inout));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_guards(impes_handle h, int64_t* n_nonfinite, double* s_max) {
+  RET_IF(check_handle(h));
+  CK(cudaMemsetAsync(h->guard, 0, sizeof(unsigned long long) * 2, h->stream));
+  {
+    Scope sc(h, KC_MISC, 1);
+    k_guards<<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->S[h->scur], h->guard, h->guard + 1);
+  }
+  unsigned long long hg[2];
+  CK(cudaMemcpyAsync(hg, h->guard, sizeof hg, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  long long bad = (long long)hg[0];
+  unsigned long long b = hg[1];
+  double mx;
+  if (b == 0) mx = -INFINITY;
+  else {
+    b = (b & 0x8000000000000000ull) ? (b & 0x7fffffffffffffffull) : ~b;
+    memcpy(&mx, &b, 8);
+  }
+  if (h->L.nranks > 1) {  // MPI_Allreduce(SUM) / (MAX) of the reference [REF src/run_parallel.cpp:220-230]
+    double* tmp = h->scal + 4;
+    double hv[2] = {(double)bad, mx};
+    CK(cudaMemcpyAsync(tmp, hv, sizeof hv, cudaMemcpyHostToDevice, h->stream));
+    NK(h->nccl.AllReduce(tmp, tmp, 1, ncclFloat64, ncclSum, h->comm, h->stream));
+    NK(h->nccl.AllReduce(tmp + 1, tmp + 1, 1, ncclFloat64, ncclMax, h->comm, h->stream));
+    CK(cudaMemcpyAsync(hv, tmp, sizeof hv, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    bad = (long long)hv[0];
+    mx = hv[1];
+  }
+  if (n_nonfinite) *n_nonfinite = bad;
+  if (s_max) *s_max = mx;
+  return 0;
+}
+
+API int impes_darcy_apply(impes_handle h, const double* x_host, double* y_host) {
+  RET_IF(check_handle(h));
+  if (!x_host || !y_host) return IMPES_ERR_BAD_ARG;
+  if (!h->coeff_valid) RET_IF(update_coeff(h));
+  RET_IF(upload_dvec(h, x_host, x_host + h->g_nv, h->tmpv));
+  CK(cudaMemsetAsync(h->q, 0, sizeof(double) * h->L.ntot, h->stream));
+  RET_IF(darcy_apply(h, h->tmpv, h->q, false, nullptr));
+  RET_IF(download_dvec_owned(h, h->q, y_host, y_host + h->g_nv));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_prec_apply(impes_handle h, const double* r_host, double* y_host) {
+  RET_IF(check_handle(h));
+  if (!r_host || !y_host) return IMPES_ERR_BAD_ARG;
+  if (!h->coeff_valid) RET_IF(update_coeff(h));
+  RET_IF(upload_dvec(h, r_host, r_host + h->g_nv, h->tmpv));
+  CK(cudaMemsetAsync(h->q, 0, sizeof(double) * h->L.ntot, h->stream));
+  {
+    Scope sc(h, KC_PREC, 1);
+    k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->L.off_p, h->tmpv, h->Md, h->q);
+  }
+  RET_IF(schur_prec(h, h->tmpv, h->q, nullptr));
+  RET_IF(download_dvec_owned(h, h->q, y_host, y_host + h->g_nv));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_get_rhs(impes_handle h, double* rhs_host) {
+  RET_IF(check_handle(h));
+  if (!rhs_host) return IMPES_ERR_BAD_ARG;
+  RET_IF(download_dvec_owned(h, h->rhs, rhs_host, rhs_host + h->g_nv));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, double* ms_avg, double* ms_min) {
+  RET_IF(check_handle(h));
+  if (reps < 1) return IMPES_ERR_BAD_ARG;
+  if (!h->coeff_valid) RET_IF(update_coeff(h));
+  if (flush_l2 && !h->flushbuf) {
+    h->flush_n = (long)(256u << 20) / 8;  // 256 MiB > 126 MB L2
+    CK(cudaMalloc((void**)&h->flushbuf, sizeof(double) * h->flush_n));
+  }
+  const Lay& L = h->L;
+  double sum = 0, mn = 1e300;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const bool prof = h->profiling;
+  h->profiling = false;
+  for (int r = -2; r < reps; ++r) {  // 2 untimed warm-ups
+    if (flush_l2) k_fill<<<h->num_sms * 4, 512, 0, h->stream>>>(h->flushbuf, h->flush_n, (double)r);
+    CK(cudaEventRecord(e0, h->stream));
+    switch (kernel) {
+      case IMPES_KERNEL_DARCY_APPLY: RET_IF(darcy_apply(h, h->u1, h->q, true, nullptr)); break;
+      case IMPES_KERNEL_SAT_SUBSTEP: {
+        Scope sc(h, KC_SAT, 1);
+        h->sp.dt = 0.0;  // dt = 0: the state is not disturbed by repeated timing launches
+        k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, h->S[h->scur],
+                                                                   h->S[h->scur ^ 1]);
+        break;
+      }
+      case IMPES_KERNEL_MINRES_UPDATE: {
+        Scope sc(h, KC_MINRES, 2);
+        k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, L.off_p, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
+                                                       h->st + 2);
+        k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, h->w0, h->w1, h->u1, h->tmpv, h->v0, h->q, h->scal + 2,
+                                                       h->scal + 3, h->st + 2, h->st + 3, 1 << 30);
+        break;
+      }
+      case IMPES_KERNEL_PREC_APPLY: {
+        {
+          Scope sc(h, KC_PREC, 1);
+          k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(L.off_p, h->v1, h->Md, h->tmpv);
+        }
+        RET_IF(schur_prec(h, h->v1, h->tmpv, nullptr));
+        break;
+      }
+      case IMPES_KERNEL_COEFF: RET_IF(update_coeff(h)); break;
+      default: h->err = "unknown kernel id"; return IMPES_ERR_BAD_ARG;
+    }
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 0) { sum += ms; mn = std::min<double>(mn, ms); }
+  }
+  h->profiling = prof;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  if (ms_avg) *ms_avg = sum / reps;
+  if (ms_min) *ms_min = mn;
+  return 0;
+}
+
+API int64_t impes_launch_count(impes_handle h) { return h ? h->launches : 0; }
+
+API int impes_profile_enable(impes_handle h, int on) {
+  if (!h) return IMPES_ERR_BAD_ARG;
+  h->profiling = on != 0;
+  memset(h->prof_ms, 0, sizeof h->prof_ms);
+  memset(h->prof_n, 0, sizeof h->prof_n);
+  return 0;
+}
+
+API int impes_profile_read(impes_handle h, double* ms_by_kernel, int64_t* launches_by_kernel) {
+  if (!h) return IMPES_ERR_BAD_ARG;
+  for (int i = 0; i < KC_N; ++i) {
+    if (ms_by_kernel) ms_by_kernel[i] = h->prof_ms[i];
+    if (launches_by_kernel) launches_by_kernel[i] = h->prof_n[i];
+  }
+  return 0;
+}

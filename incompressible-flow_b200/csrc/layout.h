@@ -1,0 +1,65 @@
+// layout.h -- device data layout of the IMPES hot path (RT0 / P0 / P0 on a Cartesian grid).
+//
+// Internal grid: always 3-D (NX, NY, NZ).  A 2-D problem (nx, ny) is stored as (nx, 1, ny):
+// the 2-D y-direction plays the role of internal z and the internal y-component is absent
+// (has_y = 0).  Native dof order [ux | uy | uz | p] of include/impes_b200.h is preserved by
+// this mapping, so host<->device transfers are per-component contiguous copies.
+//
+// Slab decomposition (one rank per GPU) along internal z.  A rank owns cell planes
+// [zlo, zhi) and, by the rule "a cell owns its lower faces", the z-face planes [zlo, zhi)
+// (the last rank also owns the top boundary plane NZ).
+//
+// One Darcy-sized device vector ("dvec") holds, each component padded to 32 doubles:
+//   ux : nzl planes of (NX+1)*NY        owned only
+//   uy : nzl planes of NX*(NY+1)        owned only          (absent when !has_y)
+//   uz : (nzl+2) planes of NX*NY        face planes zlo-1 .. zhi   (ghost below / above)
+//   p  : (nzl+2) planes of NX*NY        cell planes zlo-1 .. zhi   (ghost below / above)
+// Cell-centred coefficient arrays (mobility-weighted m_d, saturation, ...) use the p layout
+// ("cvec", (nzl+2) planes).
+#pragma once
+#include <cstdint>
+
+namespace impes {
+
+struct Lay {
+  int NX, NY, NZ;      // internal global grid
+  int has_y;           // 0 for 2-D problems
+  int zlo, zhi, nzl;   // owned cell planes [zlo, zhi)
+  int rank, nranks;
+  long plane;          // NX*NY
+  long off_x, off_y, off_z, off_p;  // component offsets inside a dvec
+  long ntot;           // padded dvec length
+  long ncl;            // owned cells = nzl*plane
+  long ncv;            // cvec length = (nzl+2)*plane
+  int nblk;            // blocks of 256 owned cells (canonical reduction granularity)
+};
+
+// Physics needed by device code: Param::Krw/Kro [REF src/param.cpp:195-215], MU_W/MU_O
+// [REF config.hpp.in:37,43].
+struct Phys {
+  int two_phase;
+  double Sor, Swc, mu_w, mu_o;
+};
+
+#if defined(__CUDACC__)
+#define IMPES_HD __host__ __device__ __forceinline__
+#else
+#define IMPES_HD inline
+#endif
+
+IMPES_HD long ix_ux(const Lay& L, int i, int j, int kl) { return L.off_x + i + (long)(L.NX + 1) * (j + (long)L.NY * kl); }
+IMPES_HD long ix_uy(const Lay& L, int i, int j, int kl) { return L.off_y + i + (long)L.NX * (j + (long)(L.NY + 1) * kl); }
+// kk = (face plane) - zlo + 1
+IMPES_HD long ix_uz(const Lay& L, int i, int j, int kk) { return L.off_z + i + (long)L.NX * (j + (long)L.NY * kk); }
+// kk = (cell plane) - zlo + 1
+IMPES_HD long ix_p(const Lay& L, int i, int j, int kk) { return L.off_p + i + (long)L.NX * (j + (long)L.NY * kk); }
+IMPES_HD long ix_c(const Lay& L, int i, int j, int kk) { return i + (long)L.NX * (j + (long)L.NY * kk); }
+
+// MINRES scalar recurrence state, device resident (double buffered by iteration parity).
+struct MinresState {
+  double beta, eta, gamma0, gamma1, sigma0, sigma1, norm_goal, eta0;
+  int it;     // iterations completed
+  int done;   // 0 running, 1 converged, 2 hit maxiter
+};
+
+}  // namespace impes
