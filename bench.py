@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- IMPES cell-steps/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+A "step" is one global IMPES step of the reference's loop [REF src/run_serial.cpp:109-143]:
+one PressureSolver call (mixed-Darcy MINRES solve, saturation frozen) followed by one
+SaturationSolver call (dt_global/dt_local = 100 explicit upwind sub-steps, velocity frozen).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C1..C4|nxXnyXnz]
+
+Workload by GPU count (BASELINE.json configs):  N=1 -> C2 (2-D 512x512 log-normal, RT0/P0);
+N=2,4 -> C3 (3-D 128x128x32 extruded log-normal); N=8 -> C4 (60x220x85, SPE10-shaped).  The mesh is cut
+into slabs, one per GPU (strong scaling of one fixed mesh per N).
+
+value  = n_cells * K / (device time of K steps, state resident in HBM), max over ranks.
+e2e    = the same through the drop-in C ABI with HOST (pinned) buffers: every step uploads S, downloads
+         x = [V|P], uploads V and S, downloads S -- exactly what the reference-signature adapter does.
+roofline = K1 (matrix-free Darcy block apply, the Krylov matvec) timed alone with CUDA events on a
+         streaming-size mesh (>= 4x L2, L2 flushed before every launch), algorithmic bytes / time against
+         the measured HBM peak of MEASURED_PEAKS.json.  The benchmark meshes C1-C4 are L2-resident
+         (SURVEY 8d), so their steps are latency-bound and say nothing about HBM; `step_breakdown`
+         reports where the step time goes on the benchmark mesh itself.
+cpu_baseline = the CPU oracle (restatement of the reference's algorithm: MFEM/HYPRE cannot be built in
+         this image) timed on the host cores on one step of the same workload.
+--impl reference = that same oracle as the whole "reference arm" (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_oracle, load_package  # noqa: E402
+
+DT_GLOBAL, DT_LOCAL = 100.0, 1.0
+NAMES = ["darcy_apply", "minres_update", "schur_prec", "sat_substep", "coeff", "dot", "misc", "comm"]
+
+
+def parse_workload(name, gpus):
+    pkg = load_package()
+    from incompressible_flow_b200 import workloads
+    if name is None:
+        name = {1: "C2", 2: "C3", 4: "C3", 8: "C4"}.get(gpus, "C3")
+    if name in workloads.CONFIGS:
+        c = dict(workloads.CONFIGS[name])
+        if c.get("order", 0) != 0:
+            raise SystemExit(f"workload {name} (RT1/Q1) is not implemented yet")
+        return name, c
+    dims = [int(v) for v in name.lower().split("x")]
+    c = dict(dim=len(dims), nx=dims[0], ny=dims[1], K="lognormal", sigma=1.0, note="custom " + name)
+    if len(dims) == 3:
+        c["nz"] = dims[2]
+    return name, c
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.p, self.lines = dev, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.dev)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.p.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_step(orc, built, threads, steps, warmup):
+    """Time the CPU oracle on `steps` IMPES steps after `warmup` (each a full step of the workload)."""
+    d, Kx, Ky, Kz, phi = built
+    o = orc.Oracle(d, Kx, Ky, Kz, phi)
+    o.set_threads(threads)
+    n = o.n_cells
+    S = np.zeros(n)
+    its, times = [], []
+    for ti in range(warmup + steps):
+        t0 = time.perf_counter()
+        x, st, rc = o.pressure_solve(S)
+        S, nsub = o.saturation_advance(x[:o.nv], S, DT_GLOBAL, DT_LOCAL)
+        dt = time.perf_counter() - t0
+        if ti >= warmup:
+            its.append(int(st.iterations))
+            times.append(dt)
+    o.close()
+    return n, its, times
+
+
+def run_reference(args, wname, cfg):
+    """Reference arm: the CPU restatement of the reference's algorithm on all host threads (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    load_package()
+    from incompressible_flow_b200 import workloads
+    orc = load_oracle()
+    built = workloads.build(**cfg)
+    threads = max(1, min(orc.lib().orc_max_threads(), os.cpu_count() or 1))
+    n, its, times = oracle_step(orc, built, threads, args.steps, args.warmup)
+    tot = sum(times)
+    value = n * args.steps / tot
+    line = {
+        "impl": "reference", "metric": "IMPES cell-steps/s", "value": value, "unit": "cell-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wname, **{k: v for k, v in cfg.items() if k != "note"}, "substeps_per_step": 100,
+                   "schur_prec": "sgs_lex (serial reference)", "minres_iters_per_step": its},
+        "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full IMPES steps of {wname} after {args.warmup} warm-up steps; "
+                                   "CPU restatement of the reference algorithm (MFEM/HYPRE unavailable in this image), "
+                                   "OpenMP in SpMV/vector ops, Gauss-Seidel sequential"},
+        "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--roofline-size", default="384x384x384", help="streaming mesh for the K1/K6 roofline (>= 4x L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    wname, cfg = parse_workload(args.workload, args.gpus)
+    if args.impl == "reference":
+        return run_reference(args, wname, cfg)
+    if args.warmup < 3:
+        print(f"note: --warmup {args.warmup} < 3 violates the timing rules; use >= 3 for reportable numbers", file=sys.stderr)
+
+    import torch
+    import torch.distributed as dist
+    pkg = load_package()
+    from incompressible_flow_b200 import abi, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the IMPES hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    d, Kx, Ky, Kz, phi = workloads.build(**cfg)
+    d.rank, d.world_size, d.device = rank, world, local
+    n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
+    s = pkg.Solver(d, Kx, Ky, Kz, phi)
+    if world > 1:
+        uid = [s.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        s.comm_init(uid[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: state resident in HBM --------------------------------------------------
+    s.set_field(abi.FIELD_SATURATION, np.zeros(n))
+    its = []
+
+    def step(ti):
+        _, st = s.pressure_solve(None, want_x=False)
+        s.saturation_advance(None, None, ti, DT_GLOBAL, DT_LOCAL)
+        return int(st.iterations)
+
+    for ti in range(args.warmup):
+        step(ti + 1)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = s.launch_count()
+    s.event_record(0)
+    for ti in range(args.steps):
+        its.append(step(args.warmup + ti + 1))
+    s.event_record(1)
+    ms = s.event_elapsed_ms(0, 1)
+    barrier()
+    launches = s.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    value = n * args.steps / (ms * 1e-3)
+
+    # ---------------- e2e: host buffers through the drop-in C ABI ----------------------------------
+    S_host = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    x_host = torch.empty(s.nv + s.np_, dtype=torch.float64).pin_memory().numpy()
+    S_host[:] = s.get_field(abi.FIELD_SATURATION)
+    lo, hi = s.dims.slab_lo, s.dims.slab_hi
+    nslab = d.nz if d.dim == 3 else d.ny
+    plane = n // nslab
+
+    def gather(a, owned):
+        """All ranks end up with the full host array (the reference's V.Distribute / rank-wide copies
+        [REF src/run_parallel.cpp:186]): zero what this rank does not own, sum over ranks."""
+        if world == 1:
+            return
+        m = np.zeros(a.shape[0], dtype=bool)
+        for a0, a1 in owned:
+            m[a0:a1] = True
+        a[~m] = 0.0
+        t = torch.from_numpy(a).cuda()
+        dist.all_reduce(t)
+        a[:] = t.cpu().numpy()
+
+    nvx = int(s.dims.n_v_comp[0])
+    nvy = int(s.dims.n_v_comp[1]) if d.dim == 3 else 0
+    px = (d.nx + 1) * (d.ny if d.dim == 3 else 1)
+    py = d.nx * (d.ny + 1) if d.dim == 3 else 0
+    top = 1 if hi == nslab else 0
+    own_x = [(px * lo, px * hi), (nvx + py * lo, nvx + py * hi), (nvx + nvy + plane * lo, nvx + nvy + plane * (hi + top)),
+             (s.nv + plane * lo, s.nv + plane * hi)]
+    own_s = [(plane * lo, plane * hi)]
+    gather(S_host, own_s)
+    e2e_steps = max(1, min(args.steps, 2))
+
+    def e2e_step(ti):
+        s.pressure_solve(S_host, out=x_host)
+        gather(x_host, own_x)
+        s.saturation_advance(x_host[:s.nv], S_host, ti, DT_GLOBAL, DT_LOCAL, inplace=True)
+        gather(S_host, own_s)
+
+    e2e_step(100)  # warm the pinned path
+    barrier()
+    t0 = time.perf_counter()
+    for ti in range(e2e_steps):
+        e2e_step(101 + ti)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if True:
+        e2e = {"value": n * e2e_steps / e2e_s, "unit": "cell-steps/s",
+               "h2d_bytes_per_step": int(8 * (n + s.nv + n)), "d2h_bytes_per_step": int(8 * (s.nv + s.np_ + n)),
+               "steps": e2e_steps, "timing": "host wall clock around synchronous C-ABI calls"}
+
+    # ---------------- step breakdown on the benchmark mesh (profiled, untimed) ---------------------
+    breakdown = None
+    if world == 1:
+        s.profile_enable(True)
+        step(200)
+        pms, pn = s.profile_read()
+        s.profile_enable(False)
+        tot = sum(pms) or 1.0
+        breakdown = {NAMES[i]: {"ms": round(pms[i], 3), "launches": int(pn[i]), "share": round(pms[i] / tot, 4)}
+                     for i in range(8) if pn[i]}
+    s.close()
+
+    # ---------------- roofline: K1 / K6 alone on a streaming-size mesh -----------------------------
+    roofline = roofline_k6 = None
+    peak, peak_src = hbm_peak()
+    if rank == 0 and not args.no_roofline:
+        _, rcfg = parse_workload(args.roofline_size, 1)
+        rd, rKx, rKy, rKz, rphi = workloads.build(**rcfg)
+        rd.device = local
+        rn = rd.nx * rd.ny * (rd.nz if rd.dim == 3 else 1)
+        with pkg.Solver(rd, rKx, rKy, rKz, rphi) as rs:
+            rs.set_field(abi.FIELD_SATURATION, np.full(rn, 0.3))
+            rs.set_field(abi.FIELD_DARCY_X, np.random.default_rng(0).standard_normal(rs.nv + rs.np_))
+            k1_b = (88 if rd.dim == 3 else 64) * rn     # unique fp64 words per cell x 8 B
+            k6_b = (48 if rd.dim == 3 else 40) * rn
+            a1, m1 = rs.time_kernel(abi.KERNEL_DARCY_APPLY, 20, True)
+            a6, m6 = rs.time_kernel(abi.KERNEL_SAT_SUBSTEP, 20, True)
+        roofline = {"kernel": "k_darcy_apply<DOT> (K1, Krylov matvec + fused <u,Au>)", "bound": "hbm",
+                    "achieved": k1_b / (a1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": k1_b / (a1 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "mesh": args.roofline_size, "bytes_per_launch": k1_b, "us_per_launch": a1 * 1e3,
+                    "l2": "flushed before every timed launch"}
+        roofline_k6 = {"kernel": "k_sat_substep (K6, fused upwind flux + fractional flow + update)", "bound": "hbm",
+                       "achieved": k6_b / (a6 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": k6_b / (a6 * 1e-3) / 1e9 / peak, "traffic": None, "mesh": args.roofline_size,
+                       "bytes_per_launch": k6_b, "us_per_launch": a6 * 1e3}
+
+    # ---------------- CPU baseline beside it -------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc = load_oracle()
+        threads = max(1, min(orc.lib().orc_max_threads(), os.cpu_count() or 1))
+        built = workloads.build(**cfg)
+        cn, cits, ctimes = oracle_step(orc, built, threads, 1, 0)
+        cpu = {"value": cn / ctimes[0], "unit": "cell-steps/s", "cores": threads, "kind": "port",
+               "sample": f"1 full IMPES step (step 1, S=0) of {wname}: {cits[0]} MINRES iterations + 100 sub-steps, "
+                         f"{ctimes[0]:.1f} s; CPU restatement of the reference algorithm (MFEM/HYPRE unavailable)"}
+
+    if rank == 0:
+        line = {
+            "metric": "IMPES cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, **{k: v for k, v in cfg.items() if k != "note"},
+                       "spaces": "RT0/P0/P0", "two_phase": True, "substeps_per_step": 100,
+                       "schur_prec": "sgs_lex (parity mode: exact lexicographic symmetric Gauss-Seidel)",
+                       "minres_rtol": d.darcy_rtol, "minres_iters_per_step": its,
+                       "partition": f"{world} slab(s) along the slowest axis",
+                       "l2_policy": "step working set < L2 by construction of the BASELINE meshes; every step streams "
+                                    "fresh Krylov vectors; the roofline kernels run on a >=4xL2 mesh with L2 flushed"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "roofline_k6": roofline_k6, "step_breakdown": breakdown, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

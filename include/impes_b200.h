@@ -221,6 +221,10 @@ int  impes_get_rhs(impes_handle h, double* rhs_host);
  * per-launch duration. */
 int  impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2,
                        double* ms_avg, double* ms_min);
+/* CUDA events on the handle's stream (torch.cuda.Event cannot see it): record slot 0..7, then read
+ * the elapsed device milliseconds between two recorded slots (synchronises on the later one). */
+int  impes_event_record(impes_handle h, int slot);
+int  impes_event_elapsed_ms(impes_handle h, int slot_from, int slot_to, double* ms);
 /* Number of kernels this handle has launched since creation. */
 int64_t impes_launch_count(impes_handle h);
 /* Device-side milliseconds spent per kernel class since the last reset when

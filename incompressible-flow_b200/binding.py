@@ -21,7 +21,7 @@ EXPORTS = [
     "impes_get_dims", "impes_comm_unique_id", "impes_comm_init", "impes_pressure_solve",
     "impes_saturation_advance", "impes_guards", "impes_set_field", "impes_get_field",
     "impes_update_coefficients", "impes_darcy_apply", "impes_prec_apply", "impes_get_rhs",
-    "impes_time_kernel", "impes_launch_count", "impes_profile_enable", "impes_profile_read",
+    "impes_time_kernel", "impes_event_record", "impes_event_elapsed_ms", "impes_launch_count", "impes_profile_enable", "impes_profile_read",
 ]
 
 
@@ -74,6 +74,8 @@ def load_library():
     L.impes_prec_apply.argtypes = [H, _dp, _dp]
     L.impes_get_rhs.argtypes = [H, _dp]
     L.impes_time_kernel.argtypes = [H, C.c_int, C.c_int, C.c_int, _dp, _dp]
+    L.impes_event_record.argtypes = [H, C.c_int]
+    L.impes_event_elapsed_ms.argtypes = [H, C.c_int, C.c_int, _dp]
     L.impes_launch_count.restype = C.c_int64
     L.impes_launch_count.argtypes = [H]
     L.impes_profile_enable.argtypes = [H, C.c_int]
@@ -210,6 +212,14 @@ class Solver:
         m = C.c_double(0)
         self._chk(self.L.impes_time_kernel(self.h, kernel, reps, int(flush_l2), C.byref(a), C.byref(m)))
         return a.value, m.value
+
+    def event_record(self, slot):
+        self._chk(self.L.impes_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double(0)
+        self._chk(self.L.impes_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return int(self.L.impes_launch_count(self.h))

@@ -64,6 +64,7 @@ struct impes_ctx {
   bool coeff_valid = false;
   // launch geometry
   int grid_cells = 0, grid_vec = 0, grid_sgs = 0, num_sms = 0;
+  int sgs_mode = 2, sgs_threads = 256;  // 0 one CTA, 1 cluster, 2 cooperative grid
   // graphs
   bool use_graph = true;
   cudaGraphExec_t minres_exec = nullptr;
@@ -77,6 +78,7 @@ struct impes_ctx {
   double prof_ms[KC_N] = {0};
   long long prof_n[KC_N] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
 };
 
@@ -282,8 +284,25 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
   Lay L = h->L;
   const double* T = h->T;
   const double* Md = h->Md;
-  void* args[] = {(void*)&L, (void*)&T, (void*)&Md, (void*)&r, (void*)&y, (void*)&fwd, (void*)&bwd, (void*)&st};
-  CK(cudaLaunchCooperativeKernel((void*)k_sgs_wavefront, dim3(h->grid_sgs), dim3(BLK), args, 0, h->stream));
+  if (h->sgs_mode == 2) {
+    void* args[] = {(void*)&L, (void*)&T, (void*)&Md, (void*)&r, (void*)&y, (void*)&fwd, (void*)&bwd, (void*)&st};
+    CK(cudaLaunchCooperativeKernel((void*)k_sgs_wavefront<2>, dim3(h->grid_sgs), dim3(h->sgs_threads), args, 0, h->stream));
+  } else if (h->sgs_mode == 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->grid_sgs);
+    cfg.blockDim = dim3(h->sgs_threads);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = h->grid_sgs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_sgs_wavefront<1>, L, T, Md, r, y, fwd, bwd, st));
+  } else {
+    k_sgs_wavefront<0><<<1, h->sgs_threads, 0, h->stream>>>(L, T, Md, r, y, fwd, bwd, st);
+  }
   return 0;
 }
 
@@ -411,7 +430,7 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
     if (hs.done) break;
     if (h->d.darcy_print_level == 1 && h->L.rank == 0)
       printf("MINRES: iteration %3d: ||r||_B = %g\n", hs.it, fabs(hs.eta));
-    if (h->minres_exec) {
+    if (h->minres_exec && !h->profiling) {
       CK(cudaGraphLaunch(h->minres_exec, h->stream));
       const long long per_iter = 5;
       h->launches += per_iter * h->graph_iters;
@@ -609,6 +628,8 @@ API void impes_destroy(impes_handle h) {
   if (h->ticket) cudaFree(h->ticket);
   if (h->st) cudaFree(h->st);
   if (h->guard) cudaFree(h->guard);
+  for (cudaEvent_t e : h->user_ev)
+    if (e) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -685,11 +706,28 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
 
   h->grid_cells = L.nblk;
   h->grid_vec = (int)std::min<long>((L.ntot + BLK - 1) / BLK, (long)h->num_sms * 8);
-  {
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_wavefront, BLK, 0));
-    const long want = ((long)L.NY * L.nzl + BLK - 1) / BLK;
-    h->grid_sgs = (int)std::max<long>(1, std::min<long>(want, (long)per_sm * h->num_sms));
+  {  // Schur sweep launch shape: the fewest SMs whose barrier is cheap enough
+    const long npair = (long)L.NY * L.nzl;
+    int mode = npair <= 1024 ? 0 : 1;
+    if (const char* e = getenv("IMPES_SGS_MODE")) mode = atoi(e);
+    h->sgs_mode = mode;
+    if (mode == 0) {
+      h->grid_sgs = 1;
+      h->sgs_threads = (int)std::min<long>(1024, (npair + 31) / 32 * 32);
+    } else if (mode == 1) {
+      int csz = 8;
+      if (const char* e = getenv("IMPES_SGS_CLUSTER")) csz = atoi(e);
+      if (csz > 8) CK(cudaFuncSetAttribute(k_sgs_wavefront<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      h->grid_sgs = csz;
+      const long per = (npair + csz - 1) / csz;
+      h->sgs_threads = (int)std::min<long>(1024, std::max<long>(32, (per + 31) / 32 * 32));
+    } else {
+      int per_sm = 0;
+      h->sgs_threads = 256;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_wavefront<2>, 256, 0));
+      const long want = (npair + 255) / 256;
+      h->grid_sgs = (int)std::max<long>(1, std::min<long>(want, (long)per_sm * h->num_sms));
+    }
   }
 
   // device arrays
@@ -991,6 +1029,24 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
   CK(cudaGetLastError());
   if (ms_avg) *ms_avg = sum / reps;
   if (ms_min) *ms_min = mn;
+  return 0;
+}
+
+API int impes_event_record(impes_handle h, int slot) {
+  RET_IF(check_handle(h));
+  if (slot < 0 || slot >= 8) return IMPES_ERR_BAD_ARG;
+  if (!h->user_ev[slot]) CK(cudaEventCreate(&h->user_ev[slot]));
+  CK(cudaEventRecord(h->user_ev[slot], h->stream));
+  return 0;
+}
+
+API int impes_event_elapsed_ms(impes_handle h, int a, int b, double* ms) {
+  RET_IF(check_handle(h));
+  if (a < 0 || a >= 8 || b < 0 || b >= 8 || !h->user_ev[a] || !h->user_ev[b] || !ms) return IMPES_ERR_BAD_ARG;
+  CK(cudaEventSynchronize(h->user_ev[b]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, h->user_ev[a], h->user_ev[b]));
+  *ms = f;
   return 0;
 }
 

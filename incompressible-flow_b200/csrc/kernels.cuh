@@ -411,14 +411,24 @@ __global__ void __launch_bounds__(BLK) k_jacobi_u(long n_u, const double* __rest
 // identical dependency order, hence identical arithmetic, to the sequential sweep.
 // Cooperative launch; one grid.sync per hyperplane.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLK) k_sgs_wavefront(Lay L, const double* __restrict__ T, const double* __restrict__ Md,
-                                                       const double* __restrict__ r, double* y, int do_fwd, int do_bwd,
-                                                       const MinresState* st) {
+// MODE 0: one CTA, __syncthreads per hyperplane;  MODE 1: one thread-block cluster, hardware
+// cluster barrier per hyperplane;  MODE 2: whole grid (cooperative launch), grid.sync per hyperplane.
+template <int MODE>
+__device__ __forceinline__ void wave_sync(cg::grid_group& grid) {
+  if (MODE == 0) __syncthreads();
+  else if (MODE == 1) cg::this_cluster().sync();
+  else grid.sync();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_sgs_wavefront(Lay L, const double* __restrict__ T,
+                                                        const double* __restrict__ Md, const double* __restrict__ r,
+                                                        double* y, int do_fwd, int do_bwd, const MinresState* st) {
   if (st && st->done) return;
   cg::grid_group grid = cg::this_grid();
   const int nstage = L.NX + L.NY + L.nzl - 2;
   const long npair = (long)L.NY * L.nzl;
-  const long tid = (long)blockIdx.x * BLK + threadIdx.x, nth = (long)gridDim.x * BLK;
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
   const double* D = Md + L.off_p;
   const double* rp = r + L.off_p;
   double* yp = y + L.off_p;
@@ -431,12 +441,12 @@ __global__ void __launch_bounds__(BLK) k_sgs_wavefront(Lay L, const double* __re
         const int kk = kl + 1, k = kl + L.zlo;
         const long c = ix_c(L, i, j, kk);
         double sum = 0.0;
-        if (k > 0) sum += __ldcg(yp + c - L.plane) * (-T[ix_uz(L, i, j, kk)]);
-        if (L.has_y && j > 0) sum += __ldcg(yp + c - L.NX) * (-T[ix_uy(L, i, j, kl)]);
-        if (i > 0) sum += __ldcg(yp + c - 1) * (-T[ix_ux(L, i, j, kl)]);
+        if (k > 0) sum += yp[c - L.plane] * (-T[ix_uz(L, i, j, kk)]);
+        if (L.has_y && j > 0) sum += yp[c - L.NX] * (-T[ix_uy(L, i, j, kl)]);
+        if (i > 0) sum += yp[c - 1] * (-T[ix_ux(L, i, j, kl)]);
         yp[c] = (rp[c] - sum) / D[c];
       }
-      grid.sync();
+      wave_sync<MODE>(grid);
     }
   }
   if (do_bwd) {
@@ -448,15 +458,15 @@ __global__ void __launch_bounds__(BLK) k_sgs_wavefront(Lay L, const double* __re
         const int kk = kl + 1, k = kl + L.zlo;
         const long c = ix_c(L, i, j, kk);
         double sum = 0.0;
-        if (k > 0) sum += __ldcg(yp + c - L.plane) * (-T[ix_uz(L, i, j, kk)]);
-        if (L.has_y && j > 0) sum += __ldcg(yp + c - L.NX) * (-T[ix_uy(L, i, j, kl)]);
-        if (i > 0) sum += __ldcg(yp + c - 1) * (-T[ix_ux(L, i, j, kl)]);
-        if (i + 1 < L.NX) sum += __ldcg(yp + c + 1) * (-T[ix_ux(L, i + 1, j, kl)]);
-        if (L.has_y && j + 1 < L.NY) sum += __ldcg(yp + c + L.NX) * (-T[ix_uy(L, i, j + 1, kl)]);
-        if (k + 1 < L.NZ) sum += __ldcg(yp + c + L.plane) * (-T[ix_uz(L, i, j, kk + 1)]);
+        if (k > 0) sum += yp[c - L.plane] * (-T[ix_uz(L, i, j, kk)]);
+        if (L.has_y && j > 0) sum += yp[c - L.NX] * (-T[ix_uy(L, i, j, kl)]);
+        if (i > 0) sum += yp[c - 1] * (-T[ix_ux(L, i, j, kl)]);
+        if (i + 1 < L.NX) sum += yp[c + 1] * (-T[ix_ux(L, i + 1, j, kl)]);
+        if (L.has_y && j + 1 < L.NY) sum += yp[c + L.NX] * (-T[ix_uy(L, i, j + 1, kl)]);
+        if (k + 1 < L.NZ) sum += yp[c + L.plane] * (-T[ix_uz(L, i, j, kk + 1)]);
         yp[c] = (rp[c] - sum) / D[c];
       }
-      if (d > 0) grid.sync();
+      if (d > 0) wave_sync<MODE>(grid);
     }
   }
 }
