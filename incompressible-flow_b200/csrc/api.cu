@@ -65,6 +65,13 @@ struct impes_ctx {
   // launch geometry
   int grid_cells = 0, grid_vec = 0, grid_sgs = 0, num_sms = 0;
   int sgs_mode = 2, sgs_threads = 256;  // 0 one CTA, 1 cluster, 2 cooperative grid
+  bool sgs_skew = false;                // stage-major (skewed) sweep available for this shape
+  int sgs_ppt = 1;
+  bool sgs_tma = false;                 // one-CTA TMA ring version (<= 1024 pencils)
+  int sgs_ns = 0;
+  size_t sgs_smem = 0;
+  SgsPack pack = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+  double* pack_blk = nullptr;
   // graphs
   bool use_graph = true;
   cudaGraphExec_t minres_exec = nullptr;
@@ -257,6 +264,10 @@ int update_coeff(impes_ctx* h) {
                                            h->geo[2], h->m[0], h->m[1], h->m[2]);
     k_face_coeff<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->m[0], h->m[1], h->m[2], h->Md, h->T);
   }
+  if (h->sgs_skew) {
+    Scope sc(h, KC_COEFF, 1);
+    k_sgs_pack<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, h->T, h->Md);
+  }
   CK(cudaGetLastError());
   h->coeff_valid = true;
   return 0;
@@ -279,11 +290,44 @@ int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState*
 }
 
 // ---- K3: Schur block --------------------------------------------------------------------------
+template <int MODE>
+int launch_skew_sweep(impes_ctx* h, double* y, int fwd, int bwd, const MinresState* st) {
+  const Lay& L = h->L;
+  const double* T = h->T;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(h->grid_sgs);
+  cfg.blockDim = dim3(h->sgs_threads);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = h->grid_sgs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = MODE == 1 ? 1 : 0;
+  switch (h->sgs_ppt) {
+    case 1: CK(cudaLaunchKernelEx(&cfg, k_sgs_skew<MODE, 1>, L, h->pack, T, y, fwd, bwd, st)); break;
+    case 2: CK(cudaLaunchKernelEx(&cfg, k_sgs_skew<MODE, 2>, L, h->pack, T, y, fwd, bwd, st)); break;
+    default: CK(cudaLaunchKernelEx(&cfg, k_sgs_skew<MODE, 4>, L, h->pack, T, y, fwd, bwd, st)); break;
+  }
+  return 0;
+}
+
 int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const MinresState* st) {
-  Scope sc(h, KC_PREC, 1);
   Lay L = h->L;
   const double* T = h->T;
   const double* Md = h->Md;
+  if (h->sgs_skew) {
+    Scope sc(h, KC_PREC, 2 + (fwd ? 1 : 0));
+    if (fwd) k_sgs_skew_in<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, r, st);
+    if (h->sgs_tma)
+      k_sgs_tma<<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(L, h->pack, T, y, h->sgs_ns, fwd, bwd, st);
+    else if (h->sgs_mode == 0) RET_IF(launch_skew_sweep<0>(h, y, fwd, bwd, st));
+    else RET_IF(launch_skew_sweep<1>(h, y, fwd, bwd, st));
+    k_sgs_skew_out<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, bwd, y, st);
+    return 0;
+  }
+  Scope sc(h, KC_PREC, 1);
   if (h->sgs_mode == 2) {
     void* args[] = {(void*)&L, (void*)&T, (void*)&Md, (void*)&r, (void*)&y, (void*)&fwd, (void*)&bwd, (void*)&st};
     CK(cudaLaunchCooperativeKernel((void*)k_sgs_wavefront<2>, dim3(h->grid_sgs), dim3(h->sgs_threads), args, 0, h->stream));
@@ -432,11 +476,11 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
       printf("MINRES: iteration %3d: ||r||_B = %g\n", hs.it, fabs(hs.eta));
     if (h->minres_exec && !h->profiling) {
       CK(cudaGraphLaunch(h->minres_exec, h->stream));
-      const long long per_iter = 5;
+      const long long per_iter = h->sgs_skew ? 7 : 5;
       h->launches += per_iter * h->graph_iters;
       h->prof_n[KC_DARCY] += h->graph_iters;
       h->prof_n[KC_MINRES] += 2 * h->graph_iters;
-      h->prof_n[KC_PREC] += h->graph_iters;
+      h->prof_n[KC_PREC] += (h->sgs_skew ? 3 : 1) * h->graph_iters;
       h->prof_n[KC_DOT] += h->graph_iters;
     } else {
       for (int p = 0; p < 4; ++p) RET_IF(minres_pair(h));
@@ -622,7 +666,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   if (h->ticket) cudaFree(h->ticket);
@@ -708,25 +752,70 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   h->grid_vec = (int)std::min<long>((L.ntot + BLK - 1) / BLK, (long)h->num_sms * 8);
   {  // Schur sweep launch shape: the fewest SMs whose barrier is cheap enough
     const long npair = (long)L.NY * L.nzl;
-    int mode = npair <= 1024 ? 0 : 1;
+    int csz = 8;
+    if (const char* e = getenv("IMPES_SGS_CLUSTER")) csz = std::max(1, std::min(16, atoi(e)));
+    bool skew = true;
+    if (const char* e = getenv("IMPES_SGS_SKEW")) skew = atoi(e) != 0;
+    int mode = npair <= 4 * SGS_T ? 0 : 1;
     if (const char* e = getenv("IMPES_SGS_MODE")) mode = atoi(e);
-    h->sgs_mode = mode;
-    if (mode == 0) {
-      h->grid_sgs = 1;
-      h->sgs_threads = (int)std::min<long>(1024, (npair + 31) / 32 * 32);
-    } else if (mode == 1) {
-      int csz = 8;
-      if (const char* e = getenv("IMPES_SGS_CLUSTER")) csz = atoi(e);
-      if (csz > 8) CK(cudaFuncSetAttribute(k_sgs_wavefront<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      h->grid_sgs = csz;
-      const long per = (npair + csz - 1) / csz;
-      h->sgs_threads = (int)std::min<long>(1024, std::max<long>(32, (per + 31) / 32 * 32));
+    const long nstage = (long)L.NX + L.NY + L.nzl - 2;
+    const long cap = (long)(mode == 0 ? 1 : csz) * SGS_T * 4;
+    if (skew && mode != 2 && npair <= cap && nstage * ((npair + 31) / 32 * 32) * 6 < (1L << 33)) {
+      h->sgs_skew = true;
+      h->sgs_mode = mode;
+      h->grid_sgs = mode == 0 ? 1 : csz;
+      const long per_cta = (npair + h->grid_sgs - 1) / h->grid_sgs;
+      h->sgs_ppt = per_cta <= SGS_T ? 1 : (per_cta <= 2 * SGS_T ? 2 : 4);
+      const long thr = (per_cta + h->sgs_ppt - 1) / h->sgs_ppt;
+      h->sgs_threads = (int)std::min<long>(SGS_T, std::max<long>(32, (thr + 31) / 32 * 32));
+      if (mode == 1 && csz > 8) {
+        CK(cudaFuncSetAttribute(k_sgs_skew<1, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CK(cudaFuncSetAttribute(k_sgs_skew<1, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CK(cudaFuncSetAttribute(k_sgs_skew<1, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      }
+      h->pack.NPs = (int)((npair + 31) / 32 * 32);
+      h->pack.SS = 6 * h->pack.NPs;
+      bool tma = mode == 0 && h->pack.NPs + 32 <= 1024;
+      if (const char* e = getenv("IMPES_SGS_TMA")) tma = tma && atoi(e) != 0;
+      if (tma) {
+        const size_t row = (size_t)h->pack.NPs * 8;
+        int ns = (int)((200 * 1024 - 2 * row) / (6 * row));
+        ns = std::min(ns, 8);
+        if (ns >= 4) {
+          h->sgs_tma = true;
+          h->sgs_ns = ns;
+          h->sgs_smem = (size_t)(ns * 6 + 2) * row + (size_t)ns * 8;
+          h->sgs_threads = h->pack.NPs + 32;
+          h->sgs_ppt = 1;
+          CK(cudaFuncSetAttribute(k_sgs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sgs_smem));
+        }
+      }
+      RET_IF(dev_alloc(h, &h->pack_blk, nstage * h->pack.SS));
+      RET_IF(dev_alloc(h, &h->pack.Yb, nstage * h->pack.NPs));
+      h->pack.Rs = h->pack_blk;
+      h->pack.D = h->pack_blk + 1L * h->pack.NPs;
+      h->pack.nTx = h->pack_blk + 2L * h->pack.NPs;
+      h->pack.nTz = h->pack_blk + 3L * h->pack.NPs;
+      h->pack.Yf = h->pack_blk + 4L * h->pack.NPs;
+      h->pack.nTy = h->pack_blk + 5L * h->pack.NPs;
     } else {
-      int per_sm = 0;
-      h->sgs_threads = 256;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_wavefront<2>, 256, 0));
-      const long want = (npair + 255) / 256;
-      h->grid_sgs = (int)std::max<long>(1, std::min<long>(want, (long)per_sm * h->num_sms));
+      if (mode == 0 && npair > 1024) mode = 1;
+      h->sgs_mode = mode;
+      if (mode == 0) {
+        h->grid_sgs = 1;
+        h->sgs_threads = (int)std::min<long>(1024, (npair + 31) / 32 * 32);
+      } else if (mode == 1) {
+        if (csz > 8) CK(cudaFuncSetAttribute(k_sgs_wavefront<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        h->grid_sgs = csz;
+        const long per = (npair + csz - 1) / csz;
+        h->sgs_threads = (int)std::min<long>(1024, std::max<long>(32, (per + 31) / 32 * 32));
+      } else {
+        int per_sm = 0;
+        h->sgs_threads = 256;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_wavefront<2>, 256, 0));
+        const long want = (npair + 255) / 256;
+        h->grid_sgs = (int)std::max<long>(1, std::min<long>(want, (long)per_sm * h->num_sms));
+      }
     }
   }
 

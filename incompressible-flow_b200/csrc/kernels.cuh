@@ -472,6 +472,313 @@ __global__ void __launch_bounds__(1024) k_sgs_wavefront(Lay L, const double* __r
 }
 
 // ---------------------------------------------------------------------------------------
+// K3 (fast path): the same lexicographic symmetric Gauss-Seidel sweep on a SKEWED (stage-major)
+// copy of the Schur stencil.  Pencil p = j + NY*kl runs along x; cell (i, p) sits in stage
+// d = i + j + kl at slot d*NPs + p.  At stage d, thread p touches slot (d, p) and its neighbours
+// (d-1, p), (d-1, p-1), (d-1, p-NY) / (d+1, p), (d+1, p+1), (d+1, p+NY): every access is
+// coalesced across the threads of a stage and known one stage ahead, so it is prefetched into
+// registers before the barrier.  Neighbour y values travel through shared memory (one CTA) or
+// L2 (cluster).  The arithmetic per cell is unchanged, so the result is bit-identical to the
+// sequential sweep.
+// ---------------------------------------------------------------------------------------
+struct SgsPack {
+  // Stage-major block layout: stage d owns one contiguous block of 6 rows of NPs doubles
+  //   row 0 Rs (skewed rhs), 1 D, 2 -Tx_lo, 3 -Tz_lo, 4 Yf (forward result), 5 -Ty_lo (3-D only);
+  // (rows ordered so that a 2-D sweep streams only the first 4 (forward) / 5 (backward) rows)
+  // the pointers below address row r of stage 0, consecutive stages are SS = 6*NPs apart.
+  double *Rs, *D, *nTx, *nTy, *nTz, *Yf;
+  double* Yb;  // backward result, [stage][NPs]
+  int NPs;     // pencils padded to a multiple of 32
+  int SS;      // stage stride of the block layout
+};
+
+__device__ __forceinline__ long skew_blk(const Lay& L, const SgsPack& P, int i, int j, int kl) {
+  return (long)(i + j + kl) * P.SS + (j + L.NY * kl);
+}
+__device__ __forceinline__ long skew_row(const Lay& L, const SgsPack& P, int i, int j, int kl) {
+  return (long)(i + j + kl) * P.NPs + (j + L.NY * kl);
+}
+
+// once per pressure solve: natural -> skewed copy of the stencil
+__global__ void __launch_bounds__(BLK) k_sgs_pack(Lay L, SgsPack P, const double* __restrict__ T,
+                                                  const double* __restrict__ Md) {
+  const CellIdx ci = owned_cell(L);
+  if (!ci.ok) return;
+  const int i = ci.i, j = ci.j, kl = ci.kl, kk = kl + 1;
+  const long s = skew_blk(L, P, i, j, kl);
+  P.D[s] = Md[ix_p(L, i, j, kk)];
+  P.nTx[s] = -T[ix_ux(L, i, j, kl)];
+  P.nTy[s] = L.has_y ? -T[ix_uy(L, i, j, kl)] : 0.0;
+  P.nTz[s] = -T[ix_uz(L, i, j, kk)];
+}
+// per application: r (natural p-part) -> Rs ; Y (skewed) -> y (natural p-part)
+__global__ void __launch_bounds__(BLK) k_sgs_skew_in(Lay L, SgsPack P, const double* __restrict__ r,
+                                                     const MinresState* st) {
+  if (st && st->done) return;
+  const CellIdx ci = owned_cell(L);
+  if (!ci.ok) return;
+  P.Rs[skew_blk(L, P, ci.i, ci.j, ci.kl)] = r[ix_p(L, ci.i, ci.j, ci.kl + 1)];
+}
+__global__ void __launch_bounds__(BLK) k_sgs_skew_out(Lay L, SgsPack P, int from_bwd, double* __restrict__ y,
+                                                      const MinresState* st) {
+  if (st && st->done) return;
+  const CellIdx ci = owned_cell(L);
+  if (!ci.ok) return;
+  y[ix_p(L, ci.i, ci.j, ci.kl + 1)] =
+      from_bwd ? P.Yb[skew_row(L, P, ci.i, ci.j, ci.kl)] : P.Yf[skew_blk(L, P, ci.i, ci.j, ci.kl)];
+}
+
+constexpr int SGS_T = 512;  // threads per CTA of the register-prefetch skewed sweep
+
+// Register-prefetch variant: MODE 0 one CTA (neighbours through shared memory), MODE 1 one cluster
+// (neighbours through L2 after the hardware cluster barrier).  PPT pencils per thread.
+template <int MODE, int PPT>
+__global__ void __launch_bounds__(SGS_T) k_sgs_skew(Lay L, SgsPack P, const double* __restrict__ T, double* y,
+                                                    int do_fwd, int do_bwd, const MinresState* st) {
+  if (st && st->done) return;
+  __shared__ double sh[2][MODE == 0 ? SGS_T * PPT : 1];
+  const int nth = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NP = L.NY * L.nzl, NPs = P.NPs;
+  const long SS = P.SS;
+  const int nstage = L.NX + L.NY + L.nzl - 2;
+  double* yp = y + L.off_p;
+  int pj[PPT], pk[PPT], pp[PPT];
+  bool pv[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; ++s) {
+    pp[s] = tid + s * nth;
+    pv[s] = pp[s] < NP;
+    const int q = pv[s] ? pp[s] : 0;
+    pj[s] = q % L.NY;
+    pk[s] = q / L.NY;
+  }
+  auto sync = [&]() {
+    if (MODE == 0) __syncthreads();
+    else cg::this_cluster().sync();
+  };
+  if (do_fwd) {
+    double R[PPT], D[PPT], nx[PPT], ny[PPT], nz[PPT];
+    auto load = [&](int d) {
+#pragma unroll
+      for (int s = 0; s < PPT; ++s) {
+        const int i = d - pj[s] - pk[s];
+        if (pv[s] && i >= 0 && i < L.NX) {
+          const long o = (long)d * SS + pp[s];
+          R[s] = P.Rs[o]; D[s] = P.D[o]; nx[s] = P.nTx[o]; ny[s] = P.nTy[o]; nz[s] = P.nTz[o];
+        }
+      }
+    };
+    load(0);
+    for (int d = 0; d < nstage; ++d) {
+      const double* prev = P.Yf + (long)(d - 1) * SS;
+#pragma unroll
+      for (int s = 0; s < PPT; ++s) {
+        const int i = d - pj[s] - pk[s];
+        if (pv[s] && i >= 0 && i < L.NX) {
+          const int p = pp[s], k = pk[s] + L.zlo;
+          double sum = 0.0;
+          if (k > 0) {
+            const double yl = pk[s] > 0 ? (MODE == 0 ? sh[(d - 1) & 1][p - L.NY] : __ldcg(prev + p - L.NY))
+                                        : __ldcg(yp + ix_c(L, i, pj[s], 0));
+            sum += yl * nz[s];
+          }
+          if (L.has_y && pj[s] > 0) sum += (MODE == 0 ? sh[(d - 1) & 1][p - 1] : __ldcg(prev + p - 1)) * ny[s];
+          if (i > 0) sum += (MODE == 0 ? sh[(d - 1) & 1][p] : __ldcg(prev + p)) * nx[s];
+          const double v = (R[s] - sum) / D[s];
+          P.Yf[(long)d * SS + p] = v;
+          if (MODE == 0) sh[d & 1][p] = v;
+        }
+      }
+      if (d + 1 < nstage) load(d + 1);
+      sync();
+    }
+  }
+  if (do_bwd) {
+    double R[PPT], D[PPT], nx[PPT], ny[PPT], nz[PPT], hx[PPT], hy[PPT], hz[PPT], fx[PPT], fy[PPT], fz[PPT];
+    auto load = [&](int d) {
+#pragma unroll
+      for (int s = 0; s < PPT; ++s) {
+        const int i = d - pj[s] - pk[s];
+        if (pv[s] && i >= 0 && i < L.NX) {
+          const int p = pp[s], k = pk[s] + L.zlo;
+          const long o = (long)d * SS + p;
+          R[s] = P.Rs[o]; D[s] = P.D[o]; nx[s] = P.nTx[o]; ny[s] = P.nTy[o]; nz[s] = P.nTz[o];
+          const long up = o + SS, lo = o - SS;
+          if (i + 1 < L.NX) hx[s] = P.nTx[up];
+          if (L.has_y && pj[s] + 1 < L.NY) hy[s] = P.nTy[up + 1];
+          if (k + 1 < L.NZ) hz[s] = pk[s] + 1 < L.nzl ? P.nTz[up + L.NY] : -T[ix_uz(L, i, pj[s], pk[s] + 2)];
+          if (i > 0) fx[s] = P.Yf[lo];
+          if (L.has_y && pj[s] > 0) fy[s] = P.Yf[lo - 1];
+          if (k > 0) fz[s] = pk[s] > 0 ? P.Yf[lo - L.NY] : __ldcg(yp + ix_c(L, i, pj[s], 0));
+        }
+      }
+    };
+    load(nstage - 1);
+    for (int d = nstage - 1; d >= 0; --d) {
+      const double* next = P.Yb + (long)(d + 1) * NPs;
+#pragma unroll
+      for (int s = 0; s < PPT; ++s) {
+        const int i = d - pj[s] - pk[s];
+        if (pv[s] && i >= 0 && i < L.NX) {
+          const int p = pp[s], k = pk[s] + L.zlo;
+          double sum = 0.0;
+          if (k > 0) sum += fz[s] * nz[s];
+          if (L.has_y && pj[s] > 0) sum += fy[s] * ny[s];
+          if (i > 0) sum += fx[s] * nx[s];
+          if (i + 1 < L.NX) sum += (MODE == 0 ? sh[(d + 1) & 1][p] : __ldcg(next + p)) * hx[s];
+          if (L.has_y && pj[s] + 1 < L.NY) sum += (MODE == 0 ? sh[(d + 1) & 1][p + 1] : __ldcg(next + p + 1)) * hy[s];
+          if (k + 1 < L.NZ) {
+            const double yu = pk[s] + 1 < L.nzl ? (MODE == 0 ? sh[(d + 1) & 1][p + L.NY] : __ldcg(next + p + L.NY))
+                                                : __ldcg(yp + ix_c(L, i, pj[s], pk[s] + 2));
+            sum += yu * hz[s];
+          }
+          const double v = (R[s] - sum) / D[s];
+          P.Yb[(long)d * NPs + p] = v;
+          if (MODE == 0) sh[d & 1][p] = v;
+        }
+      }
+      if (d > 0) {
+        load(d - 1);
+        sync();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 (TMA path, one CTA): the same skewed sweep with all operands staged by the TMA engine.
+// Stage d's block (6 rows x NPs doubles, contiguous) is brought into a shared-memory ring by ONE
+// cp.async.bulk (mbarrier complete_tx) issued NS-2 stages ahead by a dedicated producer warp, which
+// is also the only waiter on the mbarriers; the compute warps see "slot ready" through the per-stage
+// __syncthreads.  Per-stage critical path of a compute warp: LDS operands + neighbour values,
+// <= 6 mul/add, one division, STS (+ a fire-and-forget coalesced global store), barrier.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// blockDim.x = 32 (producer warp) + NPs (one compute thread per pencil)
+__global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double* __restrict__ T, double* y, int NS,
+                                                  int do_fwd, int do_bwd, const MinresState* st) {
+  if (st && st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int NPs = P.NPs, NP = L.NY * L.nzl;
+  const long SS = P.SS;
+  const int nstage = L.NX + L.NY + L.nzl - 2;
+  double* ring = reinterpret_cast<double*>(smem_raw);                                        // [NS][6][NPs]
+  double* ybuf = ring + (size_t)NS * SS;                                                     // [2][NPs]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ybuf + (size_t)2 * NPs);  // [NS]
+  const bool producer = threadIdx.x < 32;
+  const int p = (int)threadIdx.x - 32;
+  const bool pv = !producer && p < NP;
+  const int pj = pv ? p % L.NY : 0, pk = pv ? p / L.NY : 0;
+  const int k = pk + L.zlo;
+  double* yp = y + L.off_p;
+  const unsigned rowb = (unsigned)NPs * 8u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  int it = 0;  // global iteration counter: ring slot = it % NS, mbarrier parity = (it / NS) & 1
+  for (int dir = 0; dir < 2; ++dir) {
+    if (dir == 0 ? !do_fwd : !do_bwd) continue;
+    const int it0 = it;
+    // stage of phase-local iteration n
+    auto stage_of = [&](int n) { return dir == 0 ? n : nstage - 1 - n; };
+    auto issue = [&](int n) {  // producer lane 0 only
+      const int j = it0 + n;
+      unsigned long long* bar = bars + (j % NS);
+      const unsigned bytes = rowb * (L.has_y ? 6u : (dir == 0 ? 4u : 5u));  // 2-D: skip the unused rows
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(ring + (size_t)(j % NS) * SS, P.Rs + (size_t)stage_of(n) * SS, bytes, bar);
+    };
+    auto wait_full = [&](int n) {
+      const int j = it0 + n;
+      mbar_wait(bars + (j % NS), (unsigned)((j / NS) & 1));
+    };
+    if (dir == 1 && do_fwd) {
+      // forward rows (row 5 of every block) were written with ordinary stores: order them before the
+      // async-proxy reads of the backward pass
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+      for (int n = 0; n < NS - 2 && n < nstage; ++n) issue(n);
+      wait_full(0);
+      if (nstage > 1) wait_full(1);
+    }
+    __syncthreads();
+    for (int n = 0; n < nstage; ++n, ++it) {
+      const int d = stage_of(n);
+      if (producer) {
+        if (threadIdx.x == 0) {
+          // slot of iteration it-2 is free (last read, as upper-face rows, during it-1)
+          if (n + NS - 2 < nstage) issue(n + NS - 2);
+          if (n + 2 < nstage) wait_full(n + 2);
+        }
+      } else {
+        const double* slot = ring + (size_t)(it % NS) * SS;
+        double* ycur = ybuf + (size_t)(it & 1) * NPs;
+        const double* yadj = ybuf + (size_t)((it + 1) & 1) * NPs;  // previous iteration's row
+        const int i = d - pj - pk;
+        if (pv && i >= 0 && i < L.NX) {
+          const double R = slot[p], D = slot[NPs + p], nx = slot[2 * NPs + p], nz = slot[3 * NPs + p];
+          const double ny = L.has_y ? slot[5 * NPs + p] : 0.0;
+          double sum = 0.0;
+          if (dir == 0) {
+            if (k > 0) sum += (pk > 0 ? yadj[p - L.NY] : __ldcg(yp + ix_c(L, i, pj, 0))) * nz;
+            if (L.has_y && pj > 0) sum += yadj[p - 1] * ny;
+            if (i > 0) sum += yadj[p] * nx;
+          } else {
+            const double* F = ring + (size_t)((it + 1) % NS) * SS + 4 * NPs;  // block of stage d-1, row Yf
+            const double* up = ring + (size_t)((it + NS - 1) % NS) * SS;      // block of stage d+1
+            if (k > 0) sum += (pk > 0 ? F[p - L.NY] : __ldcg(yp + ix_c(L, i, pj, 0))) * nz;
+            if (L.has_y && pj > 0) sum += F[p - 1] * ny;
+            if (i > 0) sum += F[p] * nx;
+            if (i + 1 < L.NX) sum += yadj[p] * up[2 * NPs + p];
+            if (L.has_y && pj + 1 < L.NY) sum += yadj[p + 1] * up[5 * NPs + p + 1];
+            if (k + 1 < L.NZ) {
+              if (pk + 1 < L.nzl) sum += yadj[p + L.NY] * up[3 * NPs + p + L.NY];
+              else sum += __ldcg(yp + ix_c(L, i, pj, pk + 2)) * (-T[ix_uz(L, i, pj, pk + 2)]);
+            }
+          }
+          const double v = (R - sum) / D;
+          ycur[p] = v;
+          if (dir == 0) P.Yf[(size_t)d * SS + p] = v;
+          else P.Yb[(size_t)d * NPs + p] = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // K6: one forward-Euler sub-step  S <- S + dt M_phi^-1 (Kt f(S) + b), fused
 //     (FS, Kt.Mult, z += b, M solve, y *= dt, S += y  [REF src/saturation_solver.cpp:76-91]);
 //     P0/RT0 closed form of the DG upwind operator:
