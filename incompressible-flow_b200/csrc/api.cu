@@ -65,12 +65,15 @@ struct impes_ctx {
   // launch geometry
   int grid_cells = 0, grid_vec = 0, grid_sgs = 0, num_sms = 0;
   int sgs_mode = 2, sgs_threads = 256;  // 0 one CTA, 1 cluster, 2 cooperative grid
+  bool sat_simple = false;              // IMPES_SAT_SIMPLE=1: untiled K6 (A/B testing)
+  int sat_tz = 8;                       // planes marched per block in the tiled K6
   bool sgs_skew = false;                // stage-major (skewed) sweep available for this shape
   int sgs_ppt = 1;
   bool sgs_tma = false;                 // one-CTA TMA ring version (<= 1024 pencils)
   int sgs_ns = 0;
   size_t sgs_smem = 0;
-  SgsPack pack = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+  SgsPack pack = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+  int sgs_yp = 0;
   double* pack_blk = nullptr;
   // graphs
   bool use_graph = true;
@@ -313,6 +316,22 @@ int launch_skew_sweep(impes_ctx* h, double* y, int fwd, int bwd, const MinresSta
   return 0;
 }
 
+template <int NPS, bool HY>
+void launch_sgs_tma_t(impes_ctx* h, double* y, int fwd, int bwd, const MinresState* st) {
+  k_sgs_tma<NPS, HY><<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(h->L, h->pack, h->T, y, h->sgs_ns, h->sgs_yp, fwd,
+                                                                    bwd, st);
+}
+void launch_sgs_tma(impes_ctx* h, double* y, int fwd, int bwd, const MinresState* st) {
+  const bool hy = h->L.has_y != 0;
+  switch (h->pack.NPs) {
+    case 64: hy ? launch_sgs_tma_t<64, true>(h, y, fwd, bwd, st) : launch_sgs_tma_t<64, false>(h, y, fwd, bwd, st); break;
+    case 128: hy ? launch_sgs_tma_t<128, true>(h, y, fwd, bwd, st) : launch_sgs_tma_t<128, false>(h, y, fwd, bwd, st); break;
+    case 256: hy ? launch_sgs_tma_t<256, true>(h, y, fwd, bwd, st) : launch_sgs_tma_t<256, false>(h, y, fwd, bwd, st); break;
+    case 512: hy ? launch_sgs_tma_t<512, true>(h, y, fwd, bwd, st) : launch_sgs_tma_t<512, false>(h, y, fwd, bwd, st); break;
+    default: hy ? launch_sgs_tma_t<0, true>(h, y, fwd, bwd, st) : launch_sgs_tma_t<0, false>(h, y, fwd, bwd, st); break;
+  }
+}
+
 int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const MinresState* st) {
   Lay L = h->L;
   const double* T = h->T;
@@ -321,7 +340,7 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
     Scope sc(h, KC_PREC, 2 + (fwd ? 1 : 0));
     if (fwd) k_sgs_skew_in<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, r, st);
     if (h->sgs_tma)
-      k_sgs_tma<<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(L, h->pack, T, y, h->sgs_ns, fwd, bwd, st);
+      launch_sgs_tma(h, y, fwd, bwd, st);
     else if (h->sgs_mode == 0) RET_IF(launch_skew_sweep<0>(h, y, fwd, bwd, st));
     else RET_IF(launch_skew_sweep<1>(h, y, fwd, bwd, st));
     k_sgs_skew_out<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, bwd, y, st);
@@ -522,11 +541,30 @@ int n_substeps(const impes_ctx* h, double global_dt, double dt) {
   return (int)(global_dt / dt);  // [REF src/saturation_solver.cpp:74-75]
 }
 
+// one K6 launch: rate = false: Sout = Sin + dt*F(Sin);  rate = true: Sout = F(Sin)
+int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout) {
+  Scope sc(h, KC_SAT, 1);
+  const Lay& L = h->L;
+  if (h->sat_simple) {
+    if (rate) k_sat_substep<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Sout);
+    else k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Sout);
+    return 0;
+  }
+  if (L.has_y) {
+    dim3 g((L.NX + 31) / 32, (L.NY + 7) / 8, (L.nzl + h->sat_tz - 1) / h->sat_tz);
+    if (rate) k_sat_tile<32, 8, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
+    else k_sat_tile<32, 8, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
+  } else {
+    dim3 g((L.NX + 255) / 256, 1, (L.nzl + h->sat_tz - 1) / h->sat_tz);
+    if (rate) k_sat_tile<256, 1, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
+    else k_sat_tile<256, 1, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
+  }
+  return 0;
+}
+
 int sat_rate(impes_ctx* h, double* Sin, double* out) {  // out = M_phi^-1 (Kt f(Sin) + b)
   RET_IF(exchange_planes(h, Sin, true, true));
-  Scope sc(h, KC_SAT, 1);
-  k_sat_substep<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->ph, h->sp, h->x, h->phi, Sin, out);
-  return 0;
+  return launch_sat(h, true, Sin, out);
 }
 int axpby(impes_ctx* h, double a, const double* x, double b, const double* y, double* out) {
   Scope sc(h, KC_SAT, 1);
@@ -558,10 +596,7 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
     double* Sn = h->S[h->scur ^ 1];
     if (ode == 1) {
       RET_IF(exchange_planes(h, S, true, true));
-      {
-        Scope sc(h, KC_SAT, 1);
-        k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->ph, h->sp, h->x, h->phi, S, Sn);
-      }
+      RET_IF(launch_sat(h, false, S, Sn));
       h->scur ^= 1;
     } else if (ode == 2) {  // RK2Solver(a = 1)
       const double a = 1.0, bb = 0.5 / a;
@@ -760,7 +795,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     if (const char* e = getenv("IMPES_SGS_MODE")) mode = atoi(e);
     const long nstage = (long)L.NX + L.NY + L.nzl - 2;
     const long cap = (long)(mode == 0 ? 1 : csz) * SGS_T * 4;
-    if (skew && mode != 2 && npair <= cap && nstage * ((npair + 31) / 32 * 32) * 6 < (1L << 33)) {
+    if (skew && mode != 2 && npair <= cap && nstage * ((npair + 31) / 32 * 32) * 7 < (1L << 33)) {
       h->sgs_skew = true;
       h->sgs_mode = mode;
       h->grid_sgs = mode == 0 ? 1 : csz;
@@ -774,30 +809,45 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
         CK(cudaFuncSetAttribute(k_sgs_skew<1, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       }
       h->pack.NPs = (int)((npair + 31) / 32 * 32);
-      h->pack.SS = 6 * h->pack.NPs;
+      for (int c : {64, 128, 256, 512})
+        if (npair <= c) { h->pack.NPs = c; break; }
+      h->pack.SS = 7 * h->pack.NPs;
       bool tma = mode == 0 && h->pack.NPs + 32 <= 1024;
       if (const char* e = getenv("IMPES_SGS_TMA")) tma = tma && atoi(e) != 0;
       if (tma) {
         const size_t row = (size_t)h->pack.NPs * 8;
-        int ns = (int)((200 * 1024 - 2 * row) / (6 * row));
+        h->sgs_yp = (L.NY + 1 + 15) / 16 * 16;
+        const size_t ybytes = 2 * (row + 2 * (size_t)h->sgs_yp * 8);
+        int ns = (int)((200 * 1024 - ybytes) / (7 * row));
         ns = std::min(ns, 8);
         if (ns >= 4) {
           h->sgs_tma = true;
           h->sgs_ns = ns;
-          h->sgs_smem = (size_t)(ns * 6 + 2) * row + (size_t)ns * 8;
+          h->sgs_smem = (size_t)ns * 7 * row + ybytes + (size_t)ns * 8;
           h->sgs_threads = h->pack.NPs + 32;
           h->sgs_ppt = 1;
-          CK(cudaFuncSetAttribute(k_sgs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sgs_smem));
+          const int sm = (int)h->sgs_smem;
+          CK(cudaFuncSetAttribute(k_sgs_tma<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+          CK(cudaFuncSetAttribute(k_sgs_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         }
       }
       RET_IF(dev_alloc(h, &h->pack_blk, nstage * h->pack.SS));
       RET_IF(dev_alloc(h, &h->pack.Yb, nstage * h->pack.NPs));
       h->pack.Rs = h->pack_blk;
       h->pack.D = h->pack_blk + 1L * h->pack.NPs;
-      h->pack.nTx = h->pack_blk + 2L * h->pack.NPs;
-      h->pack.nTz = h->pack_blk + 3L * h->pack.NPs;
-      h->pack.Yf = h->pack_blk + 4L * h->pack.NPs;
-      h->pack.nTy = h->pack_blk + 5L * h->pack.NPs;
+      h->pack.rD = h->pack_blk + 2L * h->pack.NPs;
+      h->pack.nTx = h->pack_blk + 3L * h->pack.NPs;
+      h->pack.nTz = h->pack_blk + 4L * h->pack.NPs;
+      h->pack.Yf = h->pack_blk + 5L * h->pack.NPs;
+      h->pack.nTy = h->pack_blk + 6L * h->pack.NPs;
     } else {
       if (mode == 0 && npair > 1024) mode = 1;
       h->sgs_mode = mode;
@@ -819,6 +869,13 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     }
   }
 
+  {  // K6 tiling: enough blocks for >= 2 waves when the mesh allows it
+    if (const char* e = getenv("IMPES_SAT_SIMPLE")) h->sat_simple = atoi(e) != 0;
+    const long tiles = L.has_y ? (long)((L.NX + 31) / 32) * ((L.NY + 7) / 8) : (long)((L.NX + 255) / 256);
+    long tz = (tiles * L.nzl) / (2L * h->num_sms);
+    h->sat_tz = (int)std::max<long>(1, std::min<long>(16, tz));
+    if (const char* e = getenv("IMPES_SAT_TZ")) h->sat_tz = std::max(1, atoi(e));
+  }
   // device arrays
   const double* Kin[3] = {Kx, d.dim == 3 ? Ky : nullptr, d.dim == 3 ? Kz : Ky};
   for (int c = 0; c < 3; ++c) {
@@ -1080,13 +1137,10 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
     CK(cudaEventRecord(e0, h->stream));
     switch (kernel) {
       case IMPES_KERNEL_DARCY_APPLY: RET_IF(darcy_apply(h, h->u1, h->q, true, nullptr)); break;
-      case IMPES_KERNEL_SAT_SUBSTEP: {
-        Scope sc(h, KC_SAT, 1);
+      case IMPES_KERNEL_SAT_SUBSTEP:
         h->sp.dt = 0.0;  // dt = 0: the state is not disturbed by repeated timing launches
-        k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, h->S[h->scur],
-                                                                   h->S[h->scur ^ 1]);
+        RET_IF(launch_sat(h, false, h->S[h->scur], h->S[h->scur ^ 1]));
         break;
-      }
       case IMPES_KERNEL_MINRES_UPDATE: {
         Scope sc(h, KC_MINRES, 2);
         k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, L.off_p, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,

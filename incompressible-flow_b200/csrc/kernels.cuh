@@ -483,10 +483,10 @@ __global__ void __launch_bounds__(1024) k_sgs_wavefront(Lay L, const double* __r
 // ---------------------------------------------------------------------------------------
 struct SgsPack {
   // Stage-major block layout: stage d owns one contiguous block of 6 rows of NPs doubles
-  //   row 0 Rs (skewed rhs), 1 D, 2 -Tx_lo, 3 -Tz_lo, 4 Yf (forward result), 5 -Ty_lo (3-D only);
-  // (rows ordered so that a 2-D sweep streams only the first 4 (forward) / 5 (backward) rows)
-  // the pointers below address row r of stage 0, consecutive stages are SS = 6*NPs apart.
-  double *Rs, *D, *nTx, *nTy, *nTz, *Yf;
+  //   row 0 Rs (skewed rhs), 1 D, 2 rD = RN(1/D), 3 -Tx_lo, 4 -Tz_lo, 5 Yf (forward result), 6 -Ty_lo;
+  // (rows ordered so that a 2-D sweep streams only the first 5 (forward) / 6 (backward) rows)
+  // the pointers below address row r of stage 0, consecutive stages are SS = 7*NPs apart.
+  double *Rs, *D, *rD, *nTx, *nTy, *nTz, *Yf;
   double* Yb;  // backward result, [stage][NPs]
   int NPs;     // pencils padded to a multiple of 32
   int SS;      // stage stride of the block layout
@@ -506,7 +506,9 @@ __global__ void __launch_bounds__(BLK) k_sgs_pack(Lay L, SgsPack P, const double
   if (!ci.ok) return;
   const int i = ci.i, j = ci.j, kl = ci.kl, kk = kl + 1;
   const long s = skew_blk(L, P, i, j, kl);
-  P.D[s] = Md[ix_p(L, i, j, kk)];
+  const double dg = Md[ix_p(L, i, j, kk)];
+  P.D[s] = dg;
+  P.rD[s] = 1.0 / dg;
   P.nTx[s] = -T[ix_ux(L, i, j, kl)];
   P.nTy[s] = L.has_y ? -T[ix_uy(L, i, j, kl)] : 0.0;
   P.nTz[s] = -T[ix_uz(L, i, j, kk)];
@@ -678,102 +680,161 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-// blockDim.x = 32 (producer warp) + NPs (one compute thread per pencil)
+// n / D, correctly rounded, from the correctly rounded reciprocal rD = RN(1/D): two FMA remainder
+// corrections (Markstein): q0 = n*rD is within 2 ulp, q1 = q0 + (n - q0 D) rD is faithful, and the second
+// correction of a faithful quotient with an exact remainder rounds correctly.  Bit-identical to IEEE `/`
+// for finite, non-denormal operands, with a 5-op dependent chain instead of the ~30-instruction division.
+__device__ __forceinline__ double div_exact(double n, double D, double rD) {
+  double q = n * rD;
+  double r = __fma_rn(-q, D, n);
+  q = __fma_rn(r, rD, q);
+  r = __fma_rn(-q, D, n);
+  return __fma_rn(r, rD, q);
+}
+
+// blockDim.x = 32 (producer warp) + NPs (one compute thread per pencil).
+// Shared memory: ring[NS][7][NPs] | ybuf[2][YP + NPs + YP] | mbarriers[NS],  YP = padding >= NY+1 (zeros).
+// The stage body is branch-free: neighbours that do not exist carry a zero coefficient (T = 0 on boundary
+// faces, packed slots outside the mesh are zero) and the y they multiply is always finite.
+// NPS_T > 0 fixes the row length at compile time (row offsets become immediates); HAS_Y_T = 3-D.
+// All ring / phase bookkeeping is incremental (no runtime division or 64-bit multiply inside the loop):
+// the producer lane's per-stage work is what every compute warp waits for at the barrier.
+template <int NPS_T, bool HAS_Y_T>
 __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double* __restrict__ T, double* y, int NS,
-                                                  int do_fwd, int do_bwd, const MinresState* st) {
+                                                  int YP, int do_fwd, int do_bwd, const MinresState* st) {
   if (st && st->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int NPs = P.NPs, NP = L.NY * L.nzl;
-  const long SS = P.SS;
-  const int nstage = L.NX + L.NY + L.nzl - 2;
-  double* ring = reinterpret_cast<double*>(smem_raw);                                        // [NS][6][NPs]
-  double* ybuf = ring + (size_t)NS * SS;                                                     // [2][NPs]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ybuf + (size_t)2 * NPs);  // [NS]
+  const int NPs = NPS_T > 0 ? NPS_T : P.NPs;
+  const int NY = HAS_Y_T ? L.NY : 1;
+  const int NP = NY * L.nzl;
+  const int SS = 7 * NPs;
+  const int nstage = L.NX + NY + L.nzl - 2;
+  const int YR = NPs + 2 * YP;                                                               // ybuf row length
+  double* ring = reinterpret_cast<double*>(smem_raw);                                        // [NS][7][NPs]
+  double* ybuf = ring + (size_t)NS * SS;                                                     // [2][YR]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ybuf + (size_t)2 * YR);   // [NS]
   const bool producer = threadIdx.x < 32;
   const int p = (int)threadIdx.x - 32;
   const bool pv = !producer && p < NP;
-  const int pj = pv ? p % L.NY : 0, pk = pv ? p / L.NY : 0;
+  const int pj = pv ? p % NY : 0, pk = pv ? p / NY : 0;
+  const int s0 = pj + pk;                       // first stage in which this pencil is active
   const int k = pk + L.zlo;
+  const bool ghost_lo = pv && pk == 0 && k > 0;                  // multi-rank: lower neighbour on another GPU
+  const bool ghost_hi = pv && pk + 1 == L.nzl && k + 1 < L.NZ;   // multi-rank: upper neighbour on another GPU
+  const bool in_lo = pk > 0, in_hi = pk + 1 < L.nzl, has_jlo = HAS_Y_T && pj > 0, has_jhi = HAS_Y_T && pj + 1 < NY;
   double* yp = y + L.off_p;
   const unsigned rowb = (unsigned)NPs * 8u;
+  const int ringn = NS * SS;
 
+  // ring and ybuf start as zeros: never-loaded slots / padding must hold finite values (they only ever meet
+  // zero coefficients)
+  for (int q = threadIdx.x; q < ringn + 2 * YR; q += blockDim.x) ring[q] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  int it = 0;  // global iteration counter: ring slot = it % NS, mbarrier parity = (it / NS) & 1
+  // running ring state shared by both phases (slot index and mbarrier parity of the next issue / wait / use)
+  int sl = 0, par = 0;                 // compute: slot offset (elements) and ybuf row of the current iteration
+  int is_slot = 0;                     // producer: slot of the next block to issue
+  int wt_slot = 0;
+  unsigned wt_par = 0;                 // producer: slot / parity of the next block to wait for
+
   for (int dir = 0; dir < 2; ++dir) {
     if (dir == 0 ? !do_fwd : !do_bwd) continue;
-    const int it0 = it;
-    // stage of phase-local iteration n
-    auto stage_of = [&](int n) { return dir == 0 ? n : nstage - 1 - n; };
-    auto issue = [&](int n) {  // producer lane 0 only
-      const int j = it0 + n;
-      unsigned long long* bar = bars + (j % NS);
-      const unsigned bytes = rowb * (L.has_y ? 6u : (dir == 0 ? 4u : 5u));  // 2-D: skip the unused rows
+    const unsigned bytes = rowb * (HAS_Y_T ? 7u : (dir == 0 ? 5u : 6u));  // 2-D: skip the unused rows
+    const long gstep = dir == 0 ? (long)SS : -(long)SS;
+    const double* is_src = P.Rs + (dir == 0 ? 0 : (size_t)(nstage - 1) * SS);  // next block to issue (global)
+    int n_issued = 0, n_waited = 0;
+    auto issue1 = [&]() {  // producer lane 0 only
+      unsigned long long* bar = bars + is_slot;
       mbar_expect_tx(bar, bytes);
-      bulk_g2s(ring + (size_t)(j % NS) * SS, P.Rs + (size_t)stage_of(n) * SS, bytes, bar);
+      bulk_g2s(ring + is_slot * SS, is_src, bytes, bar);
+      is_src += gstep;
+      is_slot = is_slot + 1 == NS ? 0 : is_slot + 1;
+      ++n_issued;
     };
-    auto wait_full = [&](int n) {
-      const int j = it0 + n;
-      mbar_wait(bars + (j % NS), (unsigned)((j / NS) & 1));
+    auto wait1 = [&]() {
+      mbar_wait(bars + wt_slot, wt_par);
+      if (wt_slot + 1 == NS) { wt_slot = 0; wt_par ^= 1u; }
+      else ++wt_slot;
+      ++n_waited;
     };
     if (dir == 1 && do_fwd) {
-      // forward rows (row 5 of every block) were written with ordinary stores: order them before the
+      // forward rows (row Yf of every block) were written with ordinary stores: order them before the
       // async-proxy reads of the backward pass
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) asm volatile("fence.proxy.async;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-      for (int n = 0; n < NS - 2 && n < nstage; ++n) issue(n);
-      wait_full(0);
-      if (nstage > 1) wait_full(1);
+      while (n_issued < NS - 2 && n_issued < nstage) issue1();
+      wait1();
+      if (nstage > 1) wait1();
     }
     __syncthreads();
-    for (int n = 0; n < nstage; ++n, ++it) {
-      const int d = stage_of(n);
-      if (producer) {
+    if (producer) {
+      for (int n = 0; n < nstage; ++n) {
         if (threadIdx.x == 0) {
-          // slot of iteration it-2 is free (last read, as upper-face rows, during it-1)
-          if (n + NS - 2 < nstage) issue(n + NS - 2);
-          if (n + 2 < nstage) wait_full(n + 2);
+          // the slot of iteration n-2 is free (last read, as upper-face rows, during n-1)
+          if (n_issued < nstage) issue1();
+          if (n_waited < nstage) wait1();
         }
-      } else {
-        const double* slot = ring + (size_t)(it % NS) * SS;
-        double* ycur = ybuf + (size_t)(it & 1) * NPs;
-        const double* yadj = ybuf + (size_t)((it + 1) & 1) * NPs;  // previous iteration's row
-        const int i = d - pj - pk;
-        if (pv && i >= 0 && i < L.NX) {
-          const double R = slot[p], D = slot[NPs + p], nx = slot[2 * NPs + p], nz = slot[3 * NPs + p];
-          const double ny = L.has_y ? slot[5 * NPs + p] : 0.0;
-          double sum = 0.0;
-          if (dir == 0) {
-            if (k > 0) sum += (pk > 0 ? yadj[p - L.NY] : __ldcg(yp + ix_c(L, i, pj, 0))) * nz;
-            if (L.has_y && pj > 0) sum += yadj[p - 1] * ny;
-            if (i > 0) sum += yadj[p] * nx;
-          } else {
-            const double* F = ring + (size_t)((it + 1) % NS) * SS + 4 * NPs;  // block of stage d-1, row Yf
-            const double* up = ring + (size_t)((it + NS - 1) % NS) * SS;      // block of stage d+1
-            if (k > 0) sum += (pk > 0 ? F[p - L.NY] : __ldcg(yp + ix_c(L, i, pj, 0))) * nz;
-            if (L.has_y && pj > 0) sum += F[p - 1] * ny;
-            if (i > 0) sum += F[p] * nx;
-            if (i + 1 < L.NX) sum += yadj[p] * up[2 * NPs + p];
-            if (L.has_y && pj + 1 < L.NY) sum += yadj[p + 1] * up[5 * NPs + p + 1];
-            if (k + 1 < L.NZ) {
-              if (pk + 1 < L.nzl) sum += yadj[p + L.NY] * up[3 * NPs + p + L.NY];
-              else sum += __ldcg(yp + ix_c(L, i, pj, pk + 2)) * (-T[ix_uz(L, i, pj, pk + 2)]);
-            }
-          }
-          const double v = (R - sum) / D;
-          ycur[p] = v;
-          if (dir == 0) P.Yf[(size_t)d * SS + p] = v;
-          else P.Yb[(size_t)d * NPs + p] = v;
-        }
+        __syncthreads();
       }
-      __syncthreads();
+    } else if (dir == 0) {
+      int i = -s0;
+      double* gout = P.Yf + p;
+      for (int n = 0; n < nstage; ++n, ++i) {
+        if ((unsigned)i < (unsigned)L.NX && pv) {
+          const double* slot = ring + sl + p;
+          double* ycur = ybuf + par * YR + YP + p;
+          const double* yadj = ybuf + (par ^ 1) * YR + YP + p;  // previous iteration's row
+          const double R = slot[0], D = slot[NPs], rD = slot[2 * NPs], nx = slot[3 * NPs], nz = slot[4 * NPs];
+          const double yz = ghost_lo ? __ldcg(yp + ix_c(L, i, pj, 0)) : yadj[-NY];
+          double sum = yz * nz;
+          if (HAS_Y_T) sum += yadj[-1] * slot[6 * NPs];
+          sum += yadj[0] * nx;
+          const double v = div_exact(R - sum, D, rD);
+          ycur[0] = v;
+          *gout = v;
+        }
+        __syncthreads();
+        gout += SS;
+        sl = sl + SS == ringn ? 0 : sl + SS;
+        par ^= 1;
+      }
+    } else {
+      int i = nstage - 1 - s0;
+      double* gout = P.Yb + p + (size_t)(nstage - 1) * NPs;
+      for (int n = 0; n < nstage; ++n, --i) {
+        if ((unsigned)i < (unsigned)L.NX && pv) {
+          const int sn = sl + SS == ringn ? 0 : sl + SS, su = sl == 0 ? ringn - SS : sl - SS;
+          const double* slot = ring + sl + p;
+          const double* F = ring + sn + 5 * NPs + p;  // block of stage d-1, row Yf
+          const double* up = ring + su + p;           // block of stage d+1
+          double* ycur = ybuf + par * YR + YP + p;
+          const double* yadj = ybuf + (par ^ 1) * YR + YP + p;  // previous iteration's row (stage d+1)
+          const double R = slot[0], D = slot[NPs], rD = slot[2 * NPs], nx = slot[3 * NPs], nz = slot[4 * NPs];
+          const double fz = ghost_lo ? __ldcg(yp + ix_c(L, i, pj, 0)) : (in_lo ? F[-NY] : 0.0);
+          double sum = fz * nz;
+          if (HAS_Y_T) sum += (has_jlo ? F[-1] : 0.0) * slot[6 * NPs];
+          sum += F[0] * nx;
+          sum += yadj[0] * (i + 1 < L.NX ? up[3 * NPs] : 0.0);
+          if (HAS_Y_T) sum += yadj[1] * (has_jhi ? up[6 * NPs + 1] : 0.0);
+          const double hz = ghost_hi ? -T[ix_uz(L, i, pj, pk + 2)] : (in_hi ? up[4 * NPs + NY] : 0.0);
+          const double yu = ghost_hi ? __ldcg(yp + ix_c(L, i, pj, pk + 2)) : yadj[NY];
+          sum += yu * hz;
+          const double v = div_exact(R - sum, D, rD);
+          ycur[0] = v;
+          *gout = v;
+        }
+        __syncthreads();
+        gout -= NPs;
+        sl = sl + SS == ringn ? 0 : sl + SS;
+        par ^= 1;
+      }
     }
   }
 }
@@ -853,6 +914,77 @@ __global__ void __launch_bounds__(BLK) k_sat_substep(Lay L, Phys ph, SatParam sp
     yv *= sp.dt;
     Sout[c] = Sin[c] + yv;
   }
+}
+
+// K6, tiled: same arithmetic per cell as k_sat_substep (bit-identical result), but f(S) is evaluated ~1.5x
+// per cell instead of 7x: a block owns a TX x TY tile of columns and marches TZ planes along z; each thread
+// keeps f of its own column for planes k-1, k, k+1 in registers, and f of plane k goes through a shared
+// tile (+ halo ring) for the x / y neighbours.  fp64 divisions were the bound of the simple kernel.
+template <int TX, int TY, bool RATE>
+__global__ void __launch_bounds__(TX* TY) k_sat_tile(Lay L, Phys ph, SatParam sp, int TZ, const double* __restrict__ u,
+                                                     const double* __restrict__ phi, const double* __restrict__ Sin,
+                                                     double* __restrict__ Sout) {
+  __shared__ double fs[TY + 2][TX + 2];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int i = blockIdx.x * TX + tx, j = blockIdx.y * TY + ty;
+  const int kl0 = blockIdx.z * TZ, kl1 = min(kl0 + TZ, L.nzl);
+  const bool in = i < L.NX && j < L.NY;
+  const bool xl = in && i > 0, xh = in && i + 1 < L.NX, yl = in && L.has_y && j > 0, yh = in && L.has_y && j + 1 < L.NY;
+#define GS(idx) (sp.two_phase ? frac_flow_of(ph, Sin[idx]) : Sin[idx])
+  long c = ix_c(L, in ? i : 0, in ? j : 0, kl0 + 1);
+  double f_lo = (in && kl0 + L.zlo > 0) ? GS(c - L.plane) : 0.0;
+  double f_c = in ? GS(c) : 0.0;
+  for (int kl = kl0; kl < kl1; ++kl, c += L.plane) {
+    const int k = kl + L.zlo, kk = kl + 1;
+    const bool zl = in && k > 0, zh = in && k + 1 < L.NZ;
+    const double f_hi = zh ? GS(c + L.plane) : 0.0;
+    fs[ty + 1][tx + 1] = f_c;
+    if (tx == 0) fs[ty + 1][0] = xl ? GS(c - 1) : 0.0;
+    if (tx == TX - 1) fs[ty + 1][TX + 1] = xh ? GS(c + 1) : 0.0;
+    if (TY > 1 || L.has_y) {
+      if (ty == 0) fs[0][tx + 1] = yl ? GS(c - L.NX) : 0.0;
+      if (ty == TY - 1) fs[TY + 1][tx + 1] = yh ? GS(c + L.NX) : 0.0;
+    }
+    __syncthreads();
+    if (in) {
+      const double Fxl = xl ? u[ix_ux(L, i, j, kl)] : 0.0, Fxh = xh ? u[ix_ux(L, i + 1, j, kl)] : 0.0;
+      const double Fyl = yl ? u[ix_uy(L, i, j, kl)] : 0.0, Fyh = yh ? u[ix_uy(L, i, j + 1, kl)] : 0.0;
+      const double Fzl = zl ? u[ix_uz(L, i, j, kk)] : 0.0, Fzh = zh ? u[ix_uz(L, i, j, kk + 1)] : 0.0;
+#define FPOS(F) ((F) > 0.0 ? (F) : 0.0)
+#define FNEG(F) ((F) < 0.0 ? (F) : 0.0)
+      double z = 0.0;
+      if (zl) z += FPOS(Fzl) * f_lo;
+      if (yl) z += FPOS(Fyl) * fs[ty][tx + 1];
+      if (xl) z += FPOS(Fxl) * fs[ty + 1][tx];
+      {
+        double dg = 0.0;
+        if (xl) dg += FNEG(Fxl);
+        if (xh) dg += -FPOS(Fxh);
+        if (yl) dg += FNEG(Fyl);
+        if (yh) dg += -FPOS(Fyh);
+        if (zl) dg += FNEG(Fzl);
+        if (zh) dg += -FPOS(Fzh);
+        z += dg * f_c;
+      }
+      if (xh) z += (-FNEG(Fxh)) * fs[ty + 1][tx + 2];
+      if (yh) z += (-FNEG(Fyh)) * fs[ty + 2][tx + 1];
+      if (zh) z += (-FNEG(Fzh)) * f_hi;
+#undef FPOS
+#undef FNEG
+      z += sat_source(sp, i, j, k) * sp.vol;
+      double yv = z / (phi[c] * sp.vol);
+      if (RATE) {
+        Sout[c] = yv;
+      } else {
+        yv *= sp.dt;
+        Sout[c] = Sin[c] + yv;
+      }
+    }
+    __syncthreads();
+    f_lo = f_c;
+    f_c = f_hi;
+  }
+#undef GS
 }
 
 // RK stage combinations (MPI path's -ode variants): out = a*x + b*y (owned + ghosts)
