@@ -265,14 +265,7 @@ def main():
         dist.all_reduce(t)
         a[:] = t.cpu().numpy()
 
-    nvx = int(s.dims.n_v_comp[0])
-    nvy = int(s.dims.n_v_comp[1]) if d.dim == 3 else 0
-    px = (d.nx + 1) * (d.ny if d.dim == 3 else 1)
-    py = d.nx * (d.ny + 1) if d.dim == 3 else 0
-    top = 1 if hi == nslab else 0
-    own_x = [(px * lo, px * hi), (nvx + py * lo, nvx + py * hi), (nvx + nvy + plane * lo, nvx + nvy + plane * (hi + top)),
-             (s.nv + plane * lo, s.nv + plane * hi)]
-    own_s = [(plane * lo, plane * hi)]
+    own_x, own_s = pkg.partition.owned_ranges(d.dim, d.nx, d.ny, d.nz, rank, world)
     gather(S_host, own_s)
     e2e_steps = max(1, min(args.steps, 2))
 

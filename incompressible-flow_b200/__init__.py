@@ -6,5 +6,5 @@ PressureSolver / SaturationSolver / Param interfaces).  There is no CPU fallback
 fails loudly if the native library is missing.
 """
 from . import abi  # noqa: F401
-from . import binding  # noqa: F401
+from . import binding, partition  # noqa: F401
 from .binding import Solver, build_native, load_library, library_path  # noqa: F401

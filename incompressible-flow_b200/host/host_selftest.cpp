@@ -1,0 +1,84 @@
+// host_selftest.cpp -- CPU-only checks of the host layer (no GPU needed): Param defaults and option table,
+// Krw/Kro, read_binary/write_binary round trip, descriptor flattening.  Prints one "ok <name>" per check.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "param.hpp"
+#include "utilities.hpp"
+
+#define CHECK(c) do { if (!(c)) { std::cout << "FAIL " << #c << " (" << __FILE__ << ":" << __LINE__ << ")" << std::endl; return 1; } } while (0)
+
+int main(int argc, char** argv) {
+  const std::string tmp = argc > 1 ? argv[1] : "/tmp";
+  {  // defaults [REF src/param.cpp:8-13,26-30,35-68]
+    Param p;
+    CHECK(p.spacedim == 2 && p.nx == 100 && p.ny == 100 && p.nz == 100);
+    CHECK(p.order_v == 1 && p.order_p == 1 && p.order_s == 0);
+    CHECK(p.t_final == 200 && p.dt_global == 100 && p.dt_local == 1);
+    CHECK(p.darcy.maxiter == 1000 && p.darcy.rtol == 1e-6 && p.darcy.atol == 1e-10 && p.darcy.print_level == 0);
+    CHECK(!p.two_phase_flow && p.ode_solver_type == 1 && p.inflow == 1. && p.outflow == -1. && p.saturation_source == 1.);
+    CHECK(p.injection.radius == 1. && p.production.height == 1. && p.injection.center(2) == 0.);
+    CHECK(!std::strcmp(p.K_file_x, "no-file") && !std::strcmp(p.outdir, "output") && !std::strcmp(p.extra, ""));
+    std::cout << "ok defaults" << std::endl;
+  }
+  {  // option surface
+    const char* av[] = {"prog", "-d", "3", "-nx", "7", "--ny", "5", "-nz", "3", "-sx", "14", "-ov", "0", "-op", "0", "-os", "0",
+                        "-two-phase", "-Sor", "0.1", "--Swc", "0.2", "-darcy-rtol", "1e-8", "-darcy-maxiter", "77",
+                        "-inj-xcen", "1.5", "-pro-h", "9", "-K-file-x", "kx.bin", "-ode", "3", "-dtl", "0.25", "-no-info"};
+    int ac = sizeof(av) / sizeof(av[0]);
+    Param p;
+    mfem::OptionsParser args(ac, const_cast<char**>(av));
+    p.add_options(args);
+    args.Parse();
+    CHECK(args.Good());
+    CHECK(p.spacedim == 3 && p.nx == 7 && p.ny == 5 && p.nz == 3 && p.sx == 14. && p.order_v == 0);
+    CHECK(p.two_phase_flow && p.Sor == 0.1 && p.Swc == 0.2 && p.darcy.rtol == 1e-8 && p.darcy.maxiter == 77);
+    CHECK(p.injection.center(0) == 1.5 && p.production.height == 9. && !std::strcmp(p.K_file_x, "kx.bin"));
+    CHECK(p.ode_solver_type == 3 && p.dt_local == 0.25 && !p.info);
+    CHECK(p.get_n_cells() == 105 && std::fabs(p.get_cell_volume() - 14. * 100. * 100. / 105.) < 1e-9);
+    // rel-perm [REF src/param.cpp:195-215]
+    const double S_ = (0.5 - 0.2) / (1. - 0.1 - 0.2);
+    CHECK(p.Krw(0.5) == S_ * S_ && p.Kro(0.5) == (1. - S_) * (1. - S_));
+    const impes_desc d = p.to_desc();
+    CHECK(d.dim == 3 && d.nx == 7 && d.two_phase == 1 && d.Sor == 0.1 && d.darcy_maxiter == 77 && d.mu_w == 1.0);
+    CHECK(d.injection.center[0] == 1.5 && d.production.height == 9. && d.ode_solver_type == 3);
+    const char* bad[] = {"prog", "-nx", "7", "-bogus"};
+    Param q;
+    mfem::OptionsParser a2(4, const_cast<char**>(bad));
+    q.add_options(a2);
+    a2.Parse();
+    CHECK(!a2.Good());
+    Param s;
+    CHECK(s.Krw(0.3) == 0.3 && s.Kro(0.3) == 0.7);  // single-phase
+    std::cout << "ok options" << std::endl;
+  }
+  {  // raw binary formats [REF src/utilities.cpp:21-74]
+    const int n = 11;
+    std::vector<double> a(n), b(n), c(n);
+    for (int i = 0; i < n; ++i) a[i] = 0.1 * i + 1.0 / 3.0;
+    const std::string f32 = tmp + "/impes_selftest_f32.bin", f64 = tmp + "/impes_selftest_f64.bin";
+    write_binary(f32.c_str(), n, a.data());  // always float32
+    read_binary(f32.c_str(), n, b.data());
+    for (int i = 0; i < n; ++i) CHECK(b[i] == (double)(float)a[i]);
+    FILE* fp = std::fopen(f64.c_str(), "wb");
+    CHECK(fp && std::fwrite(a.data(), sizeof(double), n, fp) == (size_t)n);
+    std::fclose(fp);
+    read_binary(f64.c_str(), n, c.data());  // float64 auto-detected
+    for (int i = 0; i < n; ++i) CHECK(c[i] == a[i]);
+    CHECK(d2s(7, 0, 0, 0, 6) == "000007" && d2s(3) == "3");
+    std::remove(f32.c_str());
+    std::remove(f64.c_str());
+    std::cout << "ok binary_io" << std::endl;
+  }
+  {  // init_arrays: constants, files, porosity floor [REF src/param.cpp:78-113]
+    Param p;
+    p.nx = 4; p.ny = 3; p.K_x = 2.5; p.phi = 1e-5;
+    p.init_arrays();
+    CHECK(p.K_array_x[11] == 2.5 && p.K_array_y[0] == 1.0 && p.K_array_z == nullptr && p.phi_array[5] == 1e-3);
+    std::cout << "ok init_arrays" << std::endl;
+  }
+  return 0;
+}

@@ -1,0 +1,28 @@
+// utilities.hpp -- the input/output formats on either side of the hot path:
+// raw binary cell arrays.  read_binary auto-detects float32 / float64 from the file length
+// [REF src/utilities.cpp:21-58]; write_binary always writes float32 [REF src/utilities.cpp:62-74].
+#pragma once
+#include <iomanip>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+
+void read_binary(const char* filename, int n_values, double* values);
+void write_binary(const char* filename, int n_values, const double* values);
+
+// number -> string with optional zero padding (file names "..._000003.bin") [REF src/utilities.hpp:29-62]
+template <typename T>
+inline std::string d2s(T data, bool scientific = false, int precision = 0, bool noperiod = false, int width = 0) {
+  std::ostringstream o;
+  if (scientific) o.setf(std::ios::scientific);
+  if (precision > 0) o.precision(precision);
+  if (width > 0) o << std::setfill('0') << std::setw(width);
+  if (!(o << data)) throw std::runtime_error("Bad conversion of data to string!");
+  std::string res = o.str();
+  if (!scientific && noperiod) {
+    const std::string::size_type pos = res.find('.');
+    if (pos != std::string::npos) res.erase(pos, 1);
+    if (width > 0 && (int)res.size() < width) res.insert(0, width - res.size(), '0');
+  }
+  return res;
+}

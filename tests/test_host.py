@@ -1,0 +1,100 @@
+"""The C++ host layer (incompressible-flow_b200/host): the reference's Param / option surface /
+PressureSolver / SaturationSolver / run_serial interfaces over the C ABI."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "incompressible-flow_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def host_bins(native_lib):
+    if not os.path.exists(os.path.join(HOST, "impes_run")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "incompressible-flow_b200")], stdout=subprocess.DEVNULL)
+    return os.path.join(HOST, "impes_run"), os.path.join(HOST, "host_selftest")
+
+
+def test_host_selftest(host_bins, tmp_path):
+    out = subprocess.run([host_bins[1], str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for name in ("defaults", "options", "binary_io", "init_arrays"):
+        assert f"ok {name}" in out.stdout
+
+
+def test_driver_usage_and_exit_codes(host_bins):
+    """argc == 1 -> hint + exit 1; bad option / -h -> usage + exit 1; -info -> info + exit 1
+    [REF src/run_serial.cpp:16-38] [REF src/main.cpp:46-65]."""
+    run = host_bins[0]
+    o = subprocess.run([run], capture_output=True, text=True)
+    assert o.returncode == 1 and "To see the available options, run" in o.stdout
+    o = subprocess.run([run, "-nx", "4", "-bogus"], capture_output=True, text=True)
+    assert o.returncode == 1 and "Unrecognized option: -bogus" in o.stdout and "--darcy-maxiter" in o.stdout
+    o = subprocess.run([run, "-h"], capture_output=True, text=True)
+    assert o.returncode == 1
+    # every flag of the reference's option table is present
+    for flag in ("-d", "-nx", "-ny", "-nz", "-sx", "-sy", "-sz", "-ov", "-op", "-os", "-tf", "-dtg", "-dtl", "-vsg", "-vsl",
+                 "-ss", "-Kx", "-Ky", "-Kz", "-phi", "-K-file-x", "-K-file-y", "-K-file-z", "-phi-file", "-outdir", "-extra",
+                 "-two-phase", "-single-phase", "-ode", "-inj-xcen", "-inj-ycen", "-inj-zcen", "-inj-r", "-inj-h",
+                 "-pro-xcen", "-pro-ycen", "-pro-zcen", "-pro-r", "-pro-h", "-inflow", "-outflow", "-sat-source", "-Sor",
+                 "-Swc", "-darcy-maxiter", "-darcy-rtol", "-darcy-atol", "-darcy-print-level", "-info", "-no-info"):
+        assert re.search(r"\s%s[ ,<]" % re.escape(flag), o.stdout), flag
+    o = subprocess.run([run, "-info"], capture_output=True, text=True)
+    assert o.returncode == 1 and "C ABI version" in o.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 3])
+def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim):
+    """A whole run of the run_serial-compatible driver (K from a float32 file, 3 global steps) reproduces the
+    oracle's loop: same MINRES iteration counts in the log, saturation dumps equal to float32 precision."""
+    from incompressible_flow_b200 import workloads
+    nx, ny, nz = (20, 16, 1) if dim == 2 else (9, 8, 6)
+    n = nx * ny * nz
+    K32 = np.exp(np.random.default_rng(3).standard_normal(n)).astype(np.float32)
+    kfile = tmp_path / "K.bin"
+    K32.tofile(kfile)
+    out = tmp_path / "out"
+    h = 100.0 / nx
+    common = ["-d", str(dim), "-nx", str(nx), "-ny", str(ny), "-nz", str(nz), "-sx", "100", "-sy", "100", "-sz", "100",
+              "-ov", "0", "-op", "0", "-os", "0", "-two-phase", "-tf", "60", "-dtg", "20", "-dtl", "1", "-vsg", "0",
+              "-K-file-x", str(kfile), "-K-file-y", str(kfile), "-K-file-z", str(kfile), "-outdir", str(out),
+              "-extra", "t", "-darcy-maxiter", "5000"]
+    if dim == 2:
+        wells = ["-inj-xcen", "0", "-inj-ycen", "0", "-inj-r", str(h), "-pro-xcen", "100", "-pro-ycen", "100", "-pro-r", str(h)]
+    else:
+        wells = ["-inj-xcen", "0", "-inj-zcen", "0", "-inj-ycen", "0", "-inj-h", "100", "-inj-r", str(h),
+                 "-pro-xcen", "100", "-pro-zcen", "100", "-pro-ycen", "0", "-pro-h", "100", "-pro-r", str(h)]
+    o = subprocess.run([host_bins[0]] + common + wells, capture_output=True, text=True, timeout=300)
+    assert o.returncode == 0, o.stdout + o.stderr
+    its = [int(m) for m in re.findall(r"Darcy solver converged\. Iter = (\d+)", o.stdout)]
+    assert "Number of global time steps: 3" in o.stdout and o.stdout.count("is done") == 3
+    # oracle loop on the same inputs
+    d = workloads.make_desc(dim, nx, ny, nz, sx=100, sy=100, sz=100, maxiter=5000)
+    for w, c, r in ((d.injection, (0, 0, 0), h), (d.production, (100, 100 if dim == 2 else 0, 100), h)):
+        w.center[0], w.center[1], w.center[2] = c
+        w.radius, w.height = r, 100.0
+    K = K32.astype(np.float64)
+    oc = orc.Oracle(d, K, K, K if dim == 3 else None, np.ones(n))
+    oc.set_arith(1)
+    S, its_o = np.zeros(n), []
+    for ti in range(1, 4):
+        x, st, rc = oc.pressure_solve(S)
+        S, _ = oc.saturation_advance(x[:oc.nv], S, 20.0, 1.0)
+        its_o.append(st.iterations)
+        dump = np.fromfile(out / f"saturation_t_{dim}D_2phase_{ti:06d}.bin", dtype=np.float32)
+        assert np.array_equal(dump, S.astype(np.float32))
+    assert its == its_o
+
+
+@pytest.mark.gpu
+def test_driver_aborts_when_not_converged(host_bins, tmp_path):
+    """Non-convergence is fatal like in the reference [REF src/pressure_solver.cpp:110-117]."""
+    o = subprocess.run([host_bins[0], "-nx", "16", "-ny", "16", "-ov", "0", "-op", "0", "-os", "0", "-darcy-maxiter", "3",
+                        "-inj-r", "7", "-pro-xcen", "100", "-pro-ycen", "100", "-pro-r", "7", "-outdir", str(tmp_path / "o")],
+                       capture_output=True, text=True, timeout=120)
+    assert o.returncode != 0
+    assert "Darcy solver DIDN'T converge. Iter = 3" in o.stderr and "The solver didn't converge => terminating" in o.stderr

@@ -1,0 +1,79 @@
+"""Multi-GPU parity check (run under torch.distributed.run with N ranks, one GPU each):
+N-slab solve vs the single-domain CPU oracle.  K1 / preconditioner / saturation sub-steps must be
+bit-identical (no cross-rank reductions in them: the Schur sweep is pipelined rank by rank in the exact
+global order); the MINRES solve differs only through the rank-wise association of the two dot products
+(iterations +-2, solution within the Krylov drift bound)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from __graft_entry__ import load_package, load_oracle
+pkg = load_package()
+from incompressible_flow_b200 import workloads, abi
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+
+def gather(a, owned):
+    m = np.zeros(a.shape[0], dtype=bool)
+    for lo, hi in owned:
+        m[lo:hi] = True
+    a = np.where(m, a, 0.0)
+    t = torch.from_numpy(a).cuda()
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+ok = True
+for cfg in (dict(dim=3, nx=12, ny=10, nz=9), dict(dim=2, nx=33, ny=21), dict(dim=3, nx=24, ny=20, nz=16)):
+    d, Kx, Ky, Kz, phi = workloads.build(K="lognormal", **cfg)
+    n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
+    phi = np.random.default_rng(7).uniform(0.1, 0.4, n)
+    d.rank, d.world_size, d.device = rank, world, local
+    s = pkg.Solver(d, Kx, Ky, Kz, phi)
+    uid = [s.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    s.comm_init(uid[0])
+    own_x, own_s = pkg.partition.owned_ranges(d.dim, d.nx, d.ny, d.nz, rank, world)
+    rng = np.random.default_rng(3)
+    S = rng.uniform(0.05, 0.95, n)
+    x = rng.standard_normal(s.nv + s.np_)
+    s.update_coefficients(S)
+    yg = gather(s.darcy_apply(x), own_x)
+    zg = gather(s.prec_apply(x), own_x)
+    xs, st = s.pressure_solve(S)
+    xs = gather(xs, own_x)
+    Sg, nsub = s.saturation_advance(xs[:s.nv], S, 1, 7.3, 0.5)
+    Sg = gather(Sg, own_s)
+    bad, mx = s.guards()
+    if rank == 0:
+        orc = load_oracle()
+        d1 = workloads.build(K="lognormal", **cfg)[0]
+        o = orc.Oracle(d1, Kx, Ky, Kz, phi)
+        o.set_arith(1)
+        o.update_coefficients(S)
+        e1 = np.array_equal(yg, o.darcy_apply(x))
+        e2 = np.array_equal(zg, o.prec_apply(x))
+        xo, sto, _ = o.pressure_solve(S)
+        So, _ = o.saturation_advance(xs[:o.nv], S, 7.3, 0.5)
+        e3 = np.array_equal(Sg, So)
+        bo, mo = o.guards(So)
+        dit = abs(st.iterations - sto.iterations)
+        ex = rel(xs[:o.nv], xo[:o.nv])
+        good = e1 and e2 and e3 and dit <= 2 and ex < 1e-6 and (bad, mx) == (bo, mo)
+        ok = ok and good
+        print(f"{cfg} world={world}: K1 bit-exact={e1} prec bit-exact={e2} sat bit-exact={e3} "
+              f"iters gpu={st.iterations} oracle={sto.iterations} rel_u={ex:.2e} guards={(bad, mx) == (bo, mo)} -> {'OK' if good else 'FAIL'}",
+              flush=True)
+    s.close()
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, src=0)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) else 1)
