@@ -105,8 +105,13 @@ class Oracle:
     def set_mass_cg(self, on):
         self.L.orc_set_mass_cg(self.h, int(on))
 
+    def _chk_S(self, S):
+        if S.shape[0] != self.ns:
+            raise ValueError(f"saturation vector has {S.shape[0]} entries, the DG space has {self.ns}")
+
     def pressure_solve(self, S):
         S = _f64(S)
+        self._chk_S(S)
         x = np.zeros(self.nv + self.np_)
         st = abi.SolveStats()
         rc = self.L.orc_pressure_solve(self.h, _p(S), _p(x), C.byref(st))
@@ -114,6 +119,7 @@ class Oracle:
 
     def update_coefficients(self, S):
         S = _f64(S)
+        self._chk_S(S)
         rc = self.L.orc_update_coefficients(self.h, _p(S))
         if rc:
             raise RuntimeError(self.L.orc_last_error(self.h).decode())

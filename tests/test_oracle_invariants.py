@@ -41,11 +41,9 @@ def test_rt0_local_mass_block_and_signs(pkg, orc):
 
 def test_rt1_reference_matrices(pkg, orc):
     """RT1 tensor structure: cell-constant coefficient => M_d = a (h_d/A_d) Mc x Mo, B = -G x Mo."""
-    d, o = build(pkg, orc, dim=2, nx=1, ny=1, sx=1.0, sy=1.0, K="homogeneous", order=1, two_phase=False)
-    import ctypes
     # boundary elimination would hide the element matrix on a 1x1 mesh: use the interior of a 3x3 mesh instead
     d, o = build(pkg, orc, dim=2, nx=3, ny=3, sx=3.0, sy=3.0, K="homogeneous", order=1, two_phase=False)
-    o.update_coefficients(np.zeros(9))
+    o.update_coefficients(np.zeros(o.ns))          # DG-Q1 saturation: 4 dofs per cell
     M = o.csr("M").toarray()
     Mc = np.array([[4, 2, -1], [2, 16, 2], [-1, 2, 4]]) / 30.0
     # x-component node grid: (2*3+1) x (2*3); interior cell (1,1): closed nodes ix=2,3,4, open node iy=2
