@@ -551,11 +551,11 @@ int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout) {
     return 0;
   }
   if (L.has_y) {
-    dim3 g((L.NX + 31) / 32, (L.NY + 7) / 8, (L.nzl + h->sat_tz - 1) / h->sat_tz);
+    dim3 g((L.NX + 29) / 30, (L.NY + 5) / 6, (L.nzl + h->sat_tz - 1) / h->sat_tz);
     if (rate) k_sat_tile<32, 8, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
     else k_sat_tile<32, 8, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
   } else {
-    dim3 g((L.NX + 255) / 256, 1, (L.nzl + h->sat_tz - 1) / h->sat_tz);
+    dim3 g((L.NX + 253) / 254, 1, (L.nzl + h->sat_tz - 1) / h->sat_tz);
     if (rate) k_sat_tile<256, 1, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
     else k_sat_tile<256, 1, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
   }
@@ -776,6 +776,8 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   h->g_nv = h->g_nvx + h->g_nvy + h->g_nvz;
   h->g_np = h->g_ncell;
   h->ph.two_phase = d.two_phase; h->ph.Sor = d.Sor; h->ph.Swc = d.Swc; h->ph.mu_w = d.mu_w; h->ph.mu_o = d.mu_o;
+  h->ph.den = 1. - d.Sor - d.Swc; h->ph.rden = 1.0 / h->ph.den; h->ph.rmu_w = 1.0 / d.mu_w; h->ph.rmu_o = 1.0 / d.mu_o;
+  if (L.ncl >= (1L << 32) || L.ntot >= (1L << 40)) { h->err = "slab too large for 32-bit cell indexing"; return IMPES_ERR_UNSUPPORTED; }
   SatParam& sp = h->sp;
   sp.two_phase = d.two_phase; sp.dt = 0; sp.vol = h->vol;
   sp.hx = h->h[0]; sp.hy = h->h[1]; sp.hz = h->h[2];
@@ -871,7 +873,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
 
   {  // K6 tiling: enough blocks for >= 2 waves when the mesh allows it
     if (const char* e = getenv("IMPES_SAT_SIMPLE")) h->sat_simple = atoi(e) != 0;
-    const long tiles = L.has_y ? (long)((L.NX + 31) / 32) * ((L.NY + 7) / 8) : (long)((L.NX + 255) / 256);
+    const long tiles = L.has_y ? (long)((L.NX + 29) / 30) * ((L.NY + 5) / 6) : (long)((L.NX + 253) / 254);
     long tz = (tiles * L.nzl) / (2L * h->num_sms);
     h->sat_tz = (int)std::max<long>(1, std::min<long>(16, tz));
     if (const char* e = getenv("IMPES_SAT_TZ")) h->sat_tz = std::max(1, atoi(e));

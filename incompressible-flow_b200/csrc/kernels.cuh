@@ -68,27 +68,45 @@ __device__ __forceinline__ void finish_dot(double v, double* partial, double* ou
   }
 }
 
+// n / D, correctly rounded, from the correctly rounded reciprocal rD = RN(1/D): two FMA remainder
+// corrections (Markstein): q0 = n*rD is within 2 ulp, q1 = q0 + (n - q0 D) rD is faithful, and the second
+// correction of a faithful quotient with an exact remainder rounds correctly.  Bit-identical to IEEE `/`
+// for finite, non-denormal operands, with a 5-op dependent chain instead of the ~30-instruction division.
+__device__ __forceinline__ double div_exact(double n, double D, double rD) {
+  double q = n * rD;
+  double r = __fma_rn(-q, D, n);
+  q = __fma_rn(r, rD, q);
+  r = __fma_rn(-q, D, n);
+  return __fma_rn(r, rD, q);
+}
+
 // ---------------------------------------------------------------------------------------
-// physics: Param::Krw / Param::Kro  [REF src/param.cpp:195-215]  (no clamping)
+// physics: Param::Krw / Param::Kro  [REF src/param.cpp:195-215]  (no clamping).
+// Divisions by the run-time constants (1 - Sor - Swc), mu_w, mu_o go through div_exact with host-computed
+// reciprocals: same bits as `/`, a fifth of the instructions.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double krw_of(const Phys& ph, double S) {
   if (ph.two_phase) {
-    const double S_ = (S - ph.Swc) / (1. - ph.Sor - ph.Swc);
+    const double S_ = div_exact(S - ph.Swc, ph.den, ph.rden);
     return S_ * S_;
   }
   return S;
 }
 __device__ __forceinline__ double kro_of(const Phys& ph, double S) {
   if (ph.two_phase) {
-    const double S_ = (S - ph.Swc) / (1. - ph.Sor - ph.Swc);
+    const double S_ = div_exact(S - ph.Swc, ph.den, ph.rden);
     return (1. - S_) * (1. - S_);
   }
   return (1. - S);
 }
+// total mobility lambda = Krw/mu_w + Kro/mu_o   (CWVectorCoefficient::Eval [REF src/param.hpp:252-254])
+__device__ __forceinline__ double lambda_of(const Phys& ph, double S) {
+  return div_exact(krw_of(ph, S), ph.mu_w, ph.rmu_w) + div_exact(kro_of(ph, S), ph.mu_o, ph.rmu_o);
+}
 // FS  [REF src/saturation_solver.cpp:8-17]
 __device__ __forceinline__ double frac_flow_of(const Phys& ph, double S) {
-  const double mw = krw_of(ph, S) / ph.mu_w;
-  const double mo = kro_of(ph, S) / ph.mu_o;
+  const double mw = div_exact(krw_of(ph, S), ph.mu_w, ph.rmu_w);
+  const double mo = div_exact(kro_of(ph, S), ph.mu_o, ph.rmu_o);
   return mw / (mw + mo);
 }
 
@@ -98,13 +116,13 @@ struct CellIdx {
 };
 __device__ __forceinline__ CellIdx owned_cell(const Lay& L) {
   CellIdx c;
-  const long t = (long)blockIdx.x * BLK + threadIdx.x;
-  c.ok = t < L.ncl;
-  const long tt = c.ok ? t : 0;
-  c.i = (int)(tt % L.NX);
-  const long r = tt / L.NX;
-  c.j = (int)(r % L.NY);
-  c.kl = (int)(r / L.NY);
+  const unsigned t = blockIdx.x * (unsigned)BLK + threadIdx.x;  // owned cells per rank < 2^32 (checked at create)
+  c.ok = t < (unsigned)L.ncl;
+  const unsigned tt = c.ok ? t : 0u;
+  const unsigned r = tt / (unsigned)L.NX;
+  c.i = (int)(tt - r * (unsigned)L.NX);
+  c.kl = (int)(r / (unsigned)L.NY);
+  c.j = (int)(r - (unsigned)c.kl * (unsigned)L.NY);
   c.k = c.kl + L.zlo;
   return c;
 }
@@ -130,7 +148,7 @@ __global__ void __launch_bounds__(BLK) k_cell_coeff(Lay L, Phys ph, const double
     return;
   }
   const double s = S[c];
-  const double lam = krw_of(ph, s) / ph.mu_w + kro_of(ph, s) / ph.mu_o;
+  const double lam = lambda_of(ph, s);
   mx[c] = (1. / (lam * Kx[c])) * gx;
   if (L.has_y) my[c] = (1. / (lam * Ky[c])) * gy;
   mz[c] = (1. / (lam * Kz[c])) * gz;
@@ -680,18 +698,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-// n / D, correctly rounded, from the correctly rounded reciprocal rD = RN(1/D): two FMA remainder
-// corrections (Markstein): q0 = n*rD is within 2 ulp, q1 = q0 + (n - q0 D) rD is faithful, and the second
-// correction of a faithful quotient with an exact remainder rounds correctly.  Bit-identical to IEEE `/`
-// for finite, non-denormal operands, with a 5-op dependent chain instead of the ~30-instruction division.
-__device__ __forceinline__ double div_exact(double n, double D, double rD) {
-  double q = n * rD;
-  double r = __fma_rn(-q, D, n);
-  q = __fma_rn(r, rD, q);
-  r = __fma_rn(-q, D, n);
-  return __fma_rn(r, rD, q);
-}
-
 // blockDim.x = 32 (producer warp) + NPs (one compute thread per pencil).
 // Shared memory: ring[NS][7][NPs] | ybuf[2][YP + NPs + YP] | mbarriers[NS],  YP = padding >= NY+1 (zeros).
 // The stage body is branch-free: neighbours that do not exist carry a zero coefficient (T = 0 on boundary
@@ -916,46 +922,63 @@ __global__ void __launch_bounds__(BLK) k_sat_substep(Lay L, Phys ph, SatParam sp
   }
 }
 
-// K6, tiled: same arithmetic per cell as k_sat_substep (bit-identical result), but f(S) is evaluated ~1.5x
-// per cell instead of 7x: a block owns a TX x TY tile of columns and marches TZ planes along z; each thread
-// keeps f of its own column for planes k-1, k, k+1 in registers, and f of plane k goes through a shared
-// tile (+ halo ring) for the x / y neighbours.  fp64 divisions were the bound of the simple kernel.
+// K6, tiled: same arithmetic per cell as k_sat_substep (bit-identical result), restructured for instruction
+// count: tiles overlap by one cell in x (and y), so EVERY thread evaluates f(S) exactly once per plane for its
+// own cell (no divergent halo work) and only the tile interior (TX-2) x (TY-2) updates; a block marches TZ
+// planes along z keeping f of its column for planes k-1, k, k+1 in registers; the x / y neighbours come from a
+// double-buffered shared tile (one barrier per plane).  f-evaluations per updated cell: ~1.6 instead of 7,
+// with one IEEE division each (the constant denominators use div_exact).  All addressing is incremental.
 template <int TX, int TY, bool RATE>
 __global__ void __launch_bounds__(TX* TY) k_sat_tile(Lay L, Phys ph, SatParam sp, int TZ, const double* __restrict__ u,
                                                      const double* __restrict__ phi, const double* __restrict__ Sin,
                                                      double* __restrict__ Sout) {
-  __shared__ double fs[TY + 2][TX + 2];
+  constexpr int OX = TX - 2, OY = TY > 1 ? TY - 2 : 1;
+  __shared__ double fs[2][TY][TX];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int i = blockIdx.x * TX + tx, j = blockIdx.y * TY + ty;
+  const int i = (int)blockIdx.x * OX + tx - 1;
+  const int j = TY > 1 ? (int)blockIdx.y * OY + ty - 1 : 0;
   const int kl0 = blockIdx.z * TZ, kl1 = min(kl0 + TZ, L.nzl);
-  const bool in = i < L.NX && j < L.NY;
-  const bool xl = in && i > 0, xh = in && i + 1 < L.NX, yl = in && L.has_y && j > 0, yh = in && L.has_y && j + 1 < L.NY;
-#define GS(idx) (sp.two_phase ? frac_flow_of(ph, Sin[idx]) : Sin[idx])
-  long c = ix_c(L, in ? i : 0, in ? j : 0, kl0 + 1);
-  double f_lo = (in && kl0 + L.zlo > 0) ? GS(c - L.plane) : 0.0;
-  double f_c = in ? GS(c) : 0.0;
-  for (int kl = kl0; kl < kl1; ++kl, c += L.plane) {
-    const int k = kl + L.zlo, kk = kl + 1;
-    const bool zl = in && k > 0, zh = in && k + 1 < L.NZ;
-    const double f_hi = zh ? GS(c + L.plane) : 0.0;
-    fs[ty + 1][tx + 1] = f_c;
-    if (tx == 0) fs[ty + 1][0] = xl ? GS(c - 1) : 0.0;
-    if (tx == TX - 1) fs[ty + 1][TX + 1] = xh ? GS(c + 1) : 0.0;
-    if (TY > 1 || L.has_y) {
-      if (ty == 0) fs[0][tx + 1] = yl ? GS(c - L.NX) : 0.0;
-      if (ty == TY - 1) fs[TY + 1][tx + 1] = yh ? GS(c + L.NX) : 0.0;
-    }
+  const bool in = i >= 0 && i < L.NX && j >= 0 && j < L.NY;                                  // cell exists
+  const bool upd = in && tx >= 1 && tx <= OX && (TY == 1 || (ty >= 1 && ty <= OY));          // tile interior
+  const bool xl = i > 0, xh = i + 1 < L.NX, yl = L.has_y && j > 0, yh = L.has_y && j + 1 < L.NY;
+#define GS(v) (sp.two_phase ? frac_flow_of(ph, (v)) : (v))
+  const long plane = L.plane;
+  const long c0 = ix_c(L, in ? i : 0, in ? j : 0, kl0 + 1);
+  const double* Sp = Sin + c0;
+  double f_lo = (in && kl0 + L.zlo > 0) ? GS(Sp[-plane]) : 0.0;
+  double s_c = in ? Sp[0] : 0.0;
+  double f_c = in ? GS(s_c) : 0.0;
+  // running pointers of this column (advance one plane per iteration)
+  const long sxp = (long)(L.NX + 1) * L.NY, syp = (long)L.NX * (L.NY + 1);
+  const double* uxp = u + ix_ux(L, in ? i : 0, in ? j : 0, kl0);
+  const double* uyp = u + (L.has_y ? ix_uy(L, in ? i : 0, in ? j : 0, kl0) : 0);
+  const double* uzp = u + ix_uz(L, in ? i : 0, in ? j : 0, kl0 + 1);
+  const double* php = phi + c0;
+  double* Op = Sout + c0;
+  // injection-box membership of the column (SaturationSourceCoefficient [REF src/param.hpp:382-406]);
+  // the plane-dependent part of the test is done per plane
+  const double px = (i + 0.5) * sp.hx, py = (j + 0.5) * sp.hy;
+  const bool col_in = sp.well_2d ? (fabs(px - sp.inj_c0) <= sp.inj_r)
+                                 : (fabs(px - sp.inj_c0) <= sp.inj_r && py >= sp.inj_c1 && py <= sp.inj_c1 + sp.inj_h);
+  const double zc = sp.well_2d ? sp.inj_c1 : sp.inj_c2;
+  int b = 0;
+  for (int kl = kl0; kl < kl1; ++kl) {
+    const int k = kl + L.zlo;
+    const bool zl = k > 0, zh = k + 1 < L.NZ;
+    const double s_hi = (in && zh) ? Sp[plane] : 0.0;
+    const double f_hi = (in && zh) ? GS(s_hi) : 0.0;
+    fs[b][ty][tx] = f_c;
     __syncthreads();
-    if (in) {
-      const double Fxl = xl ? u[ix_ux(L, i, j, kl)] : 0.0, Fxh = xh ? u[ix_ux(L, i + 1, j, kl)] : 0.0;
-      const double Fyl = yl ? u[ix_uy(L, i, j, kl)] : 0.0, Fyh = yh ? u[ix_uy(L, i, j + 1, kl)] : 0.0;
-      const double Fzl = zl ? u[ix_uz(L, i, j, kk)] : 0.0, Fzh = zh ? u[ix_uz(L, i, j, kk + 1)] : 0.0;
+    if (upd) {
+      const double Fxl = xl ? uxp[0] : 0.0, Fxh = xh ? uxp[1] : 0.0;
+      const double Fyl = yl ? uyp[0] : 0.0, Fyh = yh ? uyp[L.NX] : 0.0;
+      const double Fzl = zl ? uzp[0] : 0.0, Fzh = zh ? uzp[plane] : 0.0;
 #define FPOS(F) ((F) > 0.0 ? (F) : 0.0)
 #define FNEG(F) ((F) < 0.0 ? (F) : 0.0)
       double z = 0.0;
       if (zl) z += FPOS(Fzl) * f_lo;
-      if (yl) z += FPOS(Fyl) * fs[ty][tx + 1];
-      if (xl) z += FPOS(Fxl) * fs[ty + 1][tx];
+      if (yl) z += FPOS(Fyl) * fs[b][TY > 1 ? ty - 1 : 0][tx];
+      if (xl) z += FPOS(Fxl) * fs[b][ty][tx - 1];
       {
         double dg = 0.0;
         if (xl) dg += FNEG(Fxl);
@@ -966,23 +989,24 @@ __global__ void __launch_bounds__(TX* TY) k_sat_tile(Lay L, Phys ph, SatParam sp
         if (zh) dg += -FPOS(Fzh);
         z += dg * f_c;
       }
-      if (xh) z += (-FNEG(Fxh)) * fs[ty + 1][tx + 2];
-      if (yh) z += (-FNEG(Fyh)) * fs[ty + 2][tx + 1];
+      if (xh) z += (-FNEG(Fxh)) * fs[b][ty][tx + 1];
+      if (yh) z += (-FNEG(Fyh)) * fs[b][TY > 1 ? ty + 1 : 0][tx];
       if (zh) z += (-FNEG(Fzh)) * f_hi;
 #undef FPOS
 #undef FNEG
-      z += sat_source(sp, i, j, k) * sp.vol;
-      double yv = z / (phi[c] * sp.vol);
+      const double src = (col_in && fabs((k + 0.5) * sp.hz - zc) <= sp.inj_r) ? sp.src : 0.;
+      z += src * sp.vol;
+      double yv = z / (php[0] * sp.vol);
       if (RATE) {
-        Sout[c] = yv;
+        Op[0] = yv;
       } else {
         yv *= sp.dt;
-        Sout[c] = Sin[c] + yv;
+        Op[0] = s_c + yv;
       }
     }
-    __syncthreads();
-    f_lo = f_c;
-    f_c = f_hi;
+    b ^= 1;
+    f_lo = f_c; f_c = f_hi; s_c = s_hi;
+    Sp += plane; php += plane; Op += plane; uxp += sxp; uyp += syp; uzp += plane;
   }
 #undef GS
 }

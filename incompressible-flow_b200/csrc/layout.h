@@ -39,6 +39,9 @@ struct Lay {
 struct Phys {
   int two_phase;
   double Sor, Swc, mu_w, mu_o;
+  // constant denominators of the rel-perm / fractional-flow formulas and their correctly rounded
+  // reciprocals (for div_exact): den = 1 - Sor - Swc
+  double den, rden, rmu_w, rmu_o;
 };
 
 #if defined(__CUDACC__)

@@ -105,6 +105,36 @@ def test_saturation_substeps_bit_exact(pkg, orc, native_lib, cfg, two_phase):
     s.close()
 
 
+def test_nontrivial_relperm_constants_bit_exact(pkg, orc, native_lib):
+    """Sor, Swc, mu_w, mu_o != trivial values: the GPU evaluates the constant-denominator divisions with
+    div_exact (reciprocal + FMA corrections), which must equal IEEE division bit for bit."""
+    cfg = dict(dim=3, nx=17, ny=9, nz=11)
+    d, o, s, n = make(pkg, orc, cfg, Sor=0.13, Swc=0.21, mu_w=0.7, mu_o=2.3)
+    o.set_arith(1)
+    S = np.random.default_rng(9).uniform(0.25, 0.8, n)
+    xo, sto, _ = o.pressure_solve(S)
+    xg, stg = s.pressure_solve(S)
+    assert stg.iterations == sto.iterations and np.array_equal(xg, xo)
+    So, _ = o.saturation_advance(xo[:o.nv], S, 6.0, 0.25)
+    Sg, _ = s.saturation_advance(xo[:o.nv], S, 1, 6.0, 0.25)
+    assert np.array_equal(Sg, So)
+    s.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(dim=2, nx=300, ny=7), dict(dim=3, nx=61, ny=13, nz=5), dict(dim=3, nx=30, ny=6, nz=40)])
+def test_saturation_tile_edges(pkg, orc, native_lib, cfg):
+    """Mesh sizes around the K6 tile geometry (30x6 interior of 32x8 tiles, 254 of 256 in 2-D, z-chunks)."""
+    d, o, s, n = make(pkg, orc, cfg)
+    o.set_arith(1)
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal(o.nv)
+    S0 = rng.uniform(0, 1, n)
+    So, _ = o.saturation_advance(u, S0, 0.02, 0.005)
+    Sg, _ = s.saturation_advance(u, S0, 1, 0.02, 0.005)
+    assert np.array_equal(Sg, So)
+    s.close()
+
+
 @pytest.mark.parametrize("ode", [1, 2, 3, 4])
 def test_ode_variants_parallel_rule(pkg, orc, native_lib, ode):
     from incompressible_flow_b200 import abi

@@ -58,9 +58,10 @@ def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim):
     kfile = tmp_path / "K.bin"
     K32.tofile(kfile)
     out = tmp_path / "out"
+    dtg, dtl = (20.0, 1.0) if dim == 2 else (2.0, 0.125)
     h = 100.0 / nx
     common = ["-d", str(dim), "-nx", str(nx), "-ny", str(ny), "-nz", str(nz), "-sx", "100", "-sy", "100", "-sz", "100",
-              "-ov", "0", "-op", "0", "-os", "0", "-two-phase", "-tf", "60", "-dtg", "20", "-dtl", "1", "-vsg", "0",
+              "-ov", "0", "-op", "0", "-os", "0", "-two-phase", "-tf", str(3 * dtg), "-dtg", str(dtg), "-dtl", str(dtl), "-vsg", "0",
               "-K-file-x", str(kfile), "-K-file-y", str(kfile), "-K-file-z", str(kfile), "-outdir", str(out),
               "-extra", "t", "-darcy-maxiter", "5000"]
     if dim == 2:
@@ -83,7 +84,7 @@ def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim):
     S, its_o = np.zeros(n), []
     for ti in range(1, 4):
         x, st, rc = oc.pressure_solve(S)
-        S, _ = oc.saturation_advance(x[:oc.nv], S, 20.0, 1.0)
+        S, _ = oc.saturation_advance(x[:oc.nv], S, dtg, dtl)
         its_o.append(st.iterations)
         dump = np.fromfile(out / f"saturation_t_{dim}D_2phase_{ti:06d}.bin", dtype=np.float32)
         assert np.array_equal(dump, S.astype(np.float32))
