@@ -48,6 +48,8 @@ struct impes_ctx {
   double* K[3] = {nullptr, nullptr, nullptr};
   double* phi = nullptr;
   double* S[2] = {nullptr, nullptr};
+  double* F[2] = {nullptr, nullptr};  // f(S) carried beside S (streaming K6)
+  int sat_mode = 0;                   // 0 streaming (fs array), 1 tiled, 2 simple
   int scur = 0;
   double* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // RK stage buffers (lazy)
   double* m[3] = {nullptr, nullptr, nullptr};
@@ -541,11 +543,26 @@ int n_substeps(const impes_ctx* h, double global_dt, double dt) {
   return (int)(global_dt / dt);  // [REF src/saturation_solver.cpp:74-75]
 }
 
+// f(S) over the whole cvec (after the ghost planes of S are in place)
+int launch_frac(impes_ctx* h, const double* S, double* F) {
+  Scope sc(h, KC_SAT, 1);
+  const int g = (int)((h->L.ncv + BLK - 1) / BLK);
+  k_frac_flow<<<g, BLK, 0, h->stream>>>(h->L, h->ph, h->sp.two_phase, S, F);
+  return 0;
+}
+
 // one K6 launch: rate = false: Sout = Sin + dt*F(Sin);  rate = true: Sout = F(Sin)
-int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout) {
+// Fin / Fout: f(S) arrays of the streaming form (Fin must hold f(Sin) incl. ghost planes); ignored otherwise.
+int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout, const double* Fin = nullptr,
+               double* Fout = nullptr) {
   Scope sc(h, KC_SAT, 1);
   const Lay& L = h->L;
-  if (h->sat_simple) {
+  if (h->sat_mode == 0) {
+    if (rate) k_sat_stream<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+    else k_sat_stream<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+    return 0;
+  }
+  if (h->sat_mode == 2) {
     if (rate) k_sat_substep<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Sout);
     else k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Sout);
     return 0;
@@ -564,6 +581,10 @@ int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout) {
 
 int sat_rate(impes_ctx* h, double* Sin, double* out) {  // out = M_phi^-1 (Kt f(Sin) + b)
   RET_IF(exchange_planes(h, Sin, true, true));
+  if (h->sat_mode == 0) {
+    RET_IF(launch_frac(h, Sin, h->F[0]));
+    return launch_sat(h, true, Sin, out, h->F[0], nullptr);
+  }
   return launch_sat(h, true, Sin, out);
 }
 int axpby(impes_ctx* h, double a, const double* x, double b, const double* y, double* out) {
@@ -595,8 +616,19 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
     double* S = h->S[h->scur];
     double* Sn = h->S[h->scur ^ 1];
     if (ode == 1) {
-      RET_IF(exchange_planes(h, S, true, true));
-      RET_IF(launch_sat(h, false, S, Sn));
+      if (h->sat_mode == 0) {
+        // f(S) travels with S: F[scur] = f(S[scur]); only its ghost planes are exchanged per sub-step
+        if (ti == 1) {
+          RET_IF(exchange_planes(h, S, true, true));
+          RET_IF(launch_frac(h, S, h->F[h->scur]));
+        } else {
+          RET_IF(exchange_planes(h, h->F[h->scur], true, true));
+        }
+        RET_IF(launch_sat(h, false, S, Sn, h->F[h->scur], h->F[h->scur ^ 1]));
+      } else {
+        RET_IF(exchange_planes(h, S, true, true));
+        RET_IF(launch_sat(h, false, S, Sn));
+      }
       h->scur ^= 1;
     } else if (ode == 2) {  // RK2Solver(a = 1)
       const double a = 1.0, bb = 0.5 / a;
@@ -699,7 +731,7 @@ API void impes_destroy(impes_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->minres_exec) cudaGraphExecDestroy(h->minres_exec);
   if (h->comm) h->nccl.CommDestroy(h->comm);
-  double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->stage[0], h->stage[1], h->stage[2],
+  double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
                     h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb};
   for (double* p : ptrs)
@@ -873,6 +905,8 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
 
   {  // K6 tiling: enough blocks for >= 2 waves when the mesh allows it
     if (const char* e = getenv("IMPES_SAT_SIMPLE")) h->sat_simple = atoi(e) != 0;
+    if (const char* e = getenv("IMPES_SAT_MODE")) h->sat_mode = atoi(e);
+    if (h->sat_simple) h->sat_mode = 2;
     const long tiles = L.has_y ? (long)((L.NX + 29) / 30) * ((L.NY + 5) / 6) : (long)((L.NX + 253) / 254);
     long tz = (tiles * L.nzl) / (2L * h->num_sms);
     h->sat_tz = (int)std::max<long>(1, std::min<long>(16, tz));
@@ -894,6 +928,8 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   }
   RET_IF(dev_alloc(h, &h->S[0], L.ncv));
   RET_IF(dev_alloc(h, &h->S[1], L.ncv));
+  RET_IF(dev_alloc(h, &h->F[0], L.ncv));
+  RET_IF(dev_alloc(h, &h->F[1], L.ncv));
   double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
   for (double** v : vecs) RET_IF(dev_alloc(h, v, L.ntot));
   {  // Md = 1 everywhere first (padding and ghost entries must stay harmless under division)
@@ -1134,6 +1170,8 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
   CK(cudaEventCreate(&e1));
   const bool prof = h->profiling;
   h->profiling = false;
+  if (kernel == IMPES_KERNEL_SAT_SUBSTEP && h->sat_mode == 0)  // f(S) is carried between sub-steps
+    RET_IF(launch_frac(h, h->S[h->scur], h->F[h->scur]));
   for (int r = -2; r < reps; ++r) {  // 2 untimed warm-ups
     if (flush_l2) k_fill<<<h->num_sms * 4, 512, 0, h->stream>>>(h->flushbuf, h->flush_n, (double)r);
     CK(cudaEventRecord(e0, h->stream));
@@ -1141,7 +1179,7 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
       case IMPES_KERNEL_DARCY_APPLY: RET_IF(darcy_apply(h, h->u1, h->q, true, nullptr)); break;
       case IMPES_KERNEL_SAT_SUBSTEP:
         h->sp.dt = 0.0;  // dt = 0: the state is not disturbed by repeated timing launches
-        RET_IF(launch_sat(h, false, h->S[h->scur], h->S[h->scur ^ 1]));
+        RET_IF(launch_sat(h, false, h->S[h->scur], h->S[h->scur ^ 1], h->F[h->scur], h->F[h->scur ^ 1]));
         break;
       case IMPES_KERNEL_MINRES_UPDATE: {
         Scope sc(h, KC_MINRES, 2);
