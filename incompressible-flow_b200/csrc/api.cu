@@ -792,14 +792,21 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     L.nzl = base + (d.rank < rem ? 1 : 0);
     L.zhi = L.zlo + L.nzl;
   }
-  L.plane = (long)L.NX * L.NY;
-  L.ncl = L.plane * L.nzl;
-  L.ncv = L.plane * (L.nzl + 2);
-  L.off_x = 0;
-  L.off_y = pad32(L.off_x + (long)(L.NX + 1) * L.NY * L.nzl);
-  L.off_z = L.has_y ? pad32(L.off_y + (long)L.NX * (L.NY + 1) * L.nzl) : L.off_y;
-  L.off_p = pad32(L.off_z + L.plane * (L.nzl + 2));
-  L.ntot = pad32(L.off_p + L.plane * (L.nzl + 2));
+  {  // all per-rank element offsets must fit 32-bit ints (layout.h)
+    const long plane = (long)L.NX * L.NY;
+    const long off_y = pad32((long)(L.NX + 1) * L.NY * L.nzl);
+    const long off_z = L.has_y ? pad32(off_y + (long)L.NX * (L.NY + 1) * L.nzl) : off_y;
+    const long off_p = pad32(off_z + plane * (L.nzl + 2));
+    const long ntot = pad32(off_p + plane * (L.nzl + 2));
+    if (ntot >= (1L << 31) - 64) {
+      h->err = "slab too large: more than 2^31 Darcy dofs per GPU (use more GPUs)";
+      return IMPES_ERR_UNSUPPORTED;
+    }
+    L.plane = (int)plane;
+    L.ncl = (int)(plane * L.nzl);
+    L.ncv = (int)(plane * (L.nzl + 2));
+    L.off_x = 0; L.off_y = (int)off_y; L.off_z = (int)off_z; L.off_p = (int)off_p; L.ntot = (int)ntot;
+  }
   L.nblk = (int)((L.ncl + BLK - 1) / BLK);
   h->g_ncell = L.plane * L.NZ;
   h->g_nvx = (long)(L.NX + 1) * L.NY * L.NZ;
@@ -809,13 +816,32 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   h->g_np = h->g_ncell;
   h->ph.two_phase = d.two_phase; h->ph.Sor = d.Sor; h->ph.Swc = d.Swc; h->ph.mu_w = d.mu_w; h->ph.mu_o = d.mu_o;
   h->ph.den = 1. - d.Sor - d.Swc; h->ph.rden = 1.0 / h->ph.den; h->ph.rmu_w = 1.0 / d.mu_w; h->ph.rmu_o = 1.0 / d.mu_o;
-  if (L.ncl >= (1L << 32) || L.ntot >= (1L << 40)) { h->err = "slab too large for 32-bit cell indexing"; return IMPES_ERR_UNSUPPORTED; }
+  h->ph.unit_den = (d.Swc == 0.0 && h->ph.den == 1.0) ? 1 : 0;
+  h->ph.unit_mu = (d.mu_w == 1.0 && d.mu_o == 1.0) ? 1 : 0;
   SatParam& sp = h->sp;
   sp.two_phase = d.two_phase; sp.dt = 0; sp.vol = h->vol;
   sp.hx = h->h[0]; sp.hy = h->h[1]; sp.hz = h->h[2];
   sp.well_2d = d.dim == 2;
   sp.inj_c0 = d.injection.center[0]; sp.inj_c1 = d.injection.center[1]; sp.inj_c2 = d.injection.center[2];
   sp.inj_r = d.injection.radius; sp.inj_h = d.injection.height; sp.src = d.saturation_source;
+  {  // injection box as inclusive internal index ranges: the per-axis predicates of
+     // SaturationSourceCoefficient::eval2D/3D [REF src/param.hpp:382-406] evaluated at the cell centres
+    auto range = [](int n, auto pred, int& lo, int& hi) {
+      lo = n; hi = -1;
+      for (int q = 0; q < n; ++q)
+        if (pred(q)) { if (lo == n) lo = q; hi = q; }
+      if (hi < 0) { lo = 1; hi = 0; }
+    };
+    range(L.NX, [&](int q) { return fabs((q + 0.5) * sp.hx - sp.inj_c0) <= sp.inj_r; }, sp.bi0, sp.bi1);
+    if (d.dim == 2) {
+      sp.bj0 = 0; sp.bj1 = 0;
+      range(L.NZ, [&](int q) { return fabs((q + 0.5) * sp.hz - sp.inj_c1) <= sp.inj_r; }, sp.bk0, sp.bk1);
+    } else {
+      range(L.NY, [&](int q) { const double py = (q + 0.5) * sp.hy; return py >= sp.inj_c1 && py <= sp.inj_c1 + sp.inj_h; },
+            sp.bj0, sp.bj1);
+      range(L.NZ, [&](int q) { return fabs((q + 0.5) * sp.hz - sp.inj_c2) <= sp.inj_r; }, sp.bk0, sp.bk1);
+    }
+  }
 
   h->grid_cells = L.nblk;
   h->grid_vec = (int)std::min<long>((L.ntot + BLK - 1) / BLK, (long)h->num_sms * 8);

@@ -85,28 +85,40 @@ __device__ __forceinline__ double div_exact(double n, double D, double rD) {
 // Divisions by the run-time constants (1 - Sor - Swc), mu_w, mu_o go through div_exact with host-computed
 // reciprocals: same bits as `/`, a fifth of the instructions.
 // ---------------------------------------------------------------------------------------
+// (S - Swc)/(1 - Sor - Swc); with Swc = 0 and denominator 1 both operations are exact identities and are skipped
+__device__ __forceinline__ double s_eff(const Phys& ph, double S) {
+  return ph.unit_den ? S : div_exact(S - ph.Swc, ph.den, ph.rden);
+}
 __device__ __forceinline__ double krw_of(const Phys& ph, double S) {
   if (ph.two_phase) {
-    const double S_ = div_exact(S - ph.Swc, ph.den, ph.rden);
+    const double S_ = s_eff(ph, S);
     return S_ * S_;
   }
   return S;
 }
 __device__ __forceinline__ double kro_of(const Phys& ph, double S) {
   if (ph.two_phase) {
-    const double S_ = div_exact(S - ph.Swc, ph.den, ph.rden);
+    const double S_ = s_eff(ph, S);
     return (1. - S_) * (1. - S_);
   }
   return (1. - S);
 }
+// phase mobilities Krw/mu_w, Kro/mu_o (x/1.0 is x exactly: skipped for the reference's mu = 1)
+__device__ __forceinline__ void mobilities(const Phys& ph, double S, double& mw, double& mo) {
+  const double kw = krw_of(ph, S), ko = kro_of(ph, S);
+  if (ph.unit_mu) { mw = kw; mo = ko; }
+  else { mw = div_exact(kw, ph.mu_w, ph.rmu_w); mo = div_exact(ko, ph.mu_o, ph.rmu_o); }
+}
 // total mobility lambda = Krw/mu_w + Kro/mu_o   (CWVectorCoefficient::Eval [REF src/param.hpp:252-254])
 __device__ __forceinline__ double lambda_of(const Phys& ph, double S) {
-  return div_exact(krw_of(ph, S), ph.mu_w, ph.rmu_w) + div_exact(kro_of(ph, S), ph.mu_o, ph.rmu_o);
+  double mw, mo;
+  mobilities(ph, S, mw, mo);
+  return mw + mo;
 }
 // FS  [REF src/saturation_solver.cpp:8-17]
 __device__ __forceinline__ double frac_flow_of(const Phys& ph, double S) {
-  const double mw = div_exact(krw_of(ph, S), ph.mu_w, ph.rmu_w);
-  const double mo = div_exact(kro_of(ph, S), ph.mu_o, ph.rmu_o);
+  double mw, mo;
+  mobilities(ph, S, mw, mo);
   return mw / (mw + mo);
 }
 
@@ -858,7 +870,13 @@ struct SatParam {
   double hx, hy, hz;   // internal spacings
   int well_2d;         // injection box test in (x, internal z) only (2-D) or 3-D rule
   double inj_c0, inj_c1, inj_c2, inj_r, inj_h, src;
+  // the same box as inclusive INTERNAL cell-index ranges (cell centres tested on the host with the formulas of
+  // sat_source; membership is monotone along each axis); empty box: lo > hi
+  int bi0, bi1, bj0, bj1, bk0, bk1;
 };
+__device__ __forceinline__ double sat_source_box(const SatParam& sp, int i, int j, int k) {
+  return (i >= sp.bi0 && i <= sp.bi1 && j >= sp.bj0 && j <= sp.bj1 && k >= sp.bk0 && k <= sp.bk1) ? sp.src : 0.;
+}
 
 __device__ __forceinline__ double sat_source(const SatParam& sp, int i, int j, int k) {
   // SaturationSourceCoefficient::eval2D/eval3D at the cell centre [REF src/param.hpp:382-406]
@@ -1033,41 +1051,39 @@ __global__ void __launch_bounds__(BLK) k_sat_stream(Lay L, Phys ph, SatParam sp,
   const CellIdx ci = owned_cell(L);
   if (!ci.ok) return;
   const int i = ci.i, j = ci.j, kl = ci.kl, k = ci.k, kk = kl + 1;
-  const long c = ix_c(L, i, j, kk);
+  const int c = ix_c(L, i, j, kk);
   const bool xl = i > 0, xh = i + 1 < L.NX, yl = L.has_y && j > 0, yh = L.has_y && j + 1 < L.NY, zl = k > 0,
              zh = k + 1 < L.NZ;
-  const long fx = ix_ux(L, i, j, kl), fz = ix_uz(L, i, j, kk);
+  const int fx = ix_ux(L, i, j, kl), fz = ix_uz(L, i, j, kk);
   const double Fxl = xl ? u[fx] : 0.0, Fxh = xh ? u[fx + 1] : 0.0;
   double Fyl = 0.0, Fyh = 0.0;
   if (L.has_y) {
-    const long fy = ix_uy(L, i, j, kl);
+    const int fy = ix_uy(L, i, j, kl);
     Fyl = yl ? u[fy] : 0.0;
     Fyh = yh ? u[fy + L.NX] : 0.0;
   }
   const double Fzl = zl ? u[fz] : 0.0, Fzh = zh ? u[fz + L.plane] : 0.0;
   const double f_c = Fin[c];
-#define FPOS(F) ((F) > 0.0 ? (F) : 0.0)
-#define FNEG(F) ((F) < 0.0 ? (F) : 0.0)
+  // (F)+ = max(F,0), (F)- = min(F,0); identical to the compare/select form up to the sign of a zero, which
+  // cannot reach the result (zeros only enter sums that start from +0)
   double z = 0.0;
-  if (zl) z += FPOS(Fzl) * Fin[c - L.plane];
-  if (yl) z += FPOS(Fyl) * Fin[c - L.NX];
-  if (xl) z += FPOS(Fxl) * Fin[c - 1];
+  if (zl) z += fmax(Fzl, 0.0) * Fin[c - L.plane];
+  if (yl) z += fmax(Fyl, 0.0) * Fin[c - L.NX];
+  if (xl) z += fmax(Fxl, 0.0) * Fin[c - 1];
   {
     double dg = 0.0;
-    if (xl) dg += FNEG(Fxl);
-    if (xh) dg += -FPOS(Fxh);
-    if (yl) dg += FNEG(Fyl);
-    if (yh) dg += -FPOS(Fyh);
-    if (zl) dg += FNEG(Fzl);
-    if (zh) dg += -FPOS(Fzh);
+    if (xl) dg += fmin(Fxl, 0.0);
+    if (xh) dg += -fmax(Fxh, 0.0);
+    if (yl) dg += fmin(Fyl, 0.0);
+    if (yh) dg += -fmax(Fyh, 0.0);
+    if (zl) dg += fmin(Fzl, 0.0);
+    if (zh) dg += -fmax(Fzh, 0.0);
     z += dg * f_c;
   }
-  if (xh) z += (-FNEG(Fxh)) * Fin[c + 1];
-  if (yh) z += (-FNEG(Fyh)) * Fin[c + L.NX];
-  if (zh) z += (-FNEG(Fzh)) * Fin[c + L.plane];
-#undef FPOS
-#undef FNEG
-  z += sat_source(sp, i, j, k) * sp.vol;
+  if (xh) z += (-fmin(Fxh, 0.0)) * Fin[c + 1];
+  if (yh) z += (-fmin(Fyh, 0.0)) * Fin[c + L.NX];
+  if (zh) z += (-fmin(Fzh, 0.0)) * Fin[c + L.plane];
+  z += sat_source_box(sp, i, j, k) * sp.vol;
   double yv = z / (phi[c] * sp.vol);
   if (RATE) {
     Sout[c] = yv;

@@ -26,11 +26,12 @@ struct Lay {
   int has_y;           // 0 for 2-D problems
   int zlo, zhi, nzl;   // owned cell planes [zlo, zhi)
   int rank, nranks;
-  long plane;          // NX*NY
-  long off_x, off_y, off_z, off_p;  // component offsets inside a dvec
-  long ntot;           // padded dvec length
-  long ncl;            // owned cells = nzl*plane
-  long ncv;            // cvec length = (nzl+2)*plane
+  // all element offsets fit in 32 bits (a dvec per rank is < 2^31 doubles = 16 GiB; checked at create)
+  int plane;           // NX*NY
+  int off_x, off_y, off_z, off_p;  // component offsets inside a dvec
+  int ntot;            // padded dvec length
+  int ncl;             // owned cells = nzl*plane
+  int ncv;             // cvec length = (nzl+2)*plane
   int nblk;            // blocks of 256 owned cells (canonical reduction granularity)
 };
 
@@ -42,6 +43,8 @@ struct Phys {
   // constant denominators of the rel-perm / fractional-flow formulas and their correctly rounded
   // reciprocals (for div_exact): den = 1 - Sor - Swc
   double den, rden, rmu_w, rmu_o;
+  int unit_den;  // Swc == 0 and den == 1: (S - Swc)/den is S exactly
+  int unit_mu;   // mu_w == mu_o == 1 (the reference's compile-time values): x/mu is x exactly
 };
 
 #if defined(__CUDACC__)
@@ -50,13 +53,13 @@ struct Phys {
 #define IMPES_HD inline
 #endif
 
-IMPES_HD long ix_ux(const Lay& L, int i, int j, int kl) { return L.off_x + i + (long)(L.NX + 1) * (j + (long)L.NY * kl); }
-IMPES_HD long ix_uy(const Lay& L, int i, int j, int kl) { return L.off_y + i + (long)L.NX * (j + (long)(L.NY + 1) * kl); }
+IMPES_HD int ix_ux(const Lay& L, int i, int j, int kl) { return L.off_x + i + (L.NX + 1) * (j + L.NY * kl); }
+IMPES_HD int ix_uy(const Lay& L, int i, int j, int kl) { return L.off_y + i + L.NX * (j + (L.NY + 1) * kl); }
 // kk = (face plane) - zlo + 1
-IMPES_HD long ix_uz(const Lay& L, int i, int j, int kk) { return L.off_z + i + (long)L.NX * (j + (long)L.NY * kk); }
+IMPES_HD int ix_uz(const Lay& L, int i, int j, int kk) { return L.off_z + i + L.NX * (j + L.NY * kk); }
 // kk = (cell plane) - zlo + 1
-IMPES_HD long ix_p(const Lay& L, int i, int j, int kk) { return L.off_p + i + (long)L.NX * (j + (long)L.NY * kk); }
-IMPES_HD long ix_c(const Lay& L, int i, int j, int kk) { return i + (long)L.NX * (j + (long)L.NY * kk); }
+IMPES_HD int ix_p(const Lay& L, int i, int j, int kk) { return L.off_p + i + L.NX * (j + L.NY * kk); }
+IMPES_HD int ix_c(const Lay& L, int i, int j, int kk) { return i + L.NX * (j + L.NY * kk); }
 
 // MINRES scalar recurrence state, device resident (double buffered by iteration parity).
 struct MinresState {
