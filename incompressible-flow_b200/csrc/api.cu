@@ -72,6 +72,7 @@ struct impes_ctx {
   bool sgs_skew = false;                // stage-major (skewed) sweep available for this shape
   int sgs_ppt = 1;
   bool sgs_tma = false;                 // one-CTA TMA ring version (<= 1024 pencils)
+  bool sgs_flow = false;                // 2-D warp-dataflow version (no block barrier)
   int sgs_ns = 0;
   size_t sgs_smem = 0;
   SgsPack pack = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
@@ -320,7 +321,7 @@ int launch_skew_sweep(impes_ctx* h, double* y, int fwd, int bwd, const MinresSta
 
 template <int NPS, bool HY>
 void launch_sgs_tma_t(impes_ctx* h, double* y, int fwd, int bwd, const MinresState* st) {
-  k_sgs_tma<NPS, HY><<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(h->L, h->pack, h->T, y, h->sgs_ns, h->sgs_yp, fwd,
+  k_sgs_tma<NPS, HY><<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(h->L, h->pack, h->T, y, getenv("IMPES_SGS_NOSTORE") ? -h->sgs_ns : h->sgs_ns, getenv("IMPES_SGS_NOTMA") ? -h->sgs_yp : h->sgs_yp, fwd,
                                                                     bwd, st);
 }
 void launch_sgs_tma(impes_ctx* h, double* y, int fwd, int bwd, const MinresState* st) {
@@ -341,7 +342,9 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
   if (h->sgs_skew) {
     Scope sc(h, KC_PREC, 2 + (fwd ? 1 : 0));
     if (fwd) k_sgs_skew_in<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, r, st);
-    if (h->sgs_tma)
+    if (h->sgs_flow)
+      k_sgs_flow2d<<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(L, h->pack, T, y, fwd, bwd, st);
+    else if (h->sgs_tma)
       launch_sgs_tma(h, y, fwd, bwd, st);
     else if (h->sgs_mode == 0) RET_IF(launch_skew_sweep<0>(h, y, fwd, bwd, st));
     else RET_IF(launch_skew_sweep<1>(h, y, fwd, bwd, st));
@@ -880,6 +883,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
         const size_t ybytes = 2 * (row + 2 * (size_t)h->sgs_yp * 8);
         int ns = (int)((200 * 1024 - ybytes) / (7 * row));
         ns = std::min(ns, 8);
+        if (const char* e = getenv("IMPES_SGS_NS")) ns = std::min(ns, std::max(4, atoi(e)));
         if (ns >= 4) {
           h->sgs_tma = true;
           h->sgs_ns = ns;
@@ -897,6 +901,21 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
           CK(cudaFuncSetAttribute(k_sgs_tma<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
           CK(cudaFuncSetAttribute(k_sgs_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
           CK(cudaFuncSetAttribute(k_sgs_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        }
+      }
+      {
+        // warp-dataflow variant (no block barrier): bit-identical, but measured slower than the TMA ring
+        // kernel on B200 (485 vs 258 ns per stage on C2) -- opt-in only
+        bool flow = false;
+        if (const char* e = getenv("IMPES_SGS_FLOW")) flow = atoi(e) != 0 && !L.has_y && npair <= 512;
+        if (flow) {
+          h->sgs_flow = true;
+          h->sgs_tma = false;
+          h->sgs_mode = 0;
+          h->grid_sgs = 1;
+          h->sgs_threads = (int)((npair + 31) / 32 * 32);
+          h->sgs_smem = (size_t)(h->sgs_threads / 32) * FLOW_PD * FLOW_NOP * 32 * sizeof(double);
+          CK(cudaFuncSetAttribute(k_sgs_flow2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sgs_smem));
         }
       }
       RET_IF(dev_alloc(h, &h->pack_blk, nstage * h->pack.SS));

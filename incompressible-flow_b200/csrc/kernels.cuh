@@ -722,6 +722,9 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
                                                   int YP, int do_fwd, int do_bwd, const MinresState* st) {
   if (st && st->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int NSa = NS < 0 ? -NS : NS;  // NS < 0: timing experiment without the per-stage global store
+  const bool no_tma = YP < 0;         // YP < 0: timing experiment without the producer's TMA traffic
+  YP = YP < 0 ? -YP : YP;
   const int NPs = NPS_T > 0 ? NPS_T : P.NPs;
   const int NY = HAS_Y_T ? L.NY : 1;
   const int NP = NY * L.nzl;
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
   const int nstage = L.NX + NY + L.nzl - 2;
   const int YR = NPs + 2 * YP;                                                               // ybuf row length
   double* ring = reinterpret_cast<double*>(smem_raw);                                        // [NS][7][NPs]
-  double* ybuf = ring + (size_t)NS * SS;                                                     // [2][YR]
+  double* ybuf = ring + (size_t)NSa * SS;                                                     // [2][YR]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ybuf + (size_t)2 * YR);   // [NS]
   const bool producer = threadIdx.x < 32;
   const int p = (int)threadIdx.x - 32;
@@ -742,13 +745,13 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
   const bool in_lo = pk > 0, in_hi = pk + 1 < L.nzl, has_jlo = HAS_Y_T && pj > 0, has_jhi = HAS_Y_T && pj + 1 < NY;
   double* yp = y + L.off_p;
   const unsigned rowb = (unsigned)NPs * 8u;
-  const int ringn = NS * SS;
+  const int ringn = NSa * SS;
 
   // ring and ybuf start as zeros: never-loaded slots / padding must hold finite values (they only ever meet
   // zero coefficients)
   for (int q = threadIdx.x; q < ringn + 2 * YR; q += blockDim.x) ring[q] = 0.0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+    for (int s = 0; s < NSa; ++s) mbar_init(bars + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -770,12 +773,12 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
       mbar_expect_tx(bar, bytes);
       bulk_g2s(ring + is_slot * SS, is_src, bytes, bar);
       is_src += gstep;
-      is_slot = is_slot + 1 == NS ? 0 : is_slot + 1;
+      is_slot = is_slot + 1 == NSa ? 0 : is_slot + 1;
       ++n_issued;
     };
     auto wait1 = [&]() {
       mbar_wait(bars + wt_slot, wt_par);
-      if (wt_slot + 1 == NS) { wt_slot = 0; wt_par ^= 1u; }
+      if (wt_slot + 1 == NSa) { wt_slot = 0; wt_par ^= 1u; }
       else ++wt_slot;
       ++n_waited;
     };
@@ -786,15 +789,15 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
       __syncthreads();
       if (threadIdx.x == 0) asm volatile("fence.proxy.async;" ::: "memory");
     }
-    if (threadIdx.x == 0) {
-      while (n_issued < NS - 2 && n_issued < nstage) issue1();
+    if (threadIdx.x == 0 && !no_tma) {
+      while (n_issued < NSa - 2 && n_issued < nstage) issue1();
       wait1();
       if (nstage > 1) wait1();
     }
     __syncthreads();
     if (producer) {
       for (int n = 0; n < nstage; ++n) {
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && !no_tma) {
           // the slot of iteration n-2 is free (last read, as upper-face rows, during n-1)
           if (n_issued < nstage) issue1();
           if (n_waited < nstage) wait1();
@@ -816,7 +819,7 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
           sum += yadj[0] * nx;
           const double v = div_exact(R - sum, D, rD);
           ycur[0] = v;
-          *gout = v;
+          if (NS > 0) *gout = v;
         }
         __syncthreads();
         gout += SS;
@@ -846,7 +849,7 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
           sum += yu * hz;
           const double v = div_exact(R - sum, D, rD);
           ycur[0] = v;
-          *gout = v;
+          if (NS > 0) *gout = v;
         }
         __syncthreads();
         gout -= NPs;
@@ -854,6 +857,202 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
         par ^= 1;
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 (warp-dataflow path, 2-D meshes, one CTA): no block barrier at all.  Pencil p = row k runs along x;
+// cell (i, p) is computed at stage d = i + p by lane p%32 of warp p/32.  It needs its own previous value
+// (register), the previous-stage value of pencil p-1 (forward) / p+1 (backward): a __shfl from the neighbouring
+// lane, or -- for the first / last lane of a warp -- a value the neighbouring warp left in a small shared ring,
+// guarded by that warp's progress counter.  Each warp streams through its own stage range at its own pace,
+// one stage behind its predecessor; operands (coalesced 256 B rows of the skewed block layout) are prefetched
+// PD stages ahead into a register ring.  Per-stage critical path: shuffle + 8 dependent fp64 ops.
+// Same per-cell arithmetic as every other variant (bit-identical result).
+// ---------------------------------------------------------------------------------------
+constexpr int FLOW_R = 32;   // depth of the cross-warp exchange rings (stages)
+constexpr int FLOW_PD = 6;   // operand prefetch distance (stages)
+constexpr int FLOW_NOP = 8;  // operand slots per stage and lane: R, D, rD, nx, nz, fx, fz, hz
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_volatile_s32(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Dynamic shared memory: per-warp operand ring  opnd[warp][FLOW_PD][FLOW_NOP][32]  (each lane only ever reads
+// what it copied itself, so no cross-lane synchronisation is needed for it).
+__global__ void __launch_bounds__(512) k_sgs_flow2d(Lay L, SgsPack P, const double* __restrict__ T, double* y,
+                                                    int do_fwd, int do_bwd, const MinresState* st) {
+  if (st && st->done) return;
+  extern __shared__ __align__(16) double opnd_all[];
+  __shared__ double xr[2][17][FLOW_R];  // [dir][receiving warp][stage % R]
+  __shared__ int prog[2][18];           // [dir][warp + 1]: stages completed (index 0 / nw+1: sentinels)
+  const int NP = L.nzl, NX = L.NX, SS = P.SS, NPs = P.NPs;
+  const int nstage = NX + NP - 1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (NP + 31) >> 5;
+  const int p = threadIdx.x;
+  const bool pv = p < NP;
+  const int k = p + L.zlo;
+  const bool ghost_lo = pv && p == 0 && k > 0;                  // multi-rank: row below lives on another GPU
+  const bool ghost_hi = pv && p + 1 == NP && k + 1 < L.NZ;      // multi-rank: row above lives on another GPU
+  double* yp = y + L.off_p;
+  double* opnd = opnd_all + (size_t)w * FLOW_PD * FLOW_NOP * 32 + lane;   // [u][op] at opnd[(u*NOP+op)*32]
+  // progress counters start at "everything outside my stage range is done": forward counts completed stages
+  // upwards from 0, backward counts them downwards from nstage-1
+  if (threadIdx.x < 18) {
+    const int t = threadIdx.x, wq = t - 1;
+    const bool sentinel = t == 0 || t >= nw + 1;
+    prog[0][t] = sentinel ? (1 << 30) : 32 * wq;
+    prog[1][t] = sentinel ? (1 << 30) : nstage - 1 - (min(32 * wq + 31, NP - 1) + NX - 1);
+  }
+  __syncthreads();
+  if (w >= nw) return;
+  const int d_lo = 32 * w, d_hi = min(32 * w + 31, NP - 1) + NX - 1;  // stage range in which this warp has work
+  const int pc = pv ? p : NP - 1;                                       // clamped pencil for address safety
+
+  if (do_fwd) {
+    const double* base = P.Rs + pc;
+    auto issue = [&](int u, int d) {  // operands of stage d -> ring position u (clamped: inactive lanes load junk)
+      const int dc = min(max(d, 0), nstage - 1);
+      const double* q = base + (size_t)dc * SS;
+      double* o = opnd + (size_t)u * FLOW_NOP * 32;
+      cp_async8(o + 0 * 32, q);
+      cp_async8(o + 1 * 32, q + NPs);
+      cp_async8(o + 2 * 32, q + 2 * NPs);
+      cp_async8(o + 3 * 32, q + 3 * NPs);
+      cp_async8(o + 4 * 32, q + 4 * NPs);
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int u = 0; u < FLOW_PD; ++u) issue(u, d_lo + u);
+    double yown = 0.0;  // value of this pencil at the previous stage
+    double* gout = P.Yf + p + (size_t)d_lo * SS;
+    for (int d0 = d_lo; d0 <= d_hi; d0 += FLOW_PD) {
+#pragma unroll
+      for (int u = 0; u < FLOW_PD; ++u) {
+        const int d = d0 + u;
+        if (d <= d_hi) {
+          const int i = d - p;
+          const bool act = pv && (unsigned)i < (unsigned)NX;
+          cp_async_wait<FLOW_PD - 1>();
+          const double* o = opnd + (size_t)u * FLOW_NOP * 32;
+          const double oR = o[0], oD = o[32], orD = o[64], onx = o[96], onz = o[128];
+          // wait until the warp below has finished stage d-1 (and the warp above has consumed the ring slot
+          // this stage overwrites)
+          if (w > 0 || w + 1 < nw) {
+            const int need_lo = d, need_hi = d - FLOW_R + 2;
+            while (true) {
+              const int a0 = lane == 0 ? ld_volatile_s32(&prog[0][w]) - need_lo
+                                       : (lane == 1 ? ld_volatile_s32(&prog[0][w + 2]) - need_hi : 0);
+              if (__all_sync(0xffffffffu, a0 >= 0)) break;
+            }
+            asm volatile("" ::: "memory");
+          }
+          double left = __shfl_up_sync(0xffffffffu, yown, 1);
+          if (lane == 0) left = w > 0 ? *reinterpret_cast<const volatile double*>(&xr[0][w][(d - 1) & (FLOW_R - 1)]) : 0.0;
+          if (ghost_lo && act) left = __ldcg(yp + ix_c(L, i, 0, 0));
+          double sum = left * onz;
+          sum += yown * onx;
+          const double v = div_exact(oR - sum, oD, orD);
+          if (act) {
+            yown = v;
+            *gout = v;
+          }
+          // value, then flag, by the same thread: shared-memory stores of one thread are observed in order
+          if (lane == 31) {
+            if (w + 1 < nw) *reinterpret_cast<volatile double*>(&xr[0][w + 1][d & (FLOW_R - 1)]) = v;
+            st_volatile_s32(&prog[0][w + 1], d + 1);
+          }
+          gout += SS;
+          issue(u, d + FLOW_PD);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    if (lane == 31) st_volatile_s32(&prog[0][w + 1], 1 << 29);  // done: never block a neighbour again
+  }
+  if (do_bwd) {
+    // the forward results of all warps must be complete (and visible) before they are read as F rows
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
+    // operands of stage d: R, D, rD, nx, nz, fx = Yf(d-1,p), fz = Yf(d-1,p-1), hz = -Tz_lo(d+1,p+1);
+    // hx (upper x face of stage d) is nx of stage d+1: kept from the previous iteration
+    const double* base = P.Rs + pc;
+    auto issue = [&](int u, int d) {
+      const int dc = min(max(d, 0), nstage - 1);
+      const double* q = base + (size_t)dc * SS;
+      const double* f = base + (size_t)max(dc - 1, 0) * SS + 5 * NPs;
+      const double* hq = base + (size_t)min(dc + 1, nstage - 1) * SS + 4 * NPs + (pc + 1 < NP ? 1 : 0);
+      double* o = opnd + (size_t)u * FLOW_NOP * 32;
+      cp_async8(o + 0 * 32, q);
+      cp_async8(o + 1 * 32, q + NPs);
+      cp_async8(o + 2 * 32, q + 2 * NPs);
+      cp_async8(o + 3 * 32, q + 3 * NPs);
+      cp_async8(o + 4 * 32, q + 4 * NPs);
+      cp_async8(o + 5 * 32, f);
+      cp_async8(o + 6 * 32, f - (pc > 0 ? 1 : 0));
+      cp_async8(o + 7 * 32, hq);
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int u = 0; u < FLOW_PD; ++u) issue(u, d_hi - u);
+    double yown = 0.0, nx_prev = 0.0;  // stage d+1: own new value, own -Tx_lo
+    double* gout = P.Yb + p + (size_t)d_hi * NPs;
+    for (int d0 = d_hi; d0 >= d_lo; d0 -= FLOW_PD) {
+#pragma unroll
+      for (int u = 0; u < FLOW_PD; ++u) {
+        const int d = d0 - u;
+        if (d >= d_lo) {
+          const int i = d - p;
+          const bool act = pv && (unsigned)i < (unsigned)NX;
+          cp_async_wait<FLOW_PD - 1>();
+          const double* o = opnd + (size_t)u * FLOW_NOP * 32;
+          const double oR = o[0], oD = o[32], orD = o[64], onx = o[96], onz = o[128];
+          const double ofx = i > 0 ? o[160] : 0.0, ofz = p > 0 ? o[192] : 0.0;
+          double hz = (pv && p + 1 < NP) ? o[224] : 0.0;  // -Tz_lo of cell (i, p+1)
+          if (w > 0 || w + 1 < nw) {
+            // the warp above must have finished stage d+1: it counts completed stages downwards from nstage
+            const int need_hi = nstage - 1 - d, need_lo = need_hi - FLOW_R + 2;
+            while (true) {
+              const int a0 = lane == 0 ? ld_volatile_s32(&prog[1][w + 2]) - need_hi
+                                       : (lane == 1 ? ld_volatile_s32(&prog[1][w]) - need_lo : 0);
+              if (__all_sync(0xffffffffu, a0 >= 0)) break;
+            }
+            asm volatile("" ::: "memory");
+          }
+          double up = __shfl_down_sync(0xffffffffu, yown, 1);       // new value of pencil p+1 at stage d+1
+          if (lane == 31) up = w + 1 < nw ? *reinterpret_cast<const volatile double*>(&xr[1][w][(d + 1) & (FLOW_R - 1)]) : 0.0;
+          if (ghost_hi && act) {
+            up = __ldcg(yp + ix_c(L, i, 0, NP + 1));
+            hz = -T[ix_uz(L, i, 0, NP + 1)];
+          }
+          const double fz = (ghost_lo && act) ? __ldcg(yp + ix_c(L, i, 0, 0)) : ofz;
+          double sum = fz * onz;
+          sum += ofx * onx;
+          sum += yown * ((i + 1 < NX) ? nx_prev : 0.0);
+          sum += up * hz;
+          const double v = div_exact(oR - sum, oD, orD);
+          if (act) {
+            yown = v;
+            *gout = v;
+          }
+          nx_prev = onx;
+          if (lane == 0) {
+            if (w > 0) *reinterpret_cast<volatile double*>(&xr[1][w - 1][d & (FLOW_R - 1)]) = v;
+            st_volatile_s32(&prog[1][w + 1], nstage - d);
+          }
+          gout -= NPs;
+          issue(u, d - FLOW_PD);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    if (lane == 0) st_volatile_s32(&prog[1][w + 1], 1 << 29);
   }
 }
 
