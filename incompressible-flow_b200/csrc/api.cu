@@ -20,6 +20,7 @@
 
 #include "../../include/impes_b200.h"
 #include "kernels.cuh"
+#include "mg.cuh"
 #include "nccl_shim.h"
 
 using namespace impes;
@@ -82,6 +83,13 @@ struct impes_ctx {
   bool use_graph = true;
   cudaGraphExec_t minres_exec = nullptr;
   int graph_iters = 0;
+  // multigrid Schur preconditioner (IMPES_SCHUR_MG)
+  std::vector<MgLevel> mg;
+  std::vector<double*> mg_bufs;
+  double mg_omega = 0.8, mg_cfac = 2.0;
+  int mg_nu = 2, mg_coarse_sweeps = 16;
+  long long graph_launches = 0;
+  long long graph_prof_n[KC_N] = {0};
   // multi-GPU
   NcclShim nccl;
   ncclComm_t comm = nullptr;
@@ -274,6 +282,15 @@ int update_coeff(impes_ctx* h) {
     Scope sc(h, KC_COEFF, 1);
     k_sgs_pack<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, h->T, h->Md);
   }
+  if (!h->mg.empty()) {  // multigrid hierarchy of the Schur stencil (S depends on the saturation)
+    auto grid_of = [](const MgLevel& v) { return (int)(((long)v.nx * v.ny * v.nz + MG_B - 1) / MG_B); };
+    Scope sc(h, KC_COEFF, 1 + 2 * ((int)h->mg.size() - 1));
+    k_mg_copy_fine<<<grid_of(h->mg[0]), MG_B, 0, h->stream>>>(L, h->mg[0], h->T, h->Md);
+    for (size_t l = 1; l < h->mg.size(); ++l) {
+      k_mg_coarsen<<<grid_of(h->mg[l]), MG_B, 0, h->stream>>>(h->mg[l - 1], h->mg[l]);
+      k_mg_diag<<<grid_of(h->mg[l]), MG_B, 0, h->stream>>>(h->mg[l]);
+    }
+  }
   CK(cudaGetLastError());
   h->coeff_valid = true;
   return 0;
@@ -374,14 +391,46 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
   return 0;
 }
 
+// One V(nu,nu) cycle, zero initial guess: y_p = MG(r_p)  (mg.cuh).  Iterates alternate between ya and yb of
+// each level; all sweep counts are even, so every level's result ends in yb (level 0: the p-part of y).
+int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
+  const Lay& L = h->L;
+  std::vector<MgLevel>& mg = h->mg;
+  const int nl = (int)mg.size();
+  mg[0].r = const_cast<double*>(r) + L.off_p + L.plane;
+  mg[0].yb = y + L.off_p + L.plane;
+  auto grid_of = [](const MgLevel& v) { return (int)(((long)v.nx * v.ny * v.nz + MG_B - 1) / MG_B); };
+  auto smooth = [&](int l, int sweeps, bool from_zero) {
+    MgLevel& v = mg[l];
+    for (int s = 0; s < sweeps; ++s) {
+      // sweep s reads (s even ? yb : ya) and writes (s even ? ya : yb); with from_zero the first read is skipped
+      const double* in = (s & 1) ? v.ya : v.yb;
+      double* out = (s & 1) ? v.yb : v.ya;
+      k_mg_jacobi<<<grid_of(v), MG_B, 0, h->stream>>>(v, v.r, in, out, h->mg_omega, from_zero && s == 0, st);
+    }
+  };
+  int n = 0;
+  for (int l = 0; l + 1 < nl; ++l) {
+    smooth(l, h->mg_nu, true);
+    k_mg_restrict<<<grid_of(mg[l + 1]), MG_B, 0, h->stream>>>(mg[l], mg[l + 1], mg[l].r, mg[l].yb, mg[l + 1].r, st);
+    n += h->mg_nu + 1;
+  }
+  smooth(nl - 1, h->mg_coarse_sweeps, true);
+  n += h->mg_coarse_sweeps;
+  for (int l = nl - 2; l >= 0; --l) {
+    k_mg_prolong<<<grid_of(mg[l]), MG_B, 0, h->stream>>>(mg[l], mg[l + 1], mg[l + 1].yb, mg[l].yb, h->mg_cfac, st);
+    smooth(l, h->mg_nu, false);
+    n += h->mg_nu + 1;
+  }
+  Scope sc(h, KC_PREC, n);
+  return 0;
+}
+
 // y_p = SchurPrec(r_p).  Parity mode: lexicographic symmetric GS; across slabs the sweep is pipelined
 // rank by rank (exact global ordering, so results do not depend on the number of GPUs).
 int schur_prec(impes_ctx* h, const double* r, double* y, const MinresState* st) {
   const Lay& L = h->L;
-  if (h->d.schur_prec != IMPES_SCHUR_SGS_LEX) {
-    h->err = "schur_prec: only IMPES_SCHUR_SGS_LEX is implemented";
-    return IMPES_ERR_UNSUPPORTED;
-  }
+  if (h->d.schur_prec == IMPES_SCHUR_MG) return mg_vcycle(h, r, y, st);
   if (L.nranks == 1) return launch_sgs(h, r, y, 1, 1, st);
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   double* yp = y + L.off_p;
@@ -444,6 +493,8 @@ int build_minres_graph(impes_ctx* h) {
   int rc = 0;
   for (int p = 0; p < pairs && !rc; ++p) rc = minres_pair(h);
   cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  h->graph_launches = h->launches - l0;  // what one replay of the graph launches
+  for (int c = 0; c < KC_N; ++c) h->graph_prof_n[c] = h->prof_n[c] - n0[c];
   h->launches = l0;  // capture is not execution
   memcpy(h->prof_n, n0, sizeof n0);
   if (rc || e != cudaSuccess || !g) {
@@ -500,12 +551,8 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
       printf("MINRES: iteration %3d: ||r||_B = %g\n", hs.it, fabs(hs.eta));
     if (h->minres_exec && !h->profiling) {
       CK(cudaGraphLaunch(h->minres_exec, h->stream));
-      const long long per_iter = h->sgs_skew ? 7 : 5;
-      h->launches += per_iter * h->graph_iters;
-      h->prof_n[KC_DARCY] += h->graph_iters;
-      h->prof_n[KC_MINRES] += 2 * h->graph_iters;
-      h->prof_n[KC_PREC] += (h->sgs_skew ? 3 : 1) * h->graph_iters;
-      h->prof_n[KC_DOT] += h->graph_iters;
+      h->launches += h->graph_launches;
+      for (int c = 0; c < KC_N; ++c) h->prof_n[c] += h->graph_prof_n[c];
     } else {
       for (int p = 0; p < 4; ++p) RET_IF(minres_pair(h));
     }
@@ -739,6 +786,8 @@ API void impes_destroy(impes_handle h) {
                     h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb};
   for (double* p : ptrs)
     if (p) cudaFree(p);
+  for (double* b : h->mg_bufs)
+    if (b) cudaFree(b);
   if (h->ticket) cudaFree(h->ticket);
   if (h->st) cudaFree(h->st);
   if (h->guard) cudaFree(h->guard);
@@ -980,6 +1029,27 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   {  // Md = 1 everywhere first (padding and ghost entries must stay harmless under division)
     k_fill<<<h->grid_vec, BLK, 0, h->stream>>>(h->Md, L.ntot, 1.0);
     h->launches++;
+  }
+  if (d.schur_prec == IMPES_SCHUR_MG) {
+    if (L.nranks > 1) { h->err = "IMPES_SCHUR_MG: multi-GPU multigrid is not implemented yet"; return IMPES_ERR_UNSUPPORTED; }
+    if (d.mg_smooth > 0) h->mg_nu = (d.mg_smooth + 1) / 2 * 2;  // even sweep counts (see mg_vcycle)
+    int nx = L.NX, ny = L.NY, nz = L.NZ;
+    for (int l = 0; l < 24; ++l) {
+      MgLevel v;
+      memset(&v, 0, sizeof v);
+      v.nx = nx; v.ny = ny; v.nz = nz;
+      const long nc = (long)nx * ny * nz;
+      double** arrs[] = {&v.Tx, &v.Ty, &v.Tz, &v.D, &v.ya};
+      const long sizes[] = {(long)(nx + 1) * ny * nz, (long)nx * (ny + 1) * nz, (long)nx * ny * (nz + 1), nc, nc};
+      for (int a = 0; a < 5; ++a) { RET_IF(dev_alloc(h, arrs[a], sizes[a])); h->mg_bufs.push_back(*arrs[a]); }
+      if (l > 0) {
+        RET_IF(dev_alloc(h, &v.r, nc)); h->mg_bufs.push_back(v.r);
+        RET_IF(dev_alloc(h, &v.yb, nc)); h->mg_bufs.push_back(v.yb);
+      }
+      h->mg.push_back(v);
+      if (nx <= 4 && ny <= 4 && nz <= 4) break;
+      nx = (nx + 1) / 2; ny = ny > 1 ? (ny + 1) / 2 : 1; nz = (nz + 1) / 2;
+    }
   }
   RET_IF(dev_alloc(h, &h->partial, L.nblk + 8));
   RET_IF(dev_alloc(h, &h->scal, 8));

@@ -149,6 +149,38 @@ def test_ode_variants_parallel_rule(pkg, orc, native_lib, ode):
     s.close()
 
 
+MG_CASES = [dict(dim=2, nx=33, ny=21), dict(dim=2, nx=128, ny=96), dict(dim=3, nx=12, ny=9, nz=7),
+            dict(dim=3, nx=30, ny=44, nz=17), dict(dim=2, nx=3, ny=2)]
+
+
+@pytest.mark.parametrize("cfg", MG_CASES)
+def test_multigrid_mode_bit_exact(pkg, orc, native_lib, cfg):
+    """Throughput mode (IMPES_SCHUR_MG): the V-cycle preconditioner and the whole MINRES solve equal the
+    oracle's restatement of the same algorithm bit for bit; the converged solution agrees with the reference
+    algorithm's (SGS-preconditioned) one to solver tolerance."""
+    from incompressible_flow_b200 import abi
+    d, o, s, n = make(pkg, orc, cfg, schur_prec=abi.SCHUR_MG)
+    o.set_arith(1)
+    rng = np.random.default_rng(21)
+    S = rng.uniform(0.0, 0.9, n)
+    x = rng.standard_normal(o.nv + o.np_)
+    s.update_coefficients(S)
+    o.update_coefficients(S)
+    assert np.array_equal(s.prec_apply(x), o.prec_apply(x))
+    xo, sto, _ = o.pressure_solve(S)
+    xg, stg = s.pressure_solve(S)
+    assert stg.converged == 1 and stg.iterations == sto.iterations
+    assert np.array_equal(xg, xo)
+    s.close()
+    # same discrete problem as the reference algorithm: solutions agree to solver tolerance
+    d2, o2, s2, _ = make(pkg, orc, cfg)
+    s2.close()
+    xr, str_, _ = o2.pressure_solve(S)
+    assert rel(xg[:o.nv], xr[:o.nv]) < 1e-4
+    if n > 1000:
+        assert stg.iterations < str_.iterations
+
+
 def test_unknown_ode_is_an_error(pkg, orc, native_lib):
     from incompressible_flow_b200 import abi
     d, o, s, n = make(pkg, orc, dict(dim=2, nx=8, ny=8), substep_rule=abi.SUBSTEPS_PARALLEL, ode_solver_type=5)

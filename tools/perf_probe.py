@@ -9,6 +9,8 @@ from incompressible_flow_b200 import workloads, abi
 NAMES = ["darcy", "minres", "prec", "sat", "coeff", "dot", "misc", "comm"]
 
 def probe(name, cfg, steps=2, breakdown=True, **kw):
+    if os.environ.get('PROBE_MG'):
+        kw['schur_prec'] = abi.SCHUR_MG
     d, Kx, Ky, Kz, phi = workloads.build(**cfg, **kw)
     n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
     with pkg.Solver(d, Kx, Ky, Kz, phi) as s:
