@@ -903,7 +903,8 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     if (const char* e = getenv("IMPES_SGS_CLUSTER")) csz = std::max(1, std::min(16, atoi(e)));
     bool skew = true;
     if (const char* e = getenv("IMPES_SGS_SKEW")) skew = atoi(e) != 0;
-    int mode = npair <= 4 * SGS_T ? 0 : 1;
+    // one CTA only when the TMA ring kernel applies (<= 992 pencils); otherwise a cluster (hardware barrier)
+    int mode = (npair + 31) / 32 * 32 + 32 <= 1024 ? 0 : 1;
     if (const char* e = getenv("IMPES_SGS_MODE")) mode = atoi(e);
     const long nstage = (long)L.NX + L.NY + L.nzl - 2;
     const long cap = (long)(mode == 0 ? 1 : csz) * SGS_T * 4;
