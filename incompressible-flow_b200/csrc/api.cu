@@ -21,6 +21,7 @@
 #include "../../include/impes_b200.h"
 #include "kernels.cuh"
 #include "mg.cuh"
+#include "rt1.cuh"
 #include "nccl_shim.h"
 
 using namespace impes;
@@ -38,6 +39,11 @@ enum { KC_DARCY = 0, KC_MINRES = 1, KC_PREC = 2, KC_SAT = 3, KC_COEFF = 4, KC_DO
 struct impes_ctx {
   impes_desc d;
   Lay L;
+  int ord = 0;           // 0: RT0/P0, 1: RT1/L2-Q1 (rt1.cuh); saturation DG_0 in both
+  Lay1 L1;               // dvec1 layout (ord == 1); L then only describes the cell arrays and the flux vector
+  Rt1Const rc;
+  int vec_n = 0, vec_offp = 0;  // length and p-offset of a Darcy-sized device vector in the active layout
+  double* flux0 = nullptr;      // ord == 1: face fluxes of x in the RT0 dvec layout (input of K6)
   Phys ph;
   SatParam sp;
   int dev = 0;
@@ -181,7 +187,47 @@ int download_cells_owned(impes_ctx* h, const double* dev, double* host) {
 
 // dvec from / to a global native Darcy vector [ux|uy|uz|p]; which: bit0 = velocity, bit1 = pressure.
 // Uploads fill the ghost planes from the (global) host array as well.
+int upload_dvec1(impes_ctx* h, const double* host_v, const double* host_p, double* dev) {
+  const Lay1& L = h->L1;
+  if (host_v) {
+    const long px = (long)L.gx0 * L.gx1, py = (long)L.gy0 * L.gy1, pz = (long)L.gz0 * L.gz1;
+    CK(cudaMemcpyAsync(dev + L.off_x, host_v + px * 2 * L.zlo, sizeof(double) * px * 2 * L.nzl, cudaMemcpyHostToDevice, h->stream));
+    if (L.has_y)
+      CK(cudaMemcpyAsync(dev + L.off_y, host_v + h->g_nvx + py * 2 * L.zlo, sizeof(double) * py * 2 * L.nzl,
+                         cudaMemcpyHostToDevice, h->stream));
+    const int g0 = std::max(2 * L.zlo - 2, 0), g1 = 2 * L.zhi + 1;  // node planes [g0, g1)
+    CK(cudaMemcpyAsync(dev + L.off_z + pz * (g0 - 2 * L.zlo + 2), host_v + h->g_nvx + h->g_nvy + pz * g0,
+                       sizeof(double) * pz * (g1 - g0), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (host_p) {
+    const int k0 = std::max(L.zlo - 1, 0), k1 = std::min(L.zhi + 1, L.NZ);
+    const long pp = (long)L.plane * L.npl;
+    CK(cudaMemcpyAsync(dev + L.off_p + pp * (k0 - L.zlo + 1), host_p + pp * k0, sizeof(double) * pp * (k1 - k0),
+                       cudaMemcpyHostToDevice, h->stream));
+  }
+  return 0;
+}
+int download_dvec1_owned(impes_ctx* h, const double* dev, double* host_v, double* host_p) {
+  const Lay1& L = h->L1;
+  if (host_v) {
+    const long px = (long)L.gx0 * L.gx1, py = (long)L.gy0 * L.gy1, pz = (long)L.gz0 * L.gz1;
+    CK(cudaMemcpyAsync(host_v + px * 2 * L.zlo, dev + L.off_x, sizeof(double) * px * 2 * L.nzl, cudaMemcpyDeviceToHost, h->stream));
+    if (L.has_y)
+      CK(cudaMemcpyAsync(host_v + h->g_nvx + py * 2 * L.zlo, dev + L.off_y, sizeof(double) * py * 2 * L.nzl,
+                         cudaMemcpyDeviceToHost, h->stream));
+    const int nf = 2 * L.nzl + (L.zhi == L.NZ ? 1 : 0);  // owned node planes (+ top boundary on the last rank)
+    CK(cudaMemcpyAsync(host_v + h->g_nvx + h->g_nvy + pz * 2 * L.zlo, dev + L.off_z + pz * 2, sizeof(double) * pz * nf,
+                       cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (host_p) {
+    const long pp = (long)L.plane * L.npl;
+    CK(cudaMemcpyAsync(host_p + pp * L.zlo, dev + L.off_p + pp, sizeof(double) * pp * L.nzl, cudaMemcpyDeviceToHost, h->stream));
+  }
+  return 0;
+}
+
 int upload_dvec(impes_ctx* h, const double* host_v, const double* host_p, double* dev) {
+  if (h->ord == 1) return upload_dvec1(h, host_v, host_p, dev);
   const Lay& L = h->L;
   if (host_v) {
     const long px = (long)(L.NX + 1) * L.NY, py = (long)L.NX * (L.NY + 1);
@@ -201,6 +247,7 @@ int upload_dvec(impes_ctx* h, const double* host_v, const double* host_p, double
   return 0;
 }
 int download_dvec_owned(impes_ctx* h, const double* dev, double* host_v, double* host_p) {
+  if (h->ord == 1) return download_dvec1_owned(h, dev, host_v, host_p);
   const Lay& L = h->L;
   if (host_v) {
     const long px = (long)(L.NX + 1) * L.NY, py = (long)L.NX * (L.NY + 1);
@@ -276,7 +323,12 @@ int update_coeff(impes_ctx* h) {
     const int g = (int)((L.ncv + BLK - 1) / BLK);
     k_cell_coeff<<<g, BLK, 0, h->stream>>>(L, h->ph, h->S[h->scur], h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1],
                                            h->geo[2], h->m[0], h->m[1], h->m[2]);
-    k_face_coeff<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->m[0], h->m[1], h->m[2], h->Md, h->T);
+    if (h->ord == 1) {
+      if (L.has_y) k1_node_coeff<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->m[0], h->m[1], h->m[2], h->Md, h->T);
+      else k1_node_coeff<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->m[0], h->m[1], h->m[2], h->Md, h->T);
+    } else {
+      k_face_coeff<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->m[0], h->m[1], h->m[2], h->Md, h->T);
+    }
   }
   if (h->sgs_skew) {
     Scope sc(h, KC_COEFF, 1);
@@ -298,6 +350,20 @@ int update_coeff(impes_ctx* h) {
 
 // ---- K1 ----------------------------------------------------------------------------------------
 int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState* st) {
+  if (h->ord == 1) {
+    {
+      Scope sc(h, KC_DARCY, 1);
+      const int g = h->grid_cells;
+#define K1_LAUNCH(HY, DOT)                                                                                        \
+  k1_darcy_apply<HY, DOT><<<g, BLK, 0, h->stream>>>(h->L1, h->rc, h->m[0], h->m[1], h->m[2], x, y, h->partial, \
+                                                    h->scal + 0, h->ticket, st)
+      if (h->L.has_y) { if (dot) K1_LAUNCH(true, true); else K1_LAUNCH(true, false); }
+      else { if (dot) K1_LAUNCH(false, true); else K1_LAUNCH(false, false); }
+#undef K1_LAUNCH
+    }
+    if (dot) RET_IF(allreduce_scalar(h, h->scal + 0));
+    return 0;
+  }
   RET_IF(halo_darcy(h, x));
   {
     Scope sc(h, KC_DARCY, 1);
@@ -352,7 +418,37 @@ void launch_sgs_tma(impes_ctx* h, double* y, int fwd, int bwd, const MinresState
   }
 }
 
+template <bool HY>
+int launch_sgs1(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const MinresState* st) {
+  Lay1 L = h->L1;
+  Rt1Const C = h->rc;
+  const double* T = h->T;
+  const double* Md = h->Md;
+  Scope sc(h, KC_PREC, 1);
+  if (h->sgs_mode == 2) {
+    void* args[] = {(void*)&L, (void*)&C, (void*)&T, (void*)&Md, (void*)&r, (void*)&y, (void*)&fwd, (void*)&bwd, (void*)&st};
+    CK(cudaLaunchCooperativeKernel((void*)k1_sgs_wavefront<2, HY>, dim3(h->grid_sgs), dim3(h->sgs_threads), args, 0, h->stream));
+  } else if (h->sgs_mode == 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->grid_sgs);
+    cfg.blockDim = dim3(h->sgs_threads);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = h->grid_sgs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k1_sgs_wavefront<1, HY>, L, C, T, Md, r, y, fwd, bwd, st));
+  } else {
+    k1_sgs_wavefront<0, HY><<<1, h->sgs_threads, 0, h->stream>>>(L, C, T, Md, r, y, fwd, bwd, st);
+  }
+  return 0;
+}
+
 int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const MinresState* st) {
+  if (h->ord == 1) return h->L.has_y ? launch_sgs1<true>(h, r, y, fwd, bwd, st) : launch_sgs1<false>(h, r, y, fwd, bwd, st);
   Lay L = h->L;
   const double* T = h->T;
   const double* Md = h->Md;
@@ -448,7 +544,11 @@ int schur_prec(impes_ctx* h, const double* r, double* y, const MinresState* st) 
 int dot_owned(impes_ctx* h, const double* a, const double* b, double* out, const MinresState* st) {
   {
     Scope sc(h, KC_DOT, 1);
-    k_dot_owned<<<h->grid_cells, BLK, 0, h->stream>>>(h->L, a, b, h->partial, out, h->ticket, st);
+    if (h->ord == 1) {
+      if (h->L.has_y) k1_dot_owned<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
+      else k1_dot_owned<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
+    } else
+      k_dot_owned<<<h->grid_cells, BLK, 0, h->stream>>>(h->L, a, b, h->partial, out, h->ticket, st);
   }
   return allreduce_scalar(h, out);
 }
@@ -456,17 +556,16 @@ int dot_owned(impes_ctx* h, const double* a, const double* b, double* out, const
 // one MINRES iteration with the given vector roles; reads st_cur, writes st_next
 int minres_iteration(impes_ctx* h, double* u1, double* q, double* v0, double* v1, double* w0, double* w1,
                      const MinresState* st_cur, MinresState* st_next) {
-  const Lay& L = h->L;
   RET_IF(darcy_apply(h, u1, q, true, st_cur));
   {
     Scope sc(h, KC_MINRES, 1);
-    k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, L.off_p, q, v0, v1, h->Md, q, h->scal + 0, st_cur);
+    k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, q, v0, v1, h->Md, q, h->scal + 0, st_cur);
   }
   RET_IF(schur_prec(h, v0, q, st_cur));
   RET_IF(dot_owned(h, v0, q, h->scal + 1, st_cur));
   {
     Scope sc(h, KC_MINRES, 1);
-    k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, w0, w1, u1, h->x, v0, q, h->scal + 0, h->scal + 1, st_cur,
+    k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, w0, w1, u1, h->x, v0, q, h->scal + 0, h->scal + 1, st_cur,
                                                    st_next, h->d.darcy_maxiter);
   }
   return 0;
@@ -514,14 +613,13 @@ int build_minres_graph(impes_ctx* h) {
 }
 
 int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
-  const Lay& L = h->L;
   auto t0 = std::chrono::steady_clock::now();
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, h->stream));
   RET_IF(update_coeff(h));
-  const size_t nb = sizeof(double) * (size_t)L.ntot;
+  const size_t nb = sizeof(double) * (size_t)h->vec_n;
   CK(cudaMemsetAsync(h->x, 0, nb, h->stream));   // x = 0  [REF src/pressure_solver.cpp:101]
   CK(cudaMemsetAsync(h->v0, 0, nb, h->stream));
   CK(cudaMemsetAsync(h->w0, 0, nb, h->stream));
@@ -531,13 +629,13 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
   CK(cudaMemcpyAsync(h->v1, h->rhs, nb, cudaMemcpyDeviceToDevice, h->stream));  // v1 = b - A*0
   {
     Scope sc(h, KC_PREC, 1);
-    k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(L.off_p, h->v1, h->Md, h->u1);
+    k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_offp, h->v1, h->Md, h->u1);
   }
   RET_IF(schur_prec(h, h->v1, h->u1, nullptr));
   RET_IF(dot_owned(h, h->u1, h->v1, h->scal + 1, nullptr));
   {
     Scope sc(h, KC_MINRES, 1);
-    k_minres_init<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, h->v1, h->u1, h->scal + 1, h->st + 0, h->d.darcy_rtol,
+    k_minres_init<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->v1, h->u1, h->scal + 1, h->st + 0, h->d.darcy_rtol,
                                                       h->d.darcy_atol);
   }
   CK(cudaGetLastError());
@@ -558,7 +656,7 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
     }
     CK(cudaGetLastError());
   }
-  RET_IF(halo_darcy(h, h->x));  // ghosts of the result (velocity ghost faces feed the saturation step)
+  if (h->ord == 0) RET_IF(halo_darcy(h, h->x));  // ghosts of the result (velocity ghost faces feed the saturation step)
   CK(cudaEventRecord(e1, h->stream));
   CK(cudaEventSynchronize(e1));
   float ms = 0;
@@ -607,24 +705,25 @@ int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout, const d
                double* Fout = nullptr) {
   Scope sc(h, KC_SAT, 1);
   const Lay& L = h->L;
+  const double* satv = h->ord == 1 ? h->flux0 : h->x;  // face fluxes in the RT0 dvec layout
   if (h->sat_mode == 0) {
-    if (rate) k_sat_stream<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
-    else k_sat_stream<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+    if (rate) k_sat_stream<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
+    else k_sat_stream<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
     return 0;
   }
   if (h->sat_mode == 2) {
-    if (rate) k_sat_substep<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Sout);
-    else k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, h->x, h->phi, Sin, Sout);
+    if (rate) k_sat_substep<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Sout);
+    else k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Sout);
     return 0;
   }
   if (L.has_y) {
     dim3 g((L.NX + 29) / 30, (L.NY + 5) / 6, (L.nzl + h->sat_tz - 1) / h->sat_tz);
-    if (rate) k_sat_tile<32, 8, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
-    else k_sat_tile<32, 8, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
+    if (rate) k_sat_tile<32, 8, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
+    else k_sat_tile<32, 8, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
   } else {
     dim3 g((L.NX + 253) / 254, 1, (L.nzl + h->sat_tz - 1) / h->sat_tz);
-    if (rate) k_sat_tile<256, 1, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
-    else k_sat_tile<256, 1, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, h->x, h->phi, Sin, Sout);
+    if (rate) k_sat_tile<256, 1, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
+    else k_sat_tile<256, 1, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
   }
   return 0;
 }
@@ -652,6 +751,11 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
   const int nt = n_substeps(h, global_dt, dt);
   if (nsub) *nsub = nt;
   h->sp.dt = dt;
+  if (h->ord == 1) {  // RT1 velocity -> face fluxes once per call (the velocity is frozen during the sub-steps)
+    Scope sc(h, KC_SAT, 1);
+    if (h->L.has_y) k1_face_flux<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
+    else k1_face_flux<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
+  }
   const int ode = h->d.substep_rule == IMPES_SUBSTEPS_SERIAL ? 1 : h->d.ode_solver_type;  // serial ignores -ode
   if (ode != 1 && ode != 2 && ode != 3 && ode != 4) {
     char b[128];
@@ -783,7 +887,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   for (double* b : h->mg_bufs)
@@ -804,10 +908,13 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   if (d.dim != 2 && d.dim != 3) { h->err = "dim must be 2 or 3"; return IMPES_ERR_BAD_ARG; }
   if (d.nx < 1 || d.ny < 1 || (d.dim == 3 && d.nz < 1)) { h->err = "grid sizes must be >= 1"; return IMPES_ERR_BAD_ARG; }
   if (!Kx || !Ky || (d.dim == 3 && !Kz)) { h->err = "permeability arrays missing"; return IMPES_ERR_BAD_ARG; }
-  if (d.order_v != 0 || d.order_p != 0 || d.order_s != 0) {
-    h->err = "only RT0/P0/P0 (-ov 0 -op 0 -os 0) is implemented on the GPU path so far";
+  if (d.order_v == 0 && d.order_p == 0 && d.order_s == 0) h->ord = 0;
+  else if (d.order_v == 1 && d.order_p == 1 && d.order_s == 0) h->ord = 1;
+  else {
+    h->err = "GPU path implements -ov 0 -op 0 -os 0 (RT0/P0/P0) and -ov 1 -op 1 -os 0 (RT1/Q1/P0, the reference default)";
     return IMPES_ERR_UNSUPPORTED;
   }
+  if (h->ord == 1 && d.world_size > 1) { h->err = "RT1/Q1: multi-GPU slabs are not implemented yet"; return IMPES_ERR_UNSUPPORTED; }
   if (d.world_size < 1 || d.rank < 0 || d.rank >= d.world_size) { h->err = "bad rank/world_size"; return IMPES_ERR_BAD_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -866,6 +973,44 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   h->g_nvz = L.plane * (L.NZ + 1);
   h->g_nv = h->g_nvx + h->g_nvy + h->g_nvz;
   h->g_np = h->g_ncell;
+  h->vec_n = L.ntot;
+  h->vec_offp = L.off_p;
+  if (h->ord == 1) {  // dvec1 layout (rt1.cuh)
+    Lay1& Q = h->L1;
+    Q.NX = L.NX; Q.NY = L.NY; Q.NZ = L.NZ; Q.has_y = L.has_y; Q.oy = L.has_y ? 2 : 1; Q.npl = 4 * Q.oy;
+    Q.zlo = L.zlo; Q.zhi = L.zhi; Q.nzl = L.nzl; Q.rank = L.rank; Q.nranks = L.nranks;
+    Q.plane = L.plane; Q.ncl = L.ncl; Q.nblk = L.nblk;
+    Q.gx0 = 2 * L.NX + 1; Q.gx1 = Q.oy * L.NY;
+    Q.gy0 = 2 * L.NX; Q.gy1 = 2 * L.NY + 1;
+    Q.gz0 = 2 * L.NX; Q.gz1 = Q.oy * L.NY;
+    const long nx_ = (long)Q.gx0 * Q.gx1 * 2 * L.nzl;
+    const long ny_ = L.has_y ? (long)Q.gy0 * Q.gy1 * 2 * L.nzl : 0;
+    const long nz_ = (long)Q.gz0 * Q.gz1 * (2 * L.nzl + 3);
+    const long np_ = (long)L.plane * (L.nzl + 2) * Q.npl;
+    const long off_y = pad32(nx_), off_z = pad32(off_y + ny_), off_p = pad32(off_z + nz_), ntot = pad32(off_p + np_);
+    if (ntot >= (1L << 31) - 64) {
+      h->err = "slab too large: more than 2^31 Darcy dofs per GPU (use more GPUs)";
+      return IMPES_ERR_UNSUPPORTED;
+    }
+    Q.off_x = 0; Q.off_y = (int)off_y; Q.off_z = (int)off_z; Q.off_p = (int)off_p; Q.ntot = (int)ntot;
+    h->g_nvx = (long)Q.gx0 * Q.gx1 * 2 * L.NZ;
+    h->g_nvy = L.has_y ? (long)Q.gy0 * Q.gy1 * 2 * L.NZ : 0;
+    h->g_nvz = (long)Q.gz0 * Q.gz1 * (2 * L.NZ + 1);
+    h->g_nv = h->g_nvx + h->g_nvy + h->g_nvz;
+    h->g_np = h->g_ncell * Q.npl;
+    h->vec_n = Q.ntot;
+    h->vec_offp = Q.off_p;
+    // reference-element constants, same expressions as the oracle's canonical arithmetic
+    static const int MCI[3][3] = {{4, 2, -1}, {2, 16, 2}, {-1, 2, 4}};
+    const double r3 = sqrt(3.0) / 3.0;
+    const double G[2][3] = {{-0.5 - r3, 2.0 * r3, 0.5 - r3}, {-0.5 + r3, -2.0 * r3, 0.5 + r3}};
+    const double wt = d.dim == 3 ? 0.25 : 0.5;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) h->rc.CW[i][j] = (MCI[i][j] / 30.0) * wt;
+    for (int a = 0; a < 2; ++a)
+      for (int i = 0; i < 3; ++i) h->rc.Bv[a][i] = -(G[a][i] * wt);
+    h->rc.wflux = wt;
+  }
   h->ph.two_phase = d.two_phase; h->ph.Sor = d.Sor; h->ph.Swc = d.Swc; h->ph.mu_w = d.mu_w; h->ph.mu_o = d.mu_o;
   h->ph.den = 1. - d.Sor - d.Swc; h->ph.rden = 1.0 / h->ph.den; h->ph.rmu_w = 1.0 / d.mu_w; h->ph.rmu_o = 1.0 / d.mu_o;
   h->ph.unit_den = (d.Swc == 0.0 && h->ph.den == 1.0) ? 1 : 0;
@@ -896,15 +1041,16 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   }
 
   h->grid_cells = L.nblk;
-  h->grid_vec = (int)std::min<long>((L.ntot + BLK - 1) / BLK, (long)h->num_sms * 8);
+  h->grid_vec = (int)std::min<long>(((long)h->vec_n + BLK - 1) / BLK, (long)h->num_sms * 8);
   {  // Schur sweep launch shape: the fewest SMs whose barrier is cheap enough
     const long npair = (long)L.NY * L.nzl;
     int csz = 8;
     if (const char* e = getenv("IMPES_SGS_CLUSTER")) csz = std::max(1, std::min(16, atoi(e)));
-    bool skew = true;
-    if (const char* e = getenv("IMPES_SGS_SKEW")) skew = atoi(e) != 0;
+    bool skew = h->ord == 0;  // the stage-major packed sweep exists for the RT0/P0 stencil only
+    if (const char* e = getenv("IMPES_SGS_SKEW")) skew = skew && atoi(e) != 0;
     // one CTA only when the TMA ring kernel applies (<= 992 pencils); otherwise a cluster (hardware barrier)
     int mode = (npair + 31) / 32 * 32 + 32 <= 1024 ? 0 : 1;
+    if (h->ord == 1 && npair > 8192) mode = 2;
     if (const char* e = getenv("IMPES_SGS_MODE")) mode = atoi(e);
     const long nstage = (long)L.NX + L.NY + L.nzl - 2;
     const long cap = (long)(mode == 0 ? 1 : csz) * SGS_T * 4;
@@ -984,14 +1130,22 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
         h->grid_sgs = 1;
         h->sgs_threads = (int)std::min<long>(1024, (npair + 31) / 32 * 32);
       } else if (mode == 1) {
-        if (csz > 8) CK(cudaFuncSetAttribute(k_sgs_wavefront<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        if (csz > 8) {
+          CK(cudaFuncSetAttribute(k_sgs_wavefront<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+          CK(cudaFuncSetAttribute(k1_sgs_wavefront<1, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+          CK(cudaFuncSetAttribute(k1_sgs_wavefront<1, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
         h->grid_sgs = csz;
         const long per = (npair + csz - 1) / csz;
         h->sgs_threads = (int)std::min<long>(1024, std::max<long>(32, (per + 31) / 32 * 32));
       } else {
         int per_sm = 0;
         h->sgs_threads = 256;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_wavefront<2>, 256, 0));
+        if (h->ord == 1) {
+          if (L.has_y) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_sgs_wavefront<2, true>, 256, 0));
+          else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_sgs_wavefront<2, false>, 256, 0));
+        } else
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgs_wavefront<2>, 256, 0));
         const long want = (npair + 255) / 256;
         h->grid_sgs = (int)std::max<long>(1, std::min<long>(want, (long)per_sm * h->num_sms));
       }
@@ -1026,13 +1180,15 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   RET_IF(dev_alloc(h, &h->F[0], L.ncv));
   RET_IF(dev_alloc(h, &h->F[1], L.ncv));
   double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
-  for (double** v : vecs) RET_IF(dev_alloc(h, v, L.ntot));
+  for (double** v : vecs) RET_IF(dev_alloc(h, v, h->vec_n));
+  if (h->ord == 1) RET_IF(dev_alloc(h, &h->flux0, L.ntot));
   {  // Md = 1 everywhere first (padding and ghost entries must stay harmless under division)
-    k_fill<<<h->grid_vec, BLK, 0, h->stream>>>(h->Md, L.ntot, 1.0);
+    k_fill<<<h->grid_vec, BLK, 0, h->stream>>>(h->Md, h->vec_n, 1.0);
     h->launches++;
   }
   if (d.schur_prec == IMPES_SCHUR_MG) {
     if (L.nranks > 1) { h->err = "IMPES_SCHUR_MG: multi-GPU multigrid is not implemented yet"; return IMPES_ERR_UNSUPPORTED; }
+    if (h->ord == 1) { h->err = "IMPES_SCHUR_MG: not implemented for RT1/Q1 yet"; return IMPES_ERR_UNSUPPORTED; }
     if (d.mg_smooth > 0) h->mg_nu = (d.mg_smooth + 1) / 2 * 2;  // even sweep counts (see mg_vcycle)
     int nx = L.NX, ny = L.NY, nz = L.NZ;
     for (int l = 0; l < 24; ++l) {
@@ -1070,6 +1226,23 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   CK(cudaMalloc((void**)&h->guard, sizeof(unsigned long long) * 2));
   {  // rhs (global, native) built on the host, uploaded slab-wise
     std::vector<double> g(h->g_np);
+    if (h->ord == 1) {
+      // Q1: DomainLFIntegrator's 2-point Gauss rule coincides with the L2 nodes => g_m = -Q(x_m) |cell| / 2^dim
+      // (SURVEY A.8); well membership is tested at the Gauss points [REF src/param.hpp:285-292]
+      const double g1 = 0.5 / sqrt(3.0);
+      const double node[2] = {0.5 - g1, 0.5 + g1};
+      const double wv = h->vol * (d.dim == 3 ? 0.125 : 0.25);
+      const int npl = h->L1.npl, nb2 = d.dim == 3 ? 2 : 1;
+      for (int kz = 0; kz < (d.dim == 3 ? d.nz : 1); ++kz)
+        for (int jy = 0; jy < d.ny; ++jy)
+          for (int ix = 0; ix < d.nx; ++ix)
+            for (int b2 = 0; b2 < nb2; ++b2)
+              for (int b1 = 0; b1 < 2; ++b1)
+                for (int b0 = 0; b0 < 2; ++b0) {
+                  const double p[3] = {(ix + node[b0]) * H[0], (jy + node[b1]) * H[1], d.dim == 3 ? (kz + node[b2]) * H[2] : 0.0};
+                  g[(ix + (long)d.nx * (jy + (long)d.ny * kz)) * npl + b0 + 2 * (b1 + 2 * b2)] = -(well_Q(d, p) * wv);
+                }
+    } else
     for (int kz = 0; kz < (d.dim == 3 ? d.nz : 1); ++kz)
       for (int jy = 0; jy < d.ny; ++jy)
         for (int ix = 0; ix < d.nx; ++ix) {
@@ -1240,7 +1413,7 @@ API int impes_darcy_apply(impes_handle h, const double* x_host, double* y_host) 
   if (!x_host || !y_host) return IMPES_ERR_BAD_ARG;
   if (!h->coeff_valid) RET_IF(update_coeff(h));
   RET_IF(upload_dvec(h, x_host, x_host + h->g_nv, h->tmpv));
-  CK(cudaMemsetAsync(h->q, 0, sizeof(double) * h->L.ntot, h->stream));
+  CK(cudaMemsetAsync(h->q, 0, sizeof(double) * h->vec_n, h->stream));
   RET_IF(darcy_apply(h, h->tmpv, h->q, false, nullptr));
   RET_IF(download_dvec_owned(h, h->q, y_host, y_host + h->g_nv));
   CK(cudaStreamSynchronize(h->stream));
@@ -1252,10 +1425,10 @@ API int impes_prec_apply(impes_handle h, const double* r_host, double* y_host) {
   if (!r_host || !y_host) return IMPES_ERR_BAD_ARG;
   if (!h->coeff_valid) RET_IF(update_coeff(h));
   RET_IF(upload_dvec(h, r_host, r_host + h->g_nv, h->tmpv));
-  CK(cudaMemsetAsync(h->q, 0, sizeof(double) * h->L.ntot, h->stream));
+  CK(cudaMemsetAsync(h->q, 0, sizeof(double) * h->vec_n, h->stream));
   {
     Scope sc(h, KC_PREC, 1);
-    k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->L.off_p, h->tmpv, h->Md, h->q);
+    k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_offp, h->tmpv, h->Md, h->q);
   }
   RET_IF(schur_prec(h, h->tmpv, h->q, nullptr));
   RET_IF(download_dvec_owned(h, h->q, y_host, y_host + h->g_nv));
@@ -1299,16 +1472,16 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
         break;
       case IMPES_KERNEL_MINRES_UPDATE: {
         Scope sc(h, KC_MINRES, 2);
-        k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, L.off_p, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
+        k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
                                                        h->st + 2);
-        k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(L.ntot, h->w0, h->w1, h->u1, h->tmpv, h->v0, h->q, h->scal + 2,
+        k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->w0, h->w1, h->u1, h->tmpv, h->v0, h->q, h->scal + 2,
                                                        h->scal + 3, h->st + 2, h->st + 3, 1 << 30);
         break;
       }
       case IMPES_KERNEL_PREC_APPLY: {
         {
           Scope sc(h, KC_PREC, 1);
-          k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(L.off_p, h->v1, h->Md, h->tmpv);
+          k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_offp, h->v1, h->Md, h->tmpv);
         }
         RET_IF(schur_prec(h, h->v1, h->tmpv, nullptr));
         break;

@@ -2,7 +2,7 @@
 // cycle on S = B diag(M)^-1 B^T, the same matrix the serial reference smooths with one symmetric Gauss-Seidel
 // sweep [REF src/pressure_solver.cpp:76-91] and the MPI reference hands to BoomerAMG
 // [REF src/par_pressure_solver.cpp:83-90].  BoomerAMG is neither available nor restatable, so this
-// mode is checked against the oracle's restatement of THIS algorithm (oracle/orc_mg.inc), bit for bit.
+// mode is checked against the oracle's restatement of THIS algorithm (the CPU checker under tests), bit for bit.
 //
 // S is a two-point-flux stencil: S[c,c'] = -T_f, S[c,c] = sum_f T_f.  Hierarchy: 2x2(x2) cell aggregates;
 // coarse transmissibility = sum of the fine ones across the aggregate interface (= Galerkin R S P with

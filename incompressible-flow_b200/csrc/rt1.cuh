@@ -1,0 +1,471 @@
+// rt1.cuh -- sm_100a kernels of the IMPES pressure path for RT1 / L2-Q1 (the reference's DEFAULT orders
+// `-ov 1 -op 1` [REF src/param.cpp:43]) on a Cartesian grid, saturation in DG_0 (`-os 0`).
+//
+// Discrete structure: with MFEM's nodal bases (closed = Gauss-Lobatto {0,1/2,1} along the
+// component's own direction, open = the 2 Gauss points transversally; L2-Q1 nodes = the same Gauss points)
+// and a cell-constant coefficient,
+//     M_d|cell = m_d * Mc (x) Mo (x) Mo,     B|cell,d = -G (x) Mo (x) Mo,     Mo = diag(1/2, 1/2),
+// i.e. every operator acts on LINES of nodes along d with fixed transverse open-node indices: a 3-node
+// quadratic mass block per cell and line, and two pressure dofs per cell and line.  Nothing is assembled.
+//
+// Layout ("dvec1", per rank; slab along internal z like layout.h; 2-D (nx, ny) is stored as (nx, 1, ny) with
+// one open node of weight 1 along the absent direction):
+//   ux : (2NX+1) x (oy NY) x (2 nzl)          node (2i+a, oy j+t1, 2 kl+t2)
+//   uy : (2NX) x (2NY+1) x (2 nzl)            (absent when !has_y)
+//   uz : (2NX) x (oy NY) x (2 nzl + 3)        node plane gz - 2 zlo + 2  (two ghost node planes below, one above)
+//   p  : (nzl + 2) cell planes x npl          cell-major, local index a0 + 2 (a1 + oy a2)   (= MFEM's L2 order)
+// which is the native host layout of include/impes_b200.h restricted to the slab, so transfers are
+// contiguous copies.  Arithmetic contract: as kernels.cuh (-fmad=false, CSR column order of the oracle).
+#pragma once
+#include "kernels.cuh"
+
+namespace impes {
+
+struct Lay1 {
+  int NX, NY, NZ, has_y, oy, npl;
+  int zlo, zhi, nzl, rank, nranks;
+  int plane, ncl, nblk;
+  int gx0, gx1, gy0, gy1, gz0, gz1;  // node-grid extents (x, y) of the three components
+  int off_x, off_y, off_z, off_p, ntot;
+};
+
+// Reference-element constants, already multiplied by the transverse open-node weights
+// wt = 1/4 (3-D) or 1/2 (2-D):  CW = Mc * wt,  Bv = -(G * wt).
+struct Rt1Const {
+  double CW[3][3];
+  double Bv[2][3];
+  double wflux;  // weight of one face node in the face flux: 1/4 (3-D), 1/2 (2-D)
+};
+
+struct Cell1 {
+  int i, j, kl, k, c, pb;  // c: cvec index (ghost plane below included), pb: index of the cell's first p dof
+  bool ok;
+};
+__device__ __forceinline__ Cell1 owned_cell1(const Lay1& L) {
+  Cell1 q;
+  const unsigned t = blockIdx.x * (unsigned)BLK + threadIdx.x;
+  q.ok = t < (unsigned)L.ncl;
+  const unsigned tt = q.ok ? t : 0u;
+  const unsigned r = tt / (unsigned)L.NX;
+  q.i = (int)(tt - r * (unsigned)L.NX);
+  q.kl = (int)(r / (unsigned)L.NY);
+  q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
+  q.k = q.kl + L.zlo;
+  q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+  q.pb = L.off_p + q.c * L.npl;
+  return q;
+}
+
+// Line geometry of one (cell, direction, transverse pair): index of closed node 0, stride along the line,
+// position of the cell along the line, local index of the line's first pressure dof and the stride between
+// its two pressure dofs, and the cell-index stride to the lower neighbour along the line.
+struct Line1 {
+  int base, sd, cd, nd, lp, ps, cstride, pdn;
+};
+template <bool HY>
+__device__ __forceinline__ Line1 line_x(const Lay1& L, const Cell1& q, int t1, int t2) {
+  constexpr int oy = HY ? 2 : 1;
+  Line1 l;
+  l.base = L.off_x + 2 * q.i + L.gx0 * ((oy * q.j + t1) + L.gx1 * (2 * q.kl + t2));
+  l.sd = 1; l.cd = q.i; l.nd = L.NX; l.lp = 2 * t1 + 2 * oy * t2; l.ps = 1; l.cstride = 1; l.pdn = L.npl;
+  return l;
+}
+__device__ __forceinline__ Line1 line_y(const Lay1& L, const Cell1& q, int t0, int t2) {
+  Line1 l;
+  l.base = L.off_y + (2 * q.i + t0) + L.gy0 * (2 * q.j + L.gy1 * (2 * q.kl + t2));
+  l.sd = L.gy0; l.cd = q.j; l.nd = L.NY; l.lp = t0 + 4 * t2; l.ps = 2; l.cstride = L.NX; l.pdn = L.NX * L.npl;
+  return l;
+}
+template <bool HY>
+__device__ __forceinline__ Line1 line_z(const Lay1& L, const Cell1& q, int t0, int t1) {
+  constexpr int oy = HY ? 2 : 1;
+  Line1 l;
+  l.base = L.off_z + (2 * q.i + t0) + L.gz0 * ((oy * q.j + t1) + L.gz1 * (2 * q.kl + 2));
+  l.sd = L.gz0 * L.gz1; l.cd = q.k; l.nd = L.NZ; l.lp = t0 + 2 * t1; l.ps = 2 * oy; l.cstride = L.plane;
+  l.pdn = L.plane * L.npl;
+  return l;
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 (RT1): diag(M) and T = 1/diag(M) per velocity node (1 / 0 on eliminated boundary nodes
+// [REF src/pressure_solver.cpp:56-60]) and the diagonal of S = B diag(M)^-1 B^T [REF :76-81] per pressure dof
+// (stored in the p-part of Md).  m_d: k_cell_coeff's per-cell coefficient (cvec layout).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void line_coeff(const Rt1Const& C, const Line1& l, const double* __restrict__ m, int c,
+                                           double* __restrict__ Md, double* __restrict__ T, bool own_top,
+                                           double& D0, double& D1) {
+  const double mR = m[c];
+  double t0 = 0.0, t2 = 0.0;
+  if (l.cd > 0) {
+    const double md = m[c - l.cstride] * C.CW[2][2] + mR * C.CW[0][0];
+    t0 = 1.0 / md;
+    Md[l.base] = md; T[l.base] = t0;
+  } else { Md[l.base] = 1.0; T[l.base] = 0.0; }
+  const double md1 = mR * C.CW[1][1];
+  const double t1 = 1.0 / md1;
+  Md[l.base + l.sd] = md1; T[l.base + l.sd] = t1;
+  if (l.cd + 1 < l.nd) {
+    const double md = mR * C.CW[2][2] + m[c + l.cstride] * C.CW[0][0];
+    t2 = 1.0 / md;
+    if (own_top) { Md[l.base + 2 * l.sd] = md; T[l.base + 2 * l.sd] = t2; }  // ghost-above node plane of a slab
+  } else { Md[l.base + 2 * l.sd] = 1.0; T[l.base + 2 * l.sd] = 0.0; }
+  // S_pp = sum over the line's nodes, ascending:  b (b T)   (boundary nodes: eliminated columns, skipped)
+  if (l.cd > 0) { D0 += C.Bv[0][0] * (C.Bv[0][0] * t0); D1 += C.Bv[1][0] * (C.Bv[1][0] * t0); }
+  D0 += C.Bv[0][1] * (C.Bv[0][1] * t1); D1 += C.Bv[1][1] * (C.Bv[1][1] * t1);
+  if (l.cd + 1 < l.nd) { D0 += C.Bv[0][2] * (C.Bv[0][2] * t2); D1 += C.Bv[1][2] * (C.Bv[1][2] * t2); }
+}
+
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_node_coeff(Lay1 L, Rt1Const C, const double* __restrict__ mx,
+                                                     const double* __restrict__ my, const double* __restrict__ mz,
+                                                     double* __restrict__ Md, double* __restrict__ T) {
+  constexpr int oy = HY ? 2 : 1;
+  constexpr int NPL = 4 * oy;
+  const Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  double D[NPL];
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) D[l] = 0.0;
+#pragma unroll
+  for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+    for (int t1 = 0; t1 < oy; ++t1) {
+      const Line1 l = line_x<HY>(L, q, t1, t2);
+      const int lp = 2 * t1 + 2 * oy * t2;
+      line_coeff(C, l, mx, q.c, Md, T, false, D[lp], D[lp + 1]);
+    }
+  if constexpr (HY) {
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+      for (int t0 = 0; t0 < 2; ++t0) {
+        const Line1 l = line_y(L, q, t0, t2);
+        const int lp = t0 + 4 * t2;
+        line_coeff(C, l, my, q.c, Md, T, false, D[lp], D[lp + 2]);
+      }
+  }
+#pragma unroll
+  for (int t1 = 0; t1 < oy; ++t1)
+#pragma unroll
+    for (int t0 = 0; t0 < 2; ++t0) {
+      const Line1 l = line_z<HY>(L, q, t0, t1);
+      const int lp = t0 + 2 * t1;
+      line_coeff(C, l, mz, q.c, Md, T, q.k == L.zhi - 1, D[lp], D[lp + 2 * oy]);
+    }
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) Md[q.pb + l] = D[l];
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 (RT1): y = [M(S) B^T; B 0] x, matrix-free, boundary rows/cols eliminated [REF src/pressure_solver.cpp:47-74];
+// optional fused <x, y>.  One thread per owned cell computes, per line, the rows of closed nodes 0 (lower
+// face) and 1 (interior) -- node 2 only on the upper boundary -- and the cell's pressure rows: gather form,
+// no atomics; sums in the oracle's CSR column order (M row, then the B^T row added to it).
+// ---------------------------------------------------------------------------------------
+template <bool DOT>
+__device__ __forceinline__ void line_apply(const Rt1Const& C, const Line1& l, const double* __restrict__ m, int c,
+                                           const double* __restrict__ x, double* __restrict__ y, int pb, double pc0,
+                                           double pc1, double& yp0, double& yp1, double& acc) {
+  const double mR = m[c];
+  const double x0 = x[l.base], x1 = x[l.base + l.sd], x2 = x[l.base + 2 * l.sd];
+  if (l.cd > 0) {  // shared face node: lower cell's node 2 = this cell's node 0
+    const double mL = m[c - l.cstride];
+    double s = 0.0;
+    if (l.cd - 1 > 0) s += (mL * C.CW[2][0]) * x[l.base - 2 * l.sd];
+    s += (mL * C.CW[2][1]) * x[l.base - l.sd];
+    s += (mL * C.CW[2][2] + mR * C.CW[0][0]) * x0;
+    s += (mR * C.CW[0][1]) * x1;
+    if (l.cd + 1 < l.nd) s += (mR * C.CW[0][2]) * x2;
+    const double* pL = x + (pb - l.pdn + l.lp);
+    double t = 0.0;
+    t += C.Bv[0][2] * pL[0];
+    t += C.Bv[1][2] * pL[l.ps];
+    t += C.Bv[0][0] * pc0;
+    t += C.Bv[1][0] * pc1;
+    const double yf = s + t;
+    y[l.base] = yf;
+    if (DOT) acc += x0 * yf;
+  } else {  // eliminated boundary row: identity
+    y[l.base] = x0;
+    if (DOT) acc += x0 * x0;
+  }
+  {
+    double s = 0.0;
+    if (l.cd > 0) s += (mR * C.CW[1][0]) * x0;
+    s += (mR * C.CW[1][1]) * x1;
+    if (l.cd + 1 < l.nd) s += (mR * C.CW[1][2]) * x2;
+    double t = 0.0;
+    t += C.Bv[0][1] * pc0;
+    t += C.Bv[1][1] * pc1;
+    const double y1 = s + t;
+    y[l.base + l.sd] = y1;
+    if (DOT) acc += x1 * y1;
+  }
+  if (l.cd + 1 == l.nd) {
+    y[l.base + 2 * l.sd] = x2;
+    if (DOT) acc += x2 * x2;
+  }
+  if (l.cd > 0) { yp0 += C.Bv[0][0] * x0; yp1 += C.Bv[1][0] * x0; }
+  yp0 += C.Bv[0][1] * x1; yp1 += C.Bv[1][1] * x1;
+  if (l.cd + 1 < l.nd) { yp0 += C.Bv[0][2] * x2; yp1 += C.Bv[1][2] * x2; }
+}
+
+template <bool HY, bool DOT>
+__global__ void __launch_bounds__(BLK) k1_darcy_apply(Lay1 L, Rt1Const C, const double* __restrict__ mx,
+                                                      const double* __restrict__ my, const double* __restrict__ mz,
+                                                      const double* __restrict__ x, double* __restrict__ y,
+                                                      double* partial, double* out, unsigned* ticket,
+                                                      const MinresState* st) {
+  constexpr int oy = HY ? 2 : 1;
+  constexpr int NPL = 4 * oy;
+  if (st && st->done) return;
+  const Cell1 q = owned_cell1(L);
+  double acc = 0.0;
+  if (q.ok) {
+    double pc[NPL], yp[NPL];
+#pragma unroll
+    for (int l = 0; l < NPL; ++l) { pc[l] = x[q.pb + l]; yp[l] = 0.0; }
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+      for (int t1 = 0; t1 < oy; ++t1) {
+        const Line1 l = line_x<HY>(L, q, t1, t2);
+        const int lp = 2 * t1 + 2 * oy * t2;
+        line_apply<DOT>(C, l, mx, q.c, x, y, q.pb, pc[lp], pc[lp + 1], yp[lp], yp[lp + 1], acc);
+      }
+    if constexpr (HY) {
+#pragma unroll
+      for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+        for (int t0 = 0; t0 < 2; ++t0) {
+          const Line1 l = line_y(L, q, t0, t2);
+          const int lp = t0 + 4 * t2;
+          line_apply<DOT>(C, l, my, q.c, x, y, q.pb, pc[lp], pc[lp + 2], yp[lp], yp[lp + 2], acc);
+        }
+    }
+#pragma unroll
+    for (int t1 = 0; t1 < oy; ++t1)
+#pragma unroll
+      for (int t0 = 0; t0 < 2; ++t0) {
+        const Line1 l = line_z<HY>(L, q, t0, t1);
+        const int lp = t0 + 2 * t1;
+        line_apply<DOT>(C, l, mz, q.c, x, y, q.pb, pc[lp], pc[lp + 2 * oy], yp[lp], yp[lp + 2 * oy], acc);
+      }
+#pragma unroll
+    for (int l = 0; l < NPL; ++l) {
+      y[q.pb + l] = yp[l];
+      if (DOT) acc += pc[l] * yp[l];
+    }
+  }
+  if (DOT) finish_dot(acc, partial, out, ticket);
+}
+
+// Canonical dot <a, b> over the dofs each cell owns, in the order k1_darcy_apply visits them.
+__device__ __forceinline__ void line_dot(const Line1& l, const double* __restrict__ a, const double* __restrict__ b,
+                                         double& acc) {
+  acc += a[l.base] * b[l.base];
+  acc += a[l.base + l.sd] * b[l.base + l.sd];
+  if (l.cd + 1 == l.nd) acc += a[l.base + 2 * l.sd] * b[l.base + 2 * l.sd];
+}
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_dot_owned(Lay1 L, const double* __restrict__ a, const double* __restrict__ b,
+                                                    double* partial, double* out, unsigned* ticket,
+                                                    const MinresState* st) {
+  constexpr int oy = HY ? 2 : 1;
+  constexpr int NPL = 4 * oy;
+  if (st && st->done) return;
+  const Cell1 q = owned_cell1(L);
+  double acc = 0.0;
+  if (q.ok) {
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+      for (int t1 = 0; t1 < oy; ++t1) line_dot(line_x<HY>(L, q, t1, t2), a, b, acc);
+    if constexpr (HY) {
+#pragma unroll
+      for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+        for (int t0 = 0; t0 < 2; ++t0) line_dot(line_y(L, q, t0, t2), a, b, acc);
+    }
+#pragma unroll
+    for (int t1 = 0; t1 < oy; ++t1)
+#pragma unroll
+      for (int t0 = 0; t0 < 2; ++t0) line_dot(line_z<HY>(L, q, t0, t1), a, b, acc);
+#pragma unroll
+    for (int l = 0; l < NPL; ++l) acc += a[q.pb + l] * b[q.pb + l];
+  }
+  finish_dot(acc, partial, out, ticket);
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 (RT1), parity mode: one symmetric Gauss-Seidel sweep on S = B diag(M)^-1 B^T in the natural order of the
+// L2 dofs (cell-major, 2^dim dofs per cell) -- GSSmoother(S) [REF src/pressure_solver.cpp:84].  S couples a dof
+// to its line partners: the other dof of its cell on each line (3 shared nodes) and the two dofs of each
+// line-neighbour cell (1 shared face node), so lexicographic GS is a wavefront over CELLS (hyperplanes
+// i+j+k) with the cell's dofs swept sequentially by one thread.  Entries of S are formed on the fly from
+// T = 1/diag(M) in the oracle's SpGEMM order:  S[p,p'] = sum over shared nodes f ascending of  b_pf (b_p'f T_f).
+// Row sums run over ascending columns like SparseMatrix::Gauss_Seidel_forw/back [MFEM-recall].
+// ---------------------------------------------------------------------------------------
+// in-cell partner entry for the row with line index a (partner 1-a)
+__device__ __forceinline__ double s_in(const Rt1Const& C, int a, double T0, double T1, double T2) {
+  double v = C.Bv[a][0] * (C.Bv[1 - a][0] * T0);
+  v += C.Bv[a][1] * (C.Bv[1 - a][1] * T1);
+  v += C.Bv[a][2] * (C.Bv[1 - a][2] * T2);
+  return v;
+}
+
+// contributions of the lower / upper line-neighbour cell to row (line index a)
+__device__ __forceinline__ void sgs_lower(const Rt1Const& C, const Line1& l, int a, const double* __restrict__ T,
+                                          const double* yp, int pb, double& sum) {
+  if (l.cd > 0) {
+    const double T0 = T[l.base];
+    const double* yl = yp + (pb - l.pdn + l.lp);
+    sum += yl[0] * (C.Bv[a][0] * (C.Bv[0][2] * T0));
+    sum += yl[l.ps] * (C.Bv[a][0] * (C.Bv[1][2] * T0));
+  }
+}
+__device__ __forceinline__ void sgs_upper(const Rt1Const& C, const Line1& l, int a, const double* __restrict__ T,
+                                          const double* yp, int pb, double& sum) {
+  if (l.cd + 1 < l.nd) {
+    const double T2 = T[l.base + 2 * l.sd];
+    const double* yu = yp + (pb + l.pdn + l.lp);
+    sum += yu[0] * (C.Bv[a][2] * (C.Bv[0][0] * T2));
+    sum += yu[l.ps] * (C.Bv[a][2] * (C.Bv[1][0] * T2));
+  }
+}
+__device__ __forceinline__ double sgs_in(const Rt1Const& C, const Line1& l, int a, const double* __restrict__ T) {
+  return s_in(C, a, l.cd > 0 ? T[l.base] : 0.0, T[l.base + l.sd], l.cd + 1 < l.nd ? T[l.base + 2 * l.sd] : 0.0);
+}
+
+// one cell of a sweep.  BWD = false: forward sweep from a zero guess (upper columns multiply zeros: skipped);
+// BWD = true: backward sweep over all columns.  yp/rp/Dp: p-parts (dvec1 addressing via q.pb).
+template <bool HY, bool BWD>
+__device__ __forceinline__ void sgs_cell(const Lay1& L, const Rt1Const& C, const Cell1& q, const double* __restrict__ T,
+                                         const double* __restrict__ D, const double* __restrict__ r, double* y) {
+  constexpr int oy = HY ? 2 : 1;
+  constexpr int NPL = 4 * oy;
+  double yl[NPL];
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) yl[l] = BWD ? y[q.pb + l] : 0.0;
+#pragma unroll
+  for (int ll = 0; ll < NPL; ++ll) {
+    const int l = BWD ? NPL - 1 - ll : ll;
+    const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
+    const Line1 lx = line_x<HY>(L, q, a1, a2);
+    const Line1 lz = line_z<HY>(L, q, a0, a1);
+    double sum = 0.0;
+    // lower cells, ascending cell index: z-, y-, x-
+    sgs_lower(C, lz, a2, T, y, q.pb, sum);
+    if constexpr (HY) sgs_lower(C, line_y(L, q, a0, a2), a1, T, y, q.pb, sum);
+    sgs_lower(C, lx, a0, T, y, q.pb, sum);
+    // in-cell partners with a smaller local index, ascending: flip a2, a1, a0 from 1 to 0
+    if (a2 == 1) sum += yl[l >= 2 * oy ? l - 2 * oy : 0] * sgs_in(C, lz, 1, T);
+    if constexpr (HY) {
+      if (a1 == 1) sum += yl[l >= 2 ? l - 2 : 0] * sgs_in(C, line_y(L, q, a0, a2), 1, T);
+    }
+    if (a0 == 1) sum += yl[l >= 1 ? l - 1 : 0] * sgs_in(C, lx, 1, T);
+    if (BWD) {
+      // in-cell partners with a larger local index, ascending: flip a0, a1, a2 from 0 to 1
+      if (a0 == 0) sum += yl[(l + 1) % NPL] * sgs_in(C, lx, 0, T);
+      if constexpr (HY) {
+        if (a1 == 0) sum += yl[(l + 2) % NPL] * sgs_in(C, line_y(L, q, a0, a2), 0, T);
+      }
+      if (a2 == 0) sum += yl[(l + 2 * oy) % NPL] * sgs_in(C, lz, 0, T);
+      // upper cells: x+, y+, z+
+      sgs_upper(C, lx, a0, T, y, q.pb, sum);
+      if constexpr (HY) sgs_upper(C, line_y(L, q, a0, a2), a1, T, y, q.pb, sum);
+      sgs_upper(C, lz, a2, T, y, q.pb, sum);
+    }
+    yl[l] = (r[q.pb + l] - sum) / D[q.pb + l];
+  }
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) y[q.pb + l] = yl[l];
+}
+
+template <int MODE, bool HY>
+__global__ void __launch_bounds__(1024) k1_sgs_wavefront(Lay1 L, Rt1Const C, const double* __restrict__ T,
+                                                         const double* __restrict__ Md, const double* __restrict__ r,
+                                                         double* y, int do_fwd, int do_bwd, const MinresState* st) {
+  if (st && st->done) return;
+  cg::grid_group grid = cg::this_grid();
+  const int nstage = L.NX + L.NY + L.nzl - 2;
+  const long npair = (long)L.NY * L.nzl;
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 0 ? !do_fwd : !do_bwd) continue;
+    for (int s = 0; s < nstage; ++s) {
+      const int d = pass == 0 ? s : nstage - 1 - s;
+      for (long jk = tid; jk < npair; jk += nth) {
+        Cell1 q;
+        q.j = (int)(jk % L.NY);
+        q.kl = (int)(jk / L.NY);
+        q.i = d - q.j - q.kl;
+        if (q.i < 0 || q.i >= L.NX) continue;
+        q.k = q.kl + L.zlo;
+        q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+        q.pb = L.off_p + q.c * L.npl;
+        q.ok = true;
+        if (pass == 0) sgs_cell<HY, false>(L, C, q, T, Md, r, y);
+        else sgs_cell<HY, true>(L, C, q, T, Md, r, y);
+      }
+      if (!(pass == 1 && s == nstage - 1)) wave_sync<MODE>(grid);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Face fluxes of the RT1 velocity in the RT0 dvec layout (layout.h) for the DG_0 saturation step:
+// int_F v.n = sum of the face's RT dofs x Gauss weights [REF src/saturation_solver.cpp:32-35],
+// summed second transverse direction outer, first inner.  The K6 kernels then run unchanged.
+// ---------------------------------------------------------------------------------------
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_face_flux(Lay1 L1, Lay L0, Rt1Const C, const double* __restrict__ x,
+                                                    double* __restrict__ flux) {
+  constexpr int oy = HY ? 2 : 1;
+  const Cell1 q = owned_cell1(L1);
+  if (!q.ok) return;
+  {
+    double F0 = 0.0, F2 = 0.0;
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+      for (int t1 = 0; t1 < oy; ++t1) {
+        const Line1 l = line_x<HY>(L1, q, t1, t2);
+        F0 += C.wflux * x[l.base];
+        F2 += C.wflux * x[l.base + 2];
+      }
+    const int f = ix_ux(L0, q.i, q.j, q.kl);
+    flux[f] = F0;
+    if (q.i + 1 == L1.NX) flux[f + 1] = F2;
+  }
+  if constexpr (HY) {
+    double F0 = 0.0, F2 = 0.0;
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+      for (int t0 = 0; t0 < 2; ++t0) {
+        const Line1 l = line_y(L1, q, t0, t2);
+        F0 += C.wflux * x[l.base];
+        F2 += C.wflux * x[l.base + 2 * l.sd];
+      }
+    const int f = ix_uy(L0, q.i, q.j, q.kl);
+    flux[f] = F0;
+    if (q.j + 1 == L1.NY) flux[f + L0.NX] = F2;
+  }
+  {
+    double F0 = 0.0, F2 = 0.0;
+#pragma unroll
+    for (int t1 = 0; t1 < oy; ++t1)
+#pragma unroll
+      for (int t0 = 0; t0 < 2; ++t0) {
+        const Line1 l = line_z<HY>(L1, q, t0, t1);
+        F0 += C.wflux * x[l.base];
+        F2 += C.wflux * x[l.base + 2 * l.sd];
+      }
+    const int f = ix_uz(L0, q.i, q.j, q.kl + 1);
+    flux[f] = F0;
+    if (q.k + 1 == L1.zhi) flux[f + L0.plane] = F2;  // upper face plane of the slab (ghost above / top boundary)
+  }
+}
+
+}  // namespace impes

@@ -71,6 +71,8 @@ typedef struct orc {
                                   element matrices, the GPU's fixed dot-product tree, rho1 = sqrt(d^2+b^2)).
                                   Same algorithm, same assembled-CSR data flow; only round-off-level choices
                                   are pinned so that GPU and oracle agree bit for bit. */
+  /* canonical RT1/Q1 constants (arith == 1): CW = Mc (x) Mo (x) Mo entries, Bv = -G (x) Mo (x) Mo */
+  double c_wt, c_CW[3][3], c_Bv[2][3];
   int threads;             /* >1: OpenMP in SpMV / vector ops (CPU baseline only) */
   int mass_cg;             /* 1: invert M_phi with Jacobi-PCG like the reference */
   /* MG hierarchy for IMPES_SCHUR_MG (restated in orc_mg.inc) */
@@ -272,9 +274,58 @@ static double canon_dot(const orc *o, const double *a, const double *b) {
   return tree256(v);
 }
 
+/* Canonical dot for RT1/Q1 Darcy vectors (csrc/rt1.cuh k1_darcy_apply / k1_dot_owned): blocks of 256
+ * consecutive cells; each cell adds, per direction d (x, y, z), per transverse open-node pair (second
+ * transverse direction outer, first inner), the products of its closed nodes 0 (lower face), 1 (interior)
+ * and, on the upper boundary only, 2; then its pressure dofs in local order. */
+static inline long vidx(const orc *o, int d, int i0, int i1, int i2);
+static double canon_dot_rt1(const orc *o, const double *a, const double *b) {
+  const int dim = o->dim;
+  const long ncl = o->ncell, nblk = (ncl + 255) / 256;
+  double *partial = (double *)malloc(sizeof(double) * nblk);
+  for (long blk = 0; blk < nblk; ++blk) {
+    double v[256];
+    for (int t = 0; t < 256; ++t) {
+      const long c = blk * 256 + t;
+      double acc = 0.0;
+      if (c < ncl) {
+        const int cc[3] = {(int)(c % o->n[0]), (int)((c / o->n[0]) % o->n[1]), (int)(c / ((long)o->n[0] * o->n[1]))};
+        for (int d = 0; d < dim; ++d) {
+          int tr[2], nt = 0;
+          for (int e = 0; e < dim; ++e) if (e != d) tr[nt++] = e;
+          for (int tf = 0; tf < (nt == 2 ? 2 : 1); ++tf)
+            for (int te = 0; te < 2; ++te) {
+              int g[3] = {0, 0, 0};
+              g[tr[0]] = 2 * cc[tr[0]] + te;
+              if (nt == 2) g[tr[1]] = 2 * cc[tr[1]] + tf;
+              const int ni = cc[d] + 1 == o->n[d] ? 3 : 2;
+              for (int i = 0; i < ni; ++i) {
+                g[d] = 2 * cc[d] + i;
+                const long f = vidx(o, d, g[0], g[1], g[2]);
+                acc += a[f] * b[f];
+              }
+            }
+        }
+        for (int l = 0; l < o->npl; ++l) { const long f = o->nv + c * o->npl + l; acc += a[f] * b[f]; }
+      }
+      v[t] = acc;
+    }
+    partial[blk] = tree256(v);
+  }
+  double v[256];
+  for (int t = 0; t < 256; ++t) {
+    double acc = 0.0;
+    for (long j = t; j < nblk; j += 256) acc += partial[j];
+    v[t] = acc;
+  }
+  free(partial);
+  return tree256(v);
+}
+
 /* Vector::operator* : plain sequential sum [MFEM-recall] */
 static double vdot(const orc *o, const double *a, const double *b, long n) {
   if (o->arith == 1 && o->threads <= 1 && n == o->nv + o->np && o->kv == 0 && o->kp == 0) return canon_dot(o, a, b);
+  if (o->arith == 1 && o->threads <= 1 && n == o->nv + o->np && o->kv == 1 && o->kp == 1) return canon_dot_rt1(o, a, b);
   if (o->threads > 1) {
     double s = 0.0;
 #pragma omp parallel for schedule(static) reduction(+ : s)
@@ -403,6 +454,16 @@ ORC_API orc *orc_create(const impes_desc *d, const double *Kx, const double *Ky,
           if (id == 0 || id == o->vg[c][c] - 1) o->ess[vidx(o, c, i0, i1, i2)] = 1;
         }
   o->threads = 1;
+  {
+    static const int MCI[3][3] = {{4, 2, -1}, {2, 16, 2}, {-1, 2, 4}};
+    const double r3 = sqrt(3.0) / 3.0;
+    const double G[2][3] = {{-0.5 - r3, 2.0 * r3, 0.5 - r3}, {-0.5 + r3, -2.0 * r3, 0.5 + r3}};
+    o->c_wt = o->dim == 3 ? 0.25 : 0.5;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) o->c_CW[i][j] = (MCI[i][j] / 30.0) * o->c_wt;
+    for (int a2 = 0; a2 < 2; ++a2)
+      for (int i = 0; i < 3; ++i) o->c_Bv[a2][i] = -(G[a2][i] * o->c_wt);
+  }
   if (assemble_B_and_rhs(o)) { orc_destroy(o); return NULL; }
   return o;
 }
@@ -432,7 +493,12 @@ ORC_API int orc_max_threads(void) {
 #endif
 }
 ORC_API void orc_set_dot_mode(orc *o, int m) { o->dot_mode = m; }
-ORC_API void orc_set_arith(orc *o, int m) { o->arith = m; }
+ORC_API void orc_set_arith(orc *o, int m) {
+  if (o->arith == m) return;
+  o->arith = m;
+  assemble_B_and_rhs(o); /* B and the rhs have canonical closed forms for RT1/Q1 */
+  o->have_system = 0;
+}
 ORC_API void orc_set_mass_cg(orc *o, int on) { o->mass_cg = on; }
 ORC_API void orc_get_dims(orc *o, impes_dims *out) {
   memset(out, 0, sizeof(*out));
@@ -477,6 +543,17 @@ static int assemble_B_and_rhs(orc *o) {
                     for (int a0 = 0; a0 < cntv[0]; ++a0) {
                       const int aa[3] = {a0, a1, a2};
                       double s = 0.0;
+                      if (o->arith == 1 && kv == 1 && kp == 1) {
+                        /* canonical closed form: B|cell,d = -G(d) (x) Mo (x) Mo, Mo = diag(1/2) */
+                        int match = 1;
+                        for (int e = 0; e < dim; ++e) if (e != d && aa[e] != bb[e]) match = 0;
+                        if (!match) continue;
+                        int gi[3];
+                        for (int e = 0; e < 3; ++e) gi[e] = e < dim ? cc[e] * (kv + 1) + aa[e] : 0;
+                        const long col = vidx(o, d, gi[0], gi[1], gi[2]);
+                        ri[nnz] = prow; ci[nnz] = (int)col; vv[nnz] = o->ess[col] ? 0.0 : o->c_Bv[bb[d]][aa[d]]; ++nnz;
+                        continue;
+                      }
                       for (int q2 = 0; q2 < Q[2]->nq; ++q2)
                         for (int q1 = 0; q1 < Q[1]->nq; ++q1)
                           for (int q0 = 0; q0 < Q[0]->nq; ++q0) {
@@ -521,6 +598,14 @@ static int assemble_B_and_rhs(orc *o) {
             for (int b0 = 0; b0 < cntp[0]; ++b0) {
               const int bb[3] = {b0, b1, b2};
               double s = 0.0;
+              if (o->arith == 1 && kp == 1) {
+                /* canonical: the 2-point Gauss rule coincides with the L2 nodes => g_m = -Q(x_m) |cell| / 2^dim */
+                double p[3] = {0, 0, 0};
+                for (int e = 0; e < dim; ++e) p[e] = (cc[e] + o->pnode[bb[e]]) * o->h[e];
+                o->rhs[o->nv + cell * o->npl + b0 + (kp + 1) * (b1 + (kp + 1) * b2)] =
+                    -(well_Q(&o->d, p) * (o->vol * (dim == 3 ? 0.125 : 0.25)));
+                continue;
+              }
               for (int q2 = 0; q2 < R[2]->nq; ++q2)
                 for (int q1 = 0; q1 < R[1]->nq; ++q1)
                   for (int q0 = 0; q0 < R[0]->nq; ++q0) {
@@ -622,10 +707,22 @@ static int assemble_system(orc *o, const double *S) {
           const double geo = o->h[d] * o->h[d] / o->vol;
           const double Kd = o->K[d][cell];
           const int closed_form = o->arith == 1 && kv == 0 && o->ks == 0;
+          const int closed_form1 = o->arith == 1 && kv == 1 && o->ks == 0;
           for (int i = 0; i < li; ++i)
             for (int j = 0; j < li; ++j) {
               double s = 0.0;
               int q = 0;
+              if (closed_form1) { /* exact RT1 element matrix, cell-constant coefficient: m Mc (x) Mo (x) Mo */
+                int ai[3], aj[3], ti = i, tj = j, match = 1;
+                for (int e = 0; e < 3; ++e) { ai[e] = ti % cnt[e]; ti /= cnt[e]; aj[e] = tj % cnt[e]; tj /= cnt[e]; }
+                for (int e = 0; e < dim; ++e) if (e != d && ai[e] != aj[e]) match = 0;
+                if (!match) continue;
+                const double mm = (1. / (coef[0] * Kd)) * geo;
+                const double val0 = mm * o->c_CW[ai[d]][aj[d]];
+                const long r0 = gl[i], c0 = gl[j];
+                ri[nnz] = r0; ci[nnz] = (int)c0; vv[nnz] = (o->ess[r0] || o->ess[c0]) ? 0.0 : val0; ++nnz;
+                continue;
+              }
               if (closed_form) { /* exact RT0 element matrix m [[1/3,1/6],[1/6,1/3]] */
                 const double mm = (1. / (coef[0] * Kd)) * geo;
                 const double val0 = (i == j) ? mm * (1.0 / 3.0) : mm * (1.0 / 6.0);
