@@ -44,6 +44,7 @@ struct impes_ctx {
   Rt1Const rc;
   int vec_n = 0, vec_offp = 0;  // length and p-offset of a Darcy-sized device vector in the active layout
   double* flux0 = nullptr;      // ord == 1: face fluxes of x in the RT0 dvec layout (input of K6)
+  double* mg1_ya = nullptr;     // ord == 1: second iterate buffer of the Q1 multigrid level (p-part)
   Phys ph;
   SatParam sp;
   int dev = 0;
@@ -92,6 +93,8 @@ struct impes_ctx {
   // multigrid Schur preconditioner (IMPES_SCHUR_MG)
   std::vector<MgLevel> mg;
   std::vector<double*> mg_bufs;
+  int mg_g = 1 << 30;            // first replicated level (multi-GPU): levels < mg_g are slab-distributed
+  std::vector<int> mg_goff, mg_gcnt;  // plane offset / count of every rank's part of level mg_g
   double mg_omega = 0.8, mg_cfac = 2.0;
   int mg_nu = 2, mg_coarse_sweeps = 16;
   long long graph_launches = 0;
@@ -307,6 +310,28 @@ int halo_darcy(impes_ctx* h, double* v) {
   NK(h->nccl.GroupEnd());
   return 0;
 }
+// dvec1 halo before K1 (rt1.cuh): p ghost-below cell plane; uz ghost node planes below (2: the lower cell's
+// interior and lower-face nodes) and above (1: the shared face nodes owned by the upper rank).
+int halo_darcy1(impes_ctx* h, double* v) {
+  if (h->L1.nranks == 1) return 0;
+  const Lay1& L = h->L1;
+  const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
+  const size_t pz = (size_t)L.gz0 * L.gz1, pp = (size_t)L.plane * L.npl;
+  Scope sc(h, KC_COMM, 1);
+  NK(h->nccl.GroupStart());
+  if (up >= 0) {
+    NK(h->nccl.Send(v + L.off_p + pp * L.nzl, pp, ncclFloat64, up, h->comm, h->stream));
+    NK(h->nccl.Send(v + L.off_z + pz * (2 * L.nzl), 2 * pz, ncclFloat64, up, h->comm, h->stream));
+    NK(h->nccl.Recv(v + L.off_z + pz * (2 * L.nzl + 2), pz, ncclFloat64, up, h->comm, h->stream));
+  }
+  if (dn >= 0) {
+    NK(h->nccl.Recv(v + L.off_p, pp, ncclFloat64, dn, h->comm, h->stream));
+    NK(h->nccl.Recv(v + L.off_z, 2 * pz, ncclFloat64, dn, h->comm, h->stream));
+    NK(h->nccl.Send(v + L.off_z + pz * 2, pz, ncclFloat64, dn, h->comm, h->stream));
+  }
+  NK(h->nccl.GroupEnd());
+  return 0;
+}
 int allreduce_scalar(impes_ctx* h, double* p) {
   if (h->L.nranks == 1) return 0;
   Scope sc(h, KC_COMM, 1);
@@ -315,6 +340,8 @@ int allreduce_scalar(impes_ctx* h, double* p) {
 }
 
 // ---- coefficient update (K4) -------------------------------------------------------------------
+int mg_gather(impes_ctx* h, double* full, size_t pe);
+MgLevel mg_view(const impes_ctx* h, const MgLevel& v);
 int update_coeff(impes_ctx* h) {
   const Lay& L = h->L;
   RET_IF(exchange_planes(h, h->S[h->scur], true, true));
@@ -336,10 +363,26 @@ int update_coeff(impes_ctx* h) {
   }
   if (!h->mg.empty()) {  // multigrid hierarchy of the Schur stencil (S depends on the saturation)
     auto grid_of = [](const MgLevel& v) { return (int)(((long)v.nx * v.ny * v.nz + MG_B - 1) / MG_B); };
-    Scope sc(h, KC_COEFF, 1 + 2 * ((int)h->mg.size() - 1));
-    k_mg_copy_fine<<<grid_of(h->mg[0]), MG_B, 0, h->stream>>>(L, h->mg[0], h->T, h->Md);
+    const bool multi = L.nranks > 1;
+    {
+      Scope sc(h, KC_COEFF, 1 + 2 * ((int)h->mg.size() - 1) + (h->ord == 1 ? 1 : 0));
+      if (h->ord == 1) {
+        if (L.has_y) k1_mg_copy_fine<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->mg[0], h->T);
+        else k1_mg_copy_fine<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->mg[0], h->T);
+        k_mg_diag<<<grid_of(h->mg[0]), MG_B, 0, h->stream>>>(h->mg[0]);
+      } else
+        k_mg_copy_fine<<<grid_of(h->mg[0]), MG_B, 0, h->stream>>>(L, h->mg[0], h->T, h->Md);
+    }
     for (size_t l = 1; l < h->mg.size(); ++l) {
-      k_mg_coarsen<<<grid_of(h->mg[l]), MG_B, 0, h->stream>>>(h->mg[l - 1], h->mg[l]);
+      if (multi && (int)l == h->mg_g) {  // coarsen my planes, assemble the level on every rank
+        const MgLevel cv = mg_view(h, h->mg[l]);
+        k_mg_coarsen<<<grid_of(cv), MG_B, 0, h->stream>>>(h->mg[l - 1], cv);
+        RET_IF(mg_gather(h, h->mg[l].Tx, (size_t)(cv.nx + 1) * cv.ny));
+        if (cv.ny > 1) RET_IF(mg_gather(h, h->mg[l].Ty, (size_t)cv.nx * (cv.ny + 1)));
+        RET_IF(mg_gather(h, h->mg[l].Tz, (size_t)cv.nx * cv.ny));
+      } else {
+        k_mg_coarsen<<<grid_of(h->mg[l]), MG_B, 0, h->stream>>>(h->mg[l - 1], h->mg[l]);
+      }
       k_mg_diag<<<grid_of(h->mg[l]), MG_B, 0, h->stream>>>(h->mg[l]);
     }
   }
@@ -351,6 +394,7 @@ int update_coeff(impes_ctx* h) {
 // ---- K1 ----------------------------------------------------------------------------------------
 int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState* st) {
   if (h->ord == 1) {
+    RET_IF(halo_darcy1(h, x));
     {
       Scope sc(h, KC_DARCY, 1);
       const int g = h->grid_cells;
@@ -487,36 +531,137 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
   return 0;
 }
 
+// ---- multigrid plumbing for slabs ------------------------------------------------------------
+// ghost planes of a slab-distributed level buffer (buf = local plane 0; ghosts at buf - pe and buf + nz*pe)
+int mg_halo(impes_ctx* h, double* buf, size_t pe, int nz) {
+  const Lay& L = h->L;
+  if (L.nranks == 1) return 0;
+  const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
+  Scope sc(h, KC_COMM, 1);
+  NK(h->nccl.GroupStart());
+  if (up >= 0) {
+    NK(h->nccl.Send(buf + pe * (size_t)(nz - 1), pe, ncclFloat64, up, h->comm, h->stream));
+    NK(h->nccl.Recv(buf + pe * (size_t)nz, pe, ncclFloat64, up, h->comm, h->stream));
+  }
+  if (dn >= 0) {
+    NK(h->nccl.Send(buf, pe, ncclFloat64, dn, h->comm, h->stream));
+    NK(h->nccl.Recv(buf - pe, pe, ncclFloat64, dn, h->comm, h->stream));
+  }
+  NK(h->nccl.GroupEnd());
+  return 0;
+}
+// every rank contributes planes [off[r], off[r]+cnt[r]) of `full` (pe doubles per plane); afterwards all
+// ranks hold the whole array
+int mg_gather(impes_ctx* h, double* full, size_t pe) {
+  const Lay& L = h->L;
+  if (L.nranks == 1) return 0;
+  Scope sc(h, KC_COMM, 1);
+  NK(h->nccl.GroupStart());
+  for (int r = 0; r < L.nranks; ++r) {
+    if (r == L.rank) continue;
+    NK(h->nccl.Send(full + pe * (size_t)h->mg_goff[L.rank], pe * (size_t)h->mg_gcnt[L.rank], ncclFloat64, r, h->comm, h->stream));
+    NK(h->nccl.Recv(full + pe * (size_t)h->mg_goff[r], pe * (size_t)h->mg_gcnt[r], ncclFloat64, r, h->comm, h->stream));
+  }
+  NK(h->nccl.GroupEnd());
+  return 0;
+}
+// this rank's part of the first replicated level, addressed like a distributed level
+MgLevel mg_view(const impes_ctx* h, const MgLevel& v) {
+  MgLevel w = v;
+  const int zo = h->mg_goff[h->L.rank];
+  const long pl = (long)v.nx * v.ny;
+  w.nz = h->mg_gcnt[h->L.rank];
+  w.zoff = zo;
+  w.Tx += (long)(v.nx + 1) * v.ny * zo;
+  w.Ty += (long)v.nx * (v.ny + 1) * zo;
+  w.Tz += pl * zo;
+  w.D += pl * zo;
+  if (w.r) w.r += pl * zo;
+  if (w.ya) w.ya += pl * zo;
+  if (w.yb) w.yb += pl * zo;
+  return w;
+}
+
 // One V(nu,nu) cycle, zero initial guess: y_p = MG(r_p)  (mg.cuh).  Iterates alternate between ya and yb of
 // each level; all sweep counts are even, so every level's result ends in yb (level 0: the p-part of y).
+// Multi-GPU: levels < mg_g live on slabs (ghost planes refreshed before every sweep that reads neighbours),
+// level mg_g is assembled on every rank by a gather and the levels below it run replicated -- the same
+// arithmetic as on one GPU, so the result does not depend on the number of GPUs.
 int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
   const Lay& L = h->L;
   std::vector<MgLevel>& mg = h->mg;
   const int nl = (int)mg.size();
-  mg[0].r = const_cast<double*>(r) + L.off_p + L.plane;
-  mg[0].yb = y + L.off_p + L.plane;
+  const bool q1 = h->ord == 1;
+  const bool multi = L.nranks > 1;
+  // Q1 level (ord == 1): p-parts of the Krylov vectors; iterates alternate between qa and qb like every level
+  const size_t qpe = q1 ? (size_t)L.plane * h->L1.npl : 0;
+  const double* qr = q1 ? r + h->L1.off_p : nullptr;
+  double* qb = q1 ? y + h->L1.off_p : nullptr;
+  double* qa = h->mg1_ya;
+  const double* qD = q1 ? h->Md + h->L1.off_p : nullptr;
+  int n = 0;
+  auto q1_smooth = [&](int sweeps, bool from_zero) -> int {
+    for (int s = 0; s < sweeps; ++s) {
+      double* in = (s & 1) ? qa : qb;
+      double* out = (s & 1) ? qb : qa;
+      const int first = from_zero && s == 0;
+      if (!first && multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
+      if (L.has_y) k1_mg_jacobi<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
+      else k1_mg_jacobi<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
+      ++n;
+    }
+    return 0;
+  };
+  if (!q1) {
+    mg[0].r = const_cast<double*>(r) + L.off_p + L.plane;
+    mg[0].yb = y + L.off_p + L.plane;
+  }
   auto grid_of = [](const MgLevel& v) { return (int)(((long)v.nx * v.ny * v.nz + MG_B - 1) / MG_B); };
-  auto smooth = [&](int l, int sweeps, bool from_zero) {
+  auto dist = [&](int l) { return multi && l < h->mg_g; };
+  auto smooth = [&](int l, int sweeps, bool from_zero) -> int {
     MgLevel& v = mg[l];
     for (int s = 0; s < sweeps; ++s) {
       // sweep s reads (s even ? yb : ya) and writes (s even ? ya : yb); with from_zero the first read is skipped
-      const double* in = (s & 1) ? v.ya : v.yb;
+      double* in = (s & 1) ? v.ya : v.yb;
       double* out = (s & 1) ? v.yb : v.ya;
-      k_mg_jacobi<<<grid_of(v), MG_B, 0, h->stream>>>(v, v.r, in, out, h->mg_omega, from_zero && s == 0, st);
+      const bool first = from_zero && s == 0;
+      if (!first && dist(l)) RET_IF(mg_halo(h, in, (size_t)v.nx * v.ny, v.nz));
+      k_mg_jacobi<<<grid_of(v), MG_B, 0, h->stream>>>(v, v.r, in, out, h->mg_omega, first, st);
+      ++n;
     }
+    return 0;
   };
-  int n = 0;
-  for (int l = 0; l + 1 < nl; ++l) {
-    smooth(l, h->mg_nu, true);
-    k_mg_restrict<<<grid_of(mg[l + 1]), MG_B, 0, h->stream>>>(mg[l], mg[l + 1], mg[l].r, mg[l].yb, mg[l + 1].r, st);
-    n += h->mg_nu + 1;
+  if (q1) {
+    RET_IF(q1_smooth(h->mg_nu, true));
+    if (multi) RET_IF(mg_halo(h, qb + qpe, qpe, L.nzl));
+    if (L.has_y) k1_mg_restrict<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
+    else k1_mg_restrict<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
+    ++n;
   }
-  smooth(nl - 1, h->mg_coarse_sweeps, true);
-  n += h->mg_coarse_sweeps;
+  for (int l = 0; l + 1 < nl; ++l) {
+    RET_IF(smooth(l, h->mg_nu, true));
+    if (dist(l)) RET_IF(mg_halo(h, mg[l].yb, (size_t)mg[l].nx * mg[l].ny, mg[l].nz));
+    if (multi && l + 1 == h->mg_g) {  // my planes of the first replicated level, then assemble it everywhere
+      const MgLevel cv = mg_view(h, mg[l + 1]);
+      k_mg_restrict<<<grid_of(cv), MG_B, 0, h->stream>>>(mg[l], cv, mg[l].r, mg[l].yb, cv.r, st);
+      RET_IF(mg_gather(h, mg[l + 1].r, (size_t)cv.nx * cv.ny));
+    } else {
+      k_mg_restrict<<<grid_of(mg[l + 1]), MG_B, 0, h->stream>>>(mg[l], mg[l + 1], mg[l].r, mg[l].yb, mg[l + 1].r, st);
+    }
+    ++n;
+  }
+  RET_IF(smooth(nl - 1, h->mg_coarse_sweeps, true));
   for (int l = nl - 2; l >= 0; --l) {
-    k_mg_prolong<<<grid_of(mg[l]), MG_B, 0, h->stream>>>(mg[l], mg[l + 1], mg[l + 1].yb, mg[l].yb, h->mg_cfac, st);
-    smooth(l, h->mg_nu, false);
-    n += h->mg_nu + 1;
+    const MgLevel cv = (multi && l + 1 == h->mg_g) ? mg_view(h, mg[l + 1]) : mg[l + 1];
+    k_mg_prolong<<<grid_of(mg[l]), MG_B, 0, h->stream>>>(mg[l], cv, cv.yb, mg[l].yb, h->mg_cfac, st);
+    ++n;
+    RET_IF(smooth(l, h->mg_nu, false));
+  }
+  if (q1) {
+    if (L.has_y) k1_mg_prolong<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
+    else k1_mg_prolong<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
+    ++n;
+    RET_IF(q1_smooth(h->mg_nu, false));
   }
   Scope sc(h, KC_PREC, n);
   return 0;
@@ -529,15 +674,16 @@ int schur_prec(impes_ctx* h, const double* r, double* y, const MinresState* st) 
   if (h->d.schur_prec == IMPES_SCHUR_MG) return mg_vcycle(h, r, y, st);
   if (L.nranks == 1) return launch_sgs(h, r, y, 1, 1, st);
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
-  double* yp = y + L.off_p;
+  double* yp = y + h->vec_offp;
+  const size_t pp = (size_t)L.plane * (h->ord == 1 ? h->L1.npl : 1);  // one cell plane of pressure dofs
   // forward: wait for the plane below, sweep, hand my top plane up
-  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream)); }
+  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp, pp, ncclFloat64, dn, h->comm, h->stream)); }
   RET_IF(launch_sgs(h, r, y, 1, 0, st));
-  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream)); }
+  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + pp * L.nzl, pp, ncclFloat64, up, h->comm, h->stream)); }
   // backward: wait for the plane above, sweep, hand my bottom plane down
-  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp + L.plane * (L.nzl + 1), (size_t)L.plane, ncclFloat64, up, h->comm, h->stream)); }
+  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp + pp * (L.nzl + 1), pp, ncclFloat64, up, h->comm, h->stream)); }
   RET_IF(launch_sgs(h, r, y, 0, 1, st));
-  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + L.plane, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream)); }
+  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + pp, pp, ncclFloat64, dn, h->comm, h->stream)); }
   return 0;
 }
 
@@ -656,7 +802,7 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
     }
     CK(cudaGetLastError());
   }
-  if (h->ord == 0) RET_IF(halo_darcy(h, h->x));  // ghosts of the result (velocity ghost faces feed the saturation step)
+  RET_IF(h->ord == 1 ? halo_darcy1(h, h->x) : halo_darcy(h, h->x));  // ghosts of the result (ghost faces feed the saturation step)
   CK(cudaEventRecord(e1, h->stream));
   CK(cudaEventSynchronize(e1));
   float ms = 0;
@@ -887,7 +1033,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   for (double* b : h->mg_bufs)
@@ -914,7 +1060,6 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     h->err = "GPU path implements -ov 0 -op 0 -os 0 (RT0/P0/P0) and -ov 1 -op 1 -os 0 (RT1/Q1/P0, the reference default)";
     return IMPES_ERR_UNSUPPORTED;
   }
-  if (h->ord == 1 && d.world_size > 1) { h->err = "RT1/Q1: multi-GPU slabs are not implemented yet"; return IMPES_ERR_UNSUPPORTED; }
   if (d.world_size < 1 || d.rank < 0 || d.rank >= d.world_size) { h->err = "bad rank/world_size"; return IMPES_ERR_BAD_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -945,12 +1090,22 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   if (d.world_size > L.NZ) { h->err = "more ranks than cell planes"; return IMPES_ERR_BAD_ARG; }
   L.rank = d.rank;
   L.nranks = d.world_size;
-  {  // balanced slabs: the first (NZ % P) ranks get one extra plane
-    const int base = L.NZ / L.nranks, rem = L.NZ % L.nranks;
-    L.zlo = d.rank * base + std::min(d.rank, rem);
-    L.nzl = base + (d.rank < rem ? 1 : 0);
-    L.zhi = L.zlo + L.nzl;
+  int mg_m = 0;  // multigrid mode on several GPUs: slabs are cut in units of 2^mg_m planes
+  if (d.schur_prec == IMPES_SCHUR_MG && L.nranks > 1) {
+    while (mg_m < 6 && (L.NZ >> (mg_m + 1)) >= L.nranks) ++mg_m;
+    if (mg_m < 1) { h->err = "IMPES_SCHUR_MG: needs at least 2 cell planes per GPU"; return IMPES_ERR_BAD_ARG; }
   }
+  auto slab_of = [&](int rank, int& lo, int& hi) {
+    // balanced slabs of plane units: the first (n % P) ranks get one extra unit (unit = 1 plane
+    // outside the multi-GPU multigrid mode)
+    const int unit = 1 << mg_m, nu = (L.NZ + unit - 1) / unit;
+    const int base = nu / L.nranks, rem = nu % L.nranks;
+    const int ulo = rank * base + std::min(rank, rem), uhi = ulo + base + (rank < rem ? 1 : 0);
+    lo = ulo * unit;
+    hi = std::min(uhi * unit, L.NZ);
+  };
+  slab_of(d.rank, L.zlo, L.zhi);
+  L.nzl = L.zhi - L.zlo;
   {  // all per-rank element offsets must fit 32-bit ints (layout.h)
     const long plane = (long)L.NX * L.NY;
     const long off_y = pad32((long)(L.NX + 1) * L.NY * L.nzl);
@@ -1187,25 +1342,46 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     h->launches++;
   }
   if (d.schur_prec == IMPES_SCHUR_MG) {
-    if (L.nranks > 1) { h->err = "IMPES_SCHUR_MG: multi-GPU multigrid is not implemented yet"; return IMPES_ERR_UNSUPPORTED; }
-    if (h->ord == 1) { h->err = "IMPES_SCHUR_MG: not implemented for RT1/Q1 yet"; return IMPES_ERR_UNSUPPORTED; }
     if (d.mg_smooth > 0) h->mg_nu = (d.mg_smooth + 1) / 2 * 2;  // even sweep counts (see mg_vcycle)
-    int nx = L.NX, ny = L.NY, nz = L.NZ;
+    const bool multi = L.nranks > 1;
+    h->mg_g = multi ? mg_m : (1 << 30);
+    if (h->ord == 1) {  // second iterate buffer of the Q1 level, p-part layout with ghost planes
+      RET_IF(dev_alloc(h, &h->mg1_ya, (long)L.plane * (L.nzl + 2) * h->L1.npl));
+    }
+    int nx = L.NX, ny = L.NY, nzg = L.NZ;
     for (int l = 0; l < 24; ++l) {
       MgLevel v;
       memset(&v, 0, sizeof v);
-      v.nx = nx; v.ny = ny; v.nz = nz;
-      const long nc = (long)nx * ny * nz;
-      double** arrs[] = {&v.Tx, &v.Ty, &v.Tz, &v.D, &v.ya};
-      const long sizes[] = {(long)(nx + 1) * ny * nz, (long)nx * (ny + 1) * nz, (long)nx * ny * (nz + 1), nc, nc};
-      for (int a = 0; a < 5; ++a) { RET_IF(dev_alloc(h, arrs[a], sizes[a])); h->mg_bufs.push_back(*arrs[a]); }
-      if (l > 0) {
-        RET_IF(dev_alloc(h, &v.r, nc)); h->mg_bufs.push_back(v.r);
-        RET_IF(dev_alloc(h, &v.yb, nc)); h->mg_bufs.push_back(v.yb);
+      v.nx = nx; v.ny = ny; v.nzg = nzg;
+      if (multi && l < h->mg_g) {  // slab part: planes [zlo >> l, ceil(zhi / 2^l))
+        v.zoff = L.zlo >> l;
+        v.nz = ((L.zhi + (1 << l) - 1) >> l) - v.zoff;
+      } else {
+        v.zoff = 0; v.nz = nzg;
+      }
+      if (multi && l == h->mg_g) {
+        h->mg_goff.resize(L.nranks); h->mg_gcnt.resize(L.nranks);
+        for (int r = 0; r < L.nranks; ++r) {
+          int lo, hi;
+          slab_of(r, lo, hi);
+          h->mg_goff[r] = lo >> l;
+          h->mg_gcnt[r] = ((hi + (1 << l) - 1) >> l) - h->mg_goff[r];
+        }
+      }
+      const long pl = (long)nx * ny, nc = pl * v.nz;
+      double** arrs[] = {&v.Tx, &v.Ty, &v.Tz, &v.D};
+      const long sizes[] = {(long)(nx + 1) * ny * v.nz, (long)nx * (ny + 1) * v.nz, pl * (v.nz + 1), nc};
+      for (int a = 0; a < 4; ++a) { RET_IF(dev_alloc(h, arrs[a], sizes[a])); h->mg_bufs.push_back(*arrs[a]); }
+      // iterate / rhs buffers carry one ghost plane below and above (used by slab-distributed levels)
+      double* b = nullptr;
+      RET_IF(dev_alloc(h, &b, nc + 2 * pl)); h->mg_bufs.push_back(b); v.ya = b + pl;
+      if (l > 0 || h->ord == 1) {
+        RET_IF(dev_alloc(h, &b, nc + 2 * pl)); h->mg_bufs.push_back(b); v.r = b + pl;
+        RET_IF(dev_alloc(h, &b, nc + 2 * pl)); h->mg_bufs.push_back(b); v.yb = b + pl;
       }
       h->mg.push_back(v);
-      if (nx <= 4 && ny <= 4 && nz <= 4) break;
-      nx = (nx + 1) / 2; ny = ny > 1 ? (ny + 1) / 2 : 1; nz = (nz + 1) / 2;
+      if (nx <= 4 && ny <= 4 && nzg <= 4) break;
+      nx = (nx + 1) / 2; ny = ny > 1 ? (ny + 1) / 2 : 1; nzg = (nzg + 1) / 2;
     }
   }
   RET_IF(dev_alloc(h, &h->partial, L.nblk + 8));

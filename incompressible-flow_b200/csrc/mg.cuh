@@ -16,7 +16,9 @@
 namespace impes {
 
 struct MgLevel {
-  int nx, ny, nz;              // cells (2-D problems: ny = 1)
+  int nx, ny, nz;              // cells held by this rank (2-D problems: ny = 1)
+  int zoff, nzg;               // global index of local plane 0 and global plane count (one GPU: 0, nz).
+                               // Distributed levels carry one ghost plane below / above in r, ya, yb.
   double *Tx, *Ty, *Tz, *D;    // compact face / cell arrays: Tx[(nx+1)*ny*nz], Ty[nx*(ny+1)*nz], Tz[nx*ny*(nz+1)]
   double *r, *ya, *yb;         // right-hand side and two iterate buffers (level 0: r and yb alias Krylov vectors)
 };
@@ -41,16 +43,16 @@ __device__ __forceinline__ MgIdx mg_cell(const MgLevel& v) {
 __device__ __forceinline__ double mg_apply(const MgLevel& v, const double* __restrict__ y, int i, int j, int k, int c) {
   const int pl = v.nx * v.ny;
   double s = v.D[c] * y[c];
-  if (k > 0) s -= v.Tz[c] * y[c - pl];
+  if (k + v.zoff > 0) s -= v.Tz[c] * y[c - pl];
   if (j > 0) s -= v.Ty[i + v.nx * (j + (v.ny + 1) * k)] * y[c - v.nx];
   if (i > 0) s -= v.Tx[i + (v.nx + 1) * (j + v.ny * k)] * y[c - 1];
   if (i + 1 < v.nx) s -= v.Tx[i + 1 + (v.nx + 1) * (j + v.ny * k)] * y[c + 1];
   if (j + 1 < v.ny) s -= v.Ty[i + v.nx * (j + 1 + (v.ny + 1) * k)] * y[c + v.nx];
-  if (k + 1 < v.nz) s -= v.Tz[c + pl] * y[c + pl];
+  if (k + v.zoff + 1 < v.nzg) s -= v.Tz[c + pl] * y[c + pl];
   return s;
 }
 
-// level 0: compact copy of the fine stencil from the solver's face arrays (single GPU: zlo = 0)
+// level 0: compact copy of the fine stencil from the solver's face arrays (local planes of the slab)
 __global__ void __launch_bounds__(MG_B) k_mg_copy_fine(Lay L, MgLevel v, const double* __restrict__ T,
                                                        const double* __restrict__ Md) {
   const MgIdx ci = mg_cell(v);
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(MG_B) k_mg_copy_fine(Lay L, MgLevel v, const d
     if (j + 1 == v.ny) v.Ty[i + v.nx * (j + 1 + (v.ny + 1) * k)] = 0.0;
   }
   v.Tz[c] = T[ix_uz(L, i, j, k + 1)];
-  if (k + 1 == v.nz) v.Tz[c + pl] = 0.0;
+  if (k + 1 == v.nz) v.Tz[c + pl] = (k + v.zoff + 1 == v.nzg) ? 0.0 : T[ix_uz(L, i, j, k + 2)];  // slab top: ghost face
 }
 
 // coarse transmissibilities: sum of the fine ones across the aggregate interface (k, then j, then i ascending)
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(MG_B) k_mg_coarsen(MgLevel f, MgLevel c) {
   if (J > 0)
     for (int k = k0; k < k1; ++k)
       for (int i = i0; i < i1; ++i) ty += f.Ty[i + f.nx * (j0 + (f.ny + 1) * k)];
-  if (K > 0)
+  if (K + c.zoff > 0)
     for (int j = j0; j < j1; ++j)
       for (int i = i0; i < i1; ++i) tz += f.Tz[i + f.nx * (j + f.ny * k0)];
   const int cc = I + c.nx * (J + c.ny * K);
@@ -92,7 +94,13 @@ __global__ void __launch_bounds__(MG_B) k_mg_coarsen(MgLevel f, MgLevel c) {
     if (J + 1 == c.ny) c.Ty[I + c.nx * (J + 1 + (c.ny + 1) * K)] = 0.0;
   }
   c.Tz[cc] = tz;
-  if (K + 1 == c.nz) c.Tz[cc + c.nx * c.ny] = 0.0;
+  if (K + 1 == c.nz) {  // upper face plane of the slab: the upper rank's lowest faces (aggregates are slab aligned)
+    double tt = 0.0;
+    if (K + c.zoff + 1 < c.nzg)
+      for (int j = j0; j < j1; ++j)
+        for (int i = i0; i < i1; ++i) tt += f.Tz[i + f.nx * (j + f.ny * (k0 + 2))];
+    c.Tz[cc + c.nx * c.ny] = tt;
+  }
 }
 // coarse diagonal: sum of the level's own face transmissibilities, order x-lo, x-hi, y-lo, y-hi, z-lo, z-hi
 __global__ void __launch_bounds__(MG_B) k_mg_diag(MgLevel v) {

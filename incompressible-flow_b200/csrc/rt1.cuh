@@ -18,6 +18,7 @@
 // contiguous copies.  Arithmetic contract: as kernels.cuh (-fmad=false, CSR column order of the oracle).
 #pragma once
 #include "kernels.cuh"
+#include "mg.cuh"
 
 namespace impes {
 
@@ -337,45 +338,56 @@ __device__ __forceinline__ double sgs_in(const Rt1Const& C, const Line1& l, int 
   return s_in(C, a, l.cd > 0 ? T[l.base] : 0.0, T[l.base + l.sd], l.cd + 1 < l.nd ? T[l.base + 2 * l.sd] : 0.0);
 }
 
-// one cell of a sweep.  BWD = false: forward sweep from a zero guess (upper columns multiply zeros: skipped);
-// BWD = true: backward sweep over all columns.  yp/rp/Dp: p-parts (dvec1 addressing via q.pb).
+// Off-diagonal part of row l of S for one cell: sum over ascending columns of y[col] * S[row, col].
+// FULL = false: only columns below the row (forward sweep from a zero guess: the others multiply zeros).
+// yl: the cell's own dofs (registers); y: p-addressed array for the neighbour cells' dofs (q.pb-relative).
+template <bool HY, bool FULL>
+__device__ __forceinline__ double q1_row_sum(const Lay1& L, const Rt1Const& C, const Cell1& q,
+                                             const double* __restrict__ T, const double* y,
+                                             const double (&yl)[HY ? 8 : 4], int l) {
+  constexpr int oy = HY ? 2 : 1;
+  constexpr int NPL = 4 * oy;
+  const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
+  const Line1 lx = line_x<HY>(L, q, a1, a2);
+  const Line1 lz = line_z<HY>(L, q, a0, a1);
+  double sum = 0.0;
+  // lower cells, ascending cell index: z-, y-, x-
+  sgs_lower(C, lz, a2, T, y, q.pb, sum);
+  if constexpr (HY) sgs_lower(C, line_y(L, q, a0, a2), a1, T, y, q.pb, sum);
+  sgs_lower(C, lx, a0, T, y, q.pb, sum);
+  // in-cell partners with a smaller local index, ascending: flip a2, a1, a0 from 1 to 0
+  if (a2 == 1) sum += yl[l >= 2 * oy ? l - 2 * oy : 0] * sgs_in(C, lz, 1, T);
+  if constexpr (HY) {
+    if (a1 == 1) sum += yl[l >= 2 ? l - 2 : 0] * sgs_in(C, line_y(L, q, a0, a2), 1, T);
+  }
+  if (a0 == 1) sum += yl[l >= 1 ? l - 1 : 0] * sgs_in(C, lx, 1, T);
+  if (FULL) {
+    // in-cell partners with a larger local index, ascending: flip a0, a1, a2 from 0 to 1
+    if (a0 == 0) sum += yl[(l + 1) % NPL] * sgs_in(C, lx, 0, T);
+    if constexpr (HY) {
+      if (a1 == 0) sum += yl[(l + 2) % NPL] * sgs_in(C, line_y(L, q, a0, a2), 0, T);
+    }
+    if (a2 == 0) sum += yl[(l + 2 * oy) % NPL] * sgs_in(C, lz, 0, T);
+    // upper cells: x+, y+, z+
+    sgs_upper(C, lx, a0, T, y, q.pb, sum);
+    if constexpr (HY) sgs_upper(C, line_y(L, q, a0, a2), a1, T, y, q.pb, sum);
+    sgs_upper(C, lz, a2, T, y, q.pb, sum);
+  }
+  return sum;
+}
+
+// one cell of a sweep.  BWD = false: forward sweep from a zero guess; BWD = true: backward sweep over all columns.
 template <bool HY, bool BWD>
 __device__ __forceinline__ void sgs_cell(const Lay1& L, const Rt1Const& C, const Cell1& q, const double* __restrict__ T,
                                          const double* __restrict__ D, const double* __restrict__ r, double* y) {
-  constexpr int oy = HY ? 2 : 1;
-  constexpr int NPL = 4 * oy;
+  constexpr int NPL = HY ? 8 : 4;
   double yl[NPL];
 #pragma unroll
   for (int l = 0; l < NPL; ++l) yl[l] = BWD ? y[q.pb + l] : 0.0;
 #pragma unroll
   for (int ll = 0; ll < NPL; ++ll) {
     const int l = BWD ? NPL - 1 - ll : ll;
-    const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
-    const Line1 lx = line_x<HY>(L, q, a1, a2);
-    const Line1 lz = line_z<HY>(L, q, a0, a1);
-    double sum = 0.0;
-    // lower cells, ascending cell index: z-, y-, x-
-    sgs_lower(C, lz, a2, T, y, q.pb, sum);
-    if constexpr (HY) sgs_lower(C, line_y(L, q, a0, a2), a1, T, y, q.pb, sum);
-    sgs_lower(C, lx, a0, T, y, q.pb, sum);
-    // in-cell partners with a smaller local index, ascending: flip a2, a1, a0 from 1 to 0
-    if (a2 == 1) sum += yl[l >= 2 * oy ? l - 2 * oy : 0] * sgs_in(C, lz, 1, T);
-    if constexpr (HY) {
-      if (a1 == 1) sum += yl[l >= 2 ? l - 2 : 0] * sgs_in(C, line_y(L, q, a0, a2), 1, T);
-    }
-    if (a0 == 1) sum += yl[l >= 1 ? l - 1 : 0] * sgs_in(C, lx, 1, T);
-    if (BWD) {
-      // in-cell partners with a larger local index, ascending: flip a0, a1, a2 from 0 to 1
-      if (a0 == 0) sum += yl[(l + 1) % NPL] * sgs_in(C, lx, 0, T);
-      if constexpr (HY) {
-        if (a1 == 0) sum += yl[(l + 2) % NPL] * sgs_in(C, line_y(L, q, a0, a2), 0, T);
-      }
-      if (a2 == 0) sum += yl[(l + 2 * oy) % NPL] * sgs_in(C, lz, 0, T);
-      // upper cells: x+, y+, z+
-      sgs_upper(C, lx, a0, T, y, q.pb, sum);
-      if constexpr (HY) sgs_upper(C, line_y(L, q, a0, a2), a1, T, y, q.pb, sum);
-      sgs_upper(C, lz, a2, T, y, q.pb, sum);
-    }
+    const double sum = q1_row_sum<HY, BWD>(L, C, q, T, y, yl, l);
     yl[l] = (r[q.pb + l] - sum) / D[q.pb + l];
   }
 #pragma unroll
@@ -465,6 +477,125 @@ __global__ void __launch_bounds__(BLK) k1_face_flux(Lay1 L1, Lay L0, Rt1Const C,
     const int f = ix_uz(L0, q.i, q.j, q.kl + 1);
     flux[f] = F0;
     if (q.k + 1 == L1.zhi) flux[f + L0.plane] = F2;  // upper face plane of the slab (ghost above / top boundary)
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 (RT1), throughput mode: the finest level of the multigrid V-cycle (mg.cuh) acts on the L2-Q1 dofs with the
+// operator S itself (rows formed on the fly as above); it is aggregated cell-wise (the 2^dim dofs of a cell ->
+// one coarse unknown) onto the cell-level two-point hierarchy of mg.cuh.  All arrays here are p-parts
+// (index cell*npl + local, ghost plane below included).
+// ---------------------------------------------------------------------------------------
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
+                                                    const double* __restrict__ Dp, const double* __restrict__ rp,
+                                                    const double* __restrict__ yin, double* __restrict__ yout,
+                                                    double omega, int first, const MinresState* st) {
+  constexpr int NPL = HY ? 8 : 4;
+  if (st && st->done) return;
+  Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  q.pb = q.c * NPL;
+  if (first) {
+#pragma unroll
+    for (int l = 0; l < NPL; ++l) yout[q.pb + l] = omega * (rp[q.pb + l] / Dp[q.pb + l]);
+    return;
+  }
+  double yl[NPL];
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) yl[l] = yin[q.pb + l];
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) {
+    const double sum = q1_row_sum<HY, true>(L, C, q, T, yin, yl, l);
+    const double d = Dp[q.pb + l];
+    const double sy = d * yl[l] + sum;
+    yout[q.pb + l] = yl[l] + omega * ((rp[q.pb + l] - sy) / d);
+  }
+}
+
+// cell rhs = sum over the cell's dofs (local order) of the residual r - S y
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_mg_restrict(Lay1 L, Rt1Const C, const double* __restrict__ T,
+                                                      const double* __restrict__ Dp, const double* __restrict__ rp,
+                                                      const double* __restrict__ y, double* __restrict__ rc,
+                                                      const MinresState* st) {
+  constexpr int NPL = HY ? 8 : 4;
+  if (st && st->done) return;
+  Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  q.pb = q.c * NPL;
+  double yl[NPL];
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) yl[l] = y[q.pb + l];
+  double acc = 0.0;
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) {
+    const double sum = q1_row_sum<HY, true>(L, C, q, T, y, yl, l);
+    acc += rp[q.pb + l] - (Dp[q.pb + l] * yl[l] + sum);
+  }
+  rc[q.i + L.NX * (q.j + L.NY * q.kl)] = acc;
+}
+
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_mg_prolong(Lay1 L, const double* __restrict__ ec, double* __restrict__ y,
+                                                     double cfac, const MinresState* st) {
+  constexpr int NPL = HY ? 8 : 4;
+  if (st && st->done) return;
+  const Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  const double e = cfac * ec[q.i + L.NX * (q.j + L.NY * q.kl)];
+#pragma unroll
+  for (int l = 0; l < NPL; ++l) y[q.c * NPL + l] = y[q.c * NPL + l] + e;
+}
+
+// cell-level transmissibilities below the Q1 level: Galerkin with cell-wise constant prolongation.  The two L2
+// dofs of a cell on a line sum to -/+ wt on the line's face nodes and to 0 on its interior node, so the
+// aggregated operator is two-point with T_face = sum over the face's RT1 nodes of wt^2 T_node.
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_mg_copy_fine(Lay1 L, Rt1Const C, MgLevel v, const double* __restrict__ T) {
+  constexpr int oy = HY ? 2 : 1;
+  const Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  const double w2 = C.wflux * C.wflux;
+  const int i = q.i, j = q.j, k = q.kl, c = i + v.nx * (j + v.ny * k), pl = v.nx * v.ny;
+  {
+    double t = 0.0;
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+      for (int t1 = 0; t1 < oy; ++t1) t += w2 * T[line_x<HY>(L, q, t1, t2).base];
+    v.Tx[i + (v.nx + 1) * (j + v.ny * k)] = t;
+    if (i + 1 == v.nx) v.Tx[i + 1 + (v.nx + 1) * (j + v.ny * k)] = 0.0;
+  }
+  if constexpr (HY) {
+    double t = 0.0;
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+      for (int t0 = 0; t0 < 2; ++t0) t += w2 * T[line_y(L, q, t0, t2).base];
+    v.Ty[i + v.nx * (j + (v.ny + 1) * k)] = t;
+    if (j + 1 == v.ny) v.Ty[i + v.nx * (j + 1 + (v.ny + 1) * k)] = 0.0;
+  }
+  {
+    double t = 0.0;
+#pragma unroll
+    for (int t1 = 0; t1 < oy; ++t1)
+#pragma unroll
+      for (int t0 = 0; t0 < 2; ++t0) t += w2 * T[line_z<HY>(L, q, t0, t1).base];
+    v.Tz[c] = t;
+    if (k + 1 == v.nz) {  // slab top: the ghost-above face nodes (0 on the global boundary)
+      double tt = 0.0;
+      if (k + v.zoff + 1 < v.nzg) {
+#pragma unroll
+        for (int t1 = 0; t1 < oy; ++t1)
+#pragma unroll
+          for (int t0 = 0; t0 < 2; ++t0) {
+            const Line1 l = line_z<HY>(L, q, t0, t1);
+            tt += w2 * T[l.base + 2 * l.sd];
+          }
+      }
+      v.Tz[c + pl] = tt;
+    }
   }
 }
 

@@ -14,9 +14,28 @@ def slab_range(n_layers, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def owned_ranges(dim, nx, ny, nz, rank, world):
+def owned_ranges(dim, nx, ny, nz, rank, world, order=0, slab=None):
     """Index ranges this rank owns in the native host layout (include/impes_b200.h):
-    -> (ranges in a Darcy vector [V | P], ranges in a cell / saturation vector)."""
+    -> (ranges in a Darcy vector [V | P], ranges in a cell / saturation vector).
+    order = 0: RT0/P0; order = 1: RT1/L2-Q1 (node grids of 2n+1 closed / 2n open nodes, 2^dim L2 dofs per cell).
+    slab: explicit (lo, hi) cell-layer range (impes_get_dims slab_lo/slab_hi) overriding the balanced rule."""
+    if order == 1:
+        if dim == 2:
+            n_layers, px, py, pz, npl = ny, 2 * nx + 1, 0, 2 * nx, 4
+            nvx, nvy = (2 * nx + 1) * 2 * ny, 0
+        else:
+            n_layers, px, py, pz, npl = nz, (2 * nx + 1) * 2 * ny, 2 * nx * (2 * ny + 1), 4 * nx * ny, 8
+            nvx, nvy = (2 * nx + 1) * 2 * ny * 2 * nz, 2 * nx * (2 * ny + 1) * 2 * nz
+        plane = nx * (ny if dim == 3 else 1)
+        nv = nvx + nvy + pz * (2 * n_layers + 1)
+        lo, hi = slab if slab is not None else slab_range(n_layers, rank, world)
+        top = 1 if hi == n_layers else 0
+        darcy = [(px * 2 * lo, px * 2 * hi)]
+        if py:
+            darcy.append((nvx + py * 2 * lo, nvx + py * 2 * hi))
+        darcy.append((nvx + nvy + pz * 2 * lo, nvx + nvy + pz * (2 * hi + top)))
+        darcy.append((nv + plane * npl * lo, nv + plane * npl * hi))
+        return darcy, [(plane * lo, plane * hi)]
     if dim == 2:
         n_layers, plane, px, py = ny, nx, nx + 1, 0
         nvx, nvy = (nx + 1) * ny, 0
@@ -24,7 +43,7 @@ def owned_ranges(dim, nx, ny, nz, rank, world):
         n_layers, plane, px, py = nz, nx * ny, (nx + 1) * ny, nx * (ny + 1)
         nvx, nvy = (nx + 1) * ny * nz, nx * (ny + 1) * nz
     nv = nvx + nvy + plane * (n_layers + 1)
-    lo, hi = slab_range(n_layers, rank, world)
+    lo, hi = slab if slab is not None else slab_range(n_layers, rank, world)
     top = 1 if hi == n_layers else 0
     darcy = [(px * lo, px * hi)]
     if py:

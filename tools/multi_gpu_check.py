@@ -32,8 +32,22 @@ def rel(a, b):
 
 
 ok = True
-for cfg in (dict(dim=3, nx=12, ny=10, nz=9), dict(dim=2, nx=33, ny=21), dict(dim=3, nx=24, ny=20, nz=16)):
-    d, Kx, Ky, Kz, phi = workloads.build(K="lognormal", **cfg)
+CASES = [
+    (dict(dim=3, nx=12, ny=10, nz=9), 0, abi.SCHUR_SGS_LEX),
+    (dict(dim=2, nx=33, ny=21), 0, abi.SCHUR_SGS_LEX),
+    (dict(dim=3, nx=24, ny=20, nz=16), 0, abi.SCHUR_SGS_LEX),
+    (dict(dim=3, nx=24, ny=20, nz=16), 0, abi.SCHUR_MG),   # distributed multigrid: aligned slabs, replicated coarse levels
+    (dict(dim=2, nx=33, ny=21), 0, abi.SCHUR_MG),          # ragged: 21 layers in units of 2^m
+    (dict(dim=3, nx=6, ny=5, nz=9), 1, abi.SCHUR_SGS_LEX),  # RT1/Q1 slabs
+    (dict(dim=2, nx=9, ny=11), 1, abi.SCHUR_SGS_LEX),
+    (dict(dim=3, nx=8, ny=6, nz=16), 1, abi.SCHUR_MG),
+    (dict(dim=2, nx=16, ny=24), 1, abi.SCHUR_MG),
+]
+for cfg, order, prec in CASES:
+    nlay = cfg["nz"] if cfg["dim"] == 3 else cfg["ny"]
+    if nlay < world or (prec == abi.SCHUR_MG and nlay < 2 * world):
+        continue
+    d, Kx, Ky, Kz, phi = workloads.build(K="lognormal", order=order, order_s=0, schur_prec=prec, **cfg)
     n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
     phi = np.random.default_rng(7).uniform(0.1, 0.4, n)
     d.rank, d.world_size, d.device = rank, world, local
@@ -41,7 +55,8 @@ for cfg in (dict(dim=3, nx=12, ny=10, nz=9), dict(dim=2, nx=33, ny=21), dict(dim
     uid = [s.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     s.comm_init(uid[0])
-    own_x, own_s = pkg.partition.owned_ranges(d.dim, d.nx, d.ny, d.nz, rank, world)
+    own_x, own_s = pkg.partition.owned_ranges(d.dim, d.nx, d.ny, d.nz, rank, world, order=order,
+                                              slab=(s.dims.slab_lo, s.dims.slab_hi))
     rng = np.random.default_rng(3)
     S = rng.uniform(0.05, 0.95, n)
     x = rng.standard_normal(s.nv + s.np_)
@@ -55,7 +70,7 @@ for cfg in (dict(dim=3, nx=12, ny=10, nz=9), dict(dim=2, nx=33, ny=21), dict(dim
     bad, mx = s.guards()
     if rank == 0:
         orc = load_oracle()
-        d1 = workloads.build(K="lognormal", **cfg)[0]
+        d1 = workloads.build(K="lognormal", order=order, order_s=0, schur_prec=prec, **cfg)[0]
         o = orc.Oracle(d1, Kx, Ky, Kz, phi)
         o.set_arith(1)
         o.update_coefficients(S)
@@ -69,7 +84,8 @@ for cfg in (dict(dim=3, nx=12, ny=10, nz=9), dict(dim=2, nx=33, ny=21), dict(dim
         ex = rel(xs[:o.nv], xo[:o.nv])
         good = e1 and e2 and e3 and dit <= 2 and ex < 1e-6 and (bad, mx) == (bo, mo)
         ok = ok and good
-        print(f"{cfg} world={world}: K1 bit-exact={e1} prec bit-exact={e2} sat bit-exact={e3} "
+        print(f"{cfg} order={order} prec={'MG' if prec else 'SGS'} world={world} slab={(s.dims.slab_lo, s.dims.slab_hi)}: "
+              f"K1 bit-exact={e1} prec bit-exact={e2} sat bit-exact={e3} "
               f"iters gpu={st.iterations} oracle={sto.iterations} rel_u={ex:.2e} guards={(bad, mx) == (bo, mo)} -> {'OK' if good else 'FAIL'}",
               flush=True)
     s.close()
