@@ -7,9 +7,17 @@ SaturationSolver call (dt_global/dt_local = 100 explicit upwind sub-steps, veloc
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C1..C4|nxXnyXnz]
 
-Workload by GPU count (BASELINE.json configs; SURVEY 8d):  N=1 -> C2 (2-D 512x512 log-normal, RT0/P0);
-N=2,4 -> C3 (3-D 128x128x32 extruded log-normal); N=8 -> C4 (60x220x85, SPE10-shaped).  The mesh is cut
-into slabs, one per GPU (strong scaling of one fixed mesh per N).
+Workload by GPU count (BASELINE.json configs):
+  N=1  -> C2 (2-D 512x512 log-normal, RT0/P0) with the SERIAL reference's algorithm (lexicographic symmetric
+          Gauss-Seidel Schur preconditioner, `run_serial`): parity mode, bit-identical to the oracle;
+  N>1  -> C5 (3-D 256^3 log-normal, RT1/L2-Q1; saturation in DG_0 = the reference's default `-os 0`, DG-Q1
+          saturation is not on the GPU yet) cut into N slabs, with the PARALLEL reference's structure
+          (`run_parallel`: AMG-type Schur preconditioner -> the geometric multigrid of csrc/mg.cuh, whose result
+          does not depend on N).  Strong scaling of one fixed mesh; the same workload on 1 GPU is reported under
+          `fast_mode` of the N=1 line.
+Time steps: 2-D `-dtg 100 -dtl 1`; 3-D `-dtg 50 -dtl 0.5` -- dtl = 1 is exactly CFL = 1 at the well
+cells and blows up on heterogeneous 3-D fields (S_max >> 1.1 would trip the reference's own guard
+[REF src/run_serial.cpp:138]); both give 100 sub-steps per step.
 
 value  = n_cells * K / (device time of K steps, state resident in HBM), max over ranks.
 e2e    = the same through the drop-in C ABI with HOST (pinned) buffers: every step uploads S, downloads
@@ -48,7 +56,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_oracle, load_package  # noqa: E402
 
-DT_GLOBAL, DT_LOCAL = 100.0, 1.0
+def time_steps(dim):
+    return (100.0, 1.0) if dim == 2 else (50.0, 0.5)
+
+
 NAMES = ["darcy_apply", "minres_update", "schur_prec", "sat_substep", "coeff", "dot", "misc", "comm"]
 
 
@@ -56,17 +67,27 @@ def parse_workload(name, gpus):
     pkg = load_package()
     from incompressible_flow_b200 import workloads
     if name is None:
-        name = {1: "C2", 2: "C3", 4: "C3", 8: "C4"}.get(gpus, "C3")
+        name = "C2" if gpus == 1 else "C5"
     if name in workloads.CONFIGS:
         c = dict(workloads.CONFIGS[name])
         if c.get("order", 0) != 0:
-            raise SystemExit(f"workload {name} (RT1/Q1) is not implemented yet")
+            c["order_s"] = 0   # DG_0 saturation (reference default); DG-Q1 is not on the GPU yet
         return name, c
+    order = 0
+    if name.lower().startswith("rt1:"):
+        order, name = 1, name[4:]
     dims = [int(v) for v in name.lower().split("x")]
     c = dict(dim=len(dims), nx=dims[0], ny=dims[1], K="lognormal", sigma=1.0, note="custom " + name)
     if len(dims) == 3:
         c["nz"] = dims[2]
+    if order:
+        c.update(order=1, order_s=0)
+        name = "rt1:" + name
     return name, c
+
+
+def spaces_of(cfg):
+    return "RT1/L2-Q1/DG_0" if cfg.get("order", 0) == 1 else "RT0/P0/P0"
 
 
 class ClockSampler:
@@ -128,6 +149,7 @@ def hbm_peak():
 def oracle_step(orc, built, threads, steps, warmup):
     """Time the CPU oracle on `steps` IMPES steps after `warmup` (each a full step of the workload)."""
     d, Kx, Ky, Kz, phi = built
+    DT_GLOBAL, DT_LOCAL = time_steps(d.dim)
     o = orc.Oracle(d, Kx, Ky, Kz, phi)
     o.set_threads(threads)
     n = o.n_cells
@@ -152,8 +174,24 @@ def run_reference(args, wname, cfg):
         return
     load_package()
     from incompressible_flow_b200 import workloads
+    from incompressible_flow_b200 import abi
     orc = load_oracle()
-    built = workloads.build(**cfg)
+    scfg = dict(cfg)
+    sample = f"{args.steps} full IMPES steps of {wname} after {args.warmup} warm-up steps"
+    prec = "sgs_lex (serial reference)"
+    if args.gpus > 1:
+        # the multi-GPU arm runs the parallel reference's structure (AMG-type Schur preconditioner): same here
+        scfg["schur_prec"] = abi.SCHUR_MG
+        prec = "multigrid (stands where the MPI reference uses BoomerAMG)"
+    ncell = cfg["nx"] * cfg["ny"] * cfg.get("nz", 1)
+    if ncell > 3e5 and cfg["dim"] == 3:
+        # bounded sample: the assembled-CSR restatement cannot hold the full mesh; cell-steps/s is size-normalised
+        m = 24 if cfg.get("order", 0) == 1 else 64
+        scfg.update(nx=m, ny=m, nz=m)
+        sample = (f"{args.steps} full IMPES steps of a {m}^3 mesh of the same kind (same spaces, field statistics, wells, "
+                  f"sub-step count) after {args.warmup} warm-up steps -- the {cfg['nx']}x{cfg['ny']}x{cfg['nz']} mesh of {wname} "
+                  "does not fit an assembled-CSR CPU run; cell-steps/s is normalised by the cell count")
+    built = workloads.build(**{k: v for k, v in scfg.items() if k != "note"})
     threads = max(1, min(orc.lib().orc_max_threads(), os.cpu_count() or 1))
     n, its, times = oracle_step(orc, built, threads, args.steps, args.warmup)
     tot = sum(times)
@@ -163,9 +201,9 @@ def run_reference(args, wname, cfg):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wname, **{k: v for k, v in cfg.items() if k != "note"}, "substeps_per_step": 100,
-                   "schur_prec": "sgs_lex (serial reference)", "minres_iters_per_step": its},
+                   "spaces": spaces_of(cfg), "schur_prec": prec, "minres_iters_per_step": its},
         "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} full IMPES steps of {wname} after {args.warmup} warm-up steps; "
+                         "sample": sample + "; "
                                    "CPU restatement of the reference algorithm (MFEM/HYPRE unavailable in this image), "
                                    "OpenMP in SpMV/vector ops, Gauss-Seidel sequential"},
         "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,6 +223,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the throughput-mode (multigrid) measurements")
+    ap.add_argument("--mode", default="auto", choices=["auto", "fast"],
+                    help="auto: N=1 parity mode (serial reference), N>1 multigrid (parallel reference); fast: multigrid")
     args = ap.parse_args()
     wname, cfg = parse_workload(args.workload, args.gpus)
     if args.impl == "reference":
@@ -208,8 +248,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    d, Kx, Ky, Kz, phi = workloads.build(**cfg)
+    bcfg = {k: v for k, v in cfg.items() if k != "note"}
+    fast_headline = world > 1 or args.mode == "fast"
+    if fast_headline:
+        bcfg["schur_prec"] = abi.SCHUR_MG
+    d, Kx, Ky, Kz, phi = workloads.build(**bcfg)
     d.rank, d.world_size, d.device = rank, world, local
+    order = int(d.order_v)
+    DT_GLOBAL, DT_LOCAL = time_steps(d.dim)
     n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
     s = pkg.Solver(d, Kx, Ky, Kz, phi)
     if world > 1:
@@ -277,9 +323,9 @@ def main():
         dist.all_reduce(t)
         a[:] = t.cpu().numpy()
 
-    own_x, own_s = pkg.partition.owned_ranges(d.dim, d.nx, d.ny, d.nz, rank, world)
+    own_x, own_s = pkg.partition.owned_ranges(d.dim, d.nx, d.ny, d.nz, rank, world, order=order, slab=(lo, hi))
     gather(S_host, own_s)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = 1 if n > 4e6 else max(1, min(args.steps, 2))
 
     def e2e_step(ti):
         s.pressure_solve(S_host, out=x_host)
@@ -312,7 +358,7 @@ def main():
     s.close()
 
     # ---------------- roofline: K1 / K6 alone on a streaming-size mesh -----------------------------
-    roofline = roofline_k6 = roofline_k2 = None
+    roofline = roofline_k6 = roofline_k2 = roofline_rt1 = None
     peak, peak_src = hbm_peak()
     if rank == 0 and not args.no_roofline:
         _, rcfg = parse_workload(args.roofline_size, 1)
@@ -345,13 +391,31 @@ def main():
                        "frac": k2_b / (a2 * 1e-3) / 1e9 / peak, "traffic": None, "mesh": args.roofline_size,
                        "bytes_per_launch": k2_b, "us_per_launch": a2 * 1e3}
 
+        # K1 of the RT1/L2-Q1 path on a streaming mesh (67 fp64 words per 3-D cell)
+        r1d, r1Kx, r1Ky, r1Kz, r1phi = workloads.build(dim=3, nx=192, ny=192, nz=192, K="lognormal", order=1, order_s=0)
+        r1d.device = local
+        r1n = 192 ** 3
+        with pkg.Solver(r1d, r1Kx, r1Ky, r1Kz, r1phi) as rs:
+            rs.set_field(abi.FIELD_SATURATION, np.full(r1n, 0.3))
+            a11, m11 = rs.time_kernel(abi.KERNEL_DARCY_APPLY, 10, True)
+            a12, m12 = rs.time_kernel(abi.KERNEL_MINRES_UPDATE, 5, True)
+            k11_b = 67 * 8 * r1n
+            k12_b = 15 * 8 * (rs.nv + rs.np_)
+        roofline_rt1 = {"kernel": "k1_darcy_apply<HY,DOT> (K1 of the RT1/L2-Q1 path + fused <u,Au>)", "bound": "hbm",
+                        "achieved": k11_b / (a11 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": k11_b / (a11 * 1e-3) / 1e9 / peak, "traffic": None, "mesh": "rt1:192x192x192",
+                        "bytes_per_launch": k11_b, "us_per_launch": a11 * 1e3,
+                        "k2_on_this_mesh": {"achieved": k12_b / (a12 * 1e-3) / 1e9, "frac": k12_b / (a12 * 1e-3) / 1e9 / peak,
+                                            "us_per_launch": a12 * 1e3}}
+
     # ---------------- throughput mode (multigrid Schur preconditioner), same workload + 256^3 -------
     fast = None
-    if rank == 0 and world == 1 and not args.no_fast:
+    if rank == 0 and world == 1 and not args.no_fast and not fast_headline:
         def fast_run(fcfg, steps, warm):
-            fd, fKx, fKy, fKz, fphi = workloads.build(**fcfg, schur_prec=abi.SCHUR_MG)
+            fd, fKx, fKy, fKz, fphi = workloads.build(**{k: v for k, v in fcfg.items() if k != "note"}, schur_prec=abi.SCHUR_MG)
             fd.device = local
             fn = fd.nx * fd.ny * (fd.nz if fd.dim == 3 else 1)
+            DT_GLOBAL, DT_LOCAL = time_steps(fd.dim)
             with pkg.Solver(fd, fKx, fKy, fKz, fphi) as fs:
                 fs.set_field(abi.FIELD_SATURATION, np.zeros(fn))
                 fits = []
@@ -373,13 +437,15 @@ def main():
                 wname: fast_run(cfg, args.steps, args.warmup)}
         big = dict(dim=3, nx=256, ny=256, nz=256, K="lognormal", sigma=1.0)
         fast["256x256x256 RT0/P0 (north_star mesh, lowest order), 1 GPU"] = fast_run(big, 2, 1)
+        big1 = dict(big, order=1, order_s=0)
+        fast["C5: 256x256x256 RT1/L2-Q1/DG_0 (north_star mesh; the N>1 bench workload), 1 GPU"] = fast_run(big1, 2, 1)
 
     # ---------------- CPU baseline beside it -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         orc = load_oracle()
         threads = max(1, min(orc.lib().orc_max_threads(), os.cpu_count() or 1))
-        built = workloads.build(**cfg)
+        built = workloads.build(**bcfg)
         cn, cits, ctimes = oracle_step(orc, built, threads, 1, 0)
         cpu = {"value": cn / ctimes[0], "unit": "cell-steps/s", "cores": threads, "kind": "port",
                "sample": f"1 full IMPES step (step 1, S=0) of {wname}: {cits[0]} MINRES iterations + 100 sub-steps, "
@@ -390,15 +456,18 @@ def main():
             "metric": "IMPES cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wname, **{k: v for k, v in cfg.items() if k != "note"},
-                       "spaces": "RT0/P0/P0", "two_phase": True, "substeps_per_step": 100,
-                       "schur_prec": "sgs_lex (parity mode: exact lexicographic symmetric Gauss-Seidel)",
+            "config": {"workload": wname, **{k: v for k, v in cfg.items() if k not in ("note", "schur_prec")},
+                       "spaces": spaces_of(cfg), "two_phase": True, "substeps_per_step": 100,
+                       "dt_global": DT_GLOBAL, "dt_local": DT_LOCAL,
+                       "schur_prec": ("multigrid V(2,2) (throughput mode; stands where the MPI reference uses BoomerAMG; "
+                                      "result independent of the GPU count)") if fast_headline else
+                                     "sgs_lex (parity mode: exact lexicographic symmetric Gauss-Seidel)",
                        "minres_rtol": d.darcy_rtol, "minres_iters_per_step": its,
                        "partition": f"{world} slab(s) along the slowest axis",
                        "l2_policy": "step working set < L2 by construction of the BASELINE meshes; every step streams "
                                     "fresh Krylov vectors; the roofline kernels run on a >=4xL2 mesh with L2 flushed"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "roofline_k6": roofline_k6, "roofline_k2": roofline_k2,
+            "roofline": roofline, "roofline_k6": roofline_k6, "roofline_k2": roofline_k2, "roofline_k1_rt1": roofline_rt1,
             "step_breakdown": breakdown, "fast_mode": fast, "cpu_baseline": cpu,
         }
         emit(line)
