@@ -42,6 +42,7 @@ struct impes_ctx {
   int ord = 0;           // 0: RT0/P0, 1: RT1/L2-Q1 (rt1.cuh); saturation DG_0 in both
   Lay1 L1;               // dvec1 layout (ord == 1); L then only describes the cell arrays and the flux vector
   Rt1Const rc;
+  int grid_dofs1 = 0;    // blocks of 256 L2 dofs (ord == 1: K1, dot, Q1 multigrid level run one thread per dof)
   int vec_n = 0, vec_offp = 0;  // length and p-offset of a Darcy-sized device vector in the active layout
   double* flux0 = nullptr;      // ord == 1: face fluxes of x in the RT0 dvec layout (input of K6)
   double* mg1_ya = nullptr;     // ord == 1: second iterate buffer of the Q1 multigrid level (p-part)
@@ -397,7 +398,7 @@ int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState*
     RET_IF(halo_darcy1(h, x));
     {
       Scope sc(h, KC_DARCY, 1);
-      const int g = h->grid_cells;
+      const int g = h->grid_dofs1;
 #define K1_LAUNCH(HY, DOT)                                                                                        \
   k1_darcy_apply<HY, DOT><<<g, BLK, 0, h->stream>>>(h->L1, h->rc, h->m[0], h->m[1], h->m[2], x, y, h->partial, \
                                                     h->scal + 0, h->ticket, st)
@@ -599,6 +600,7 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
   double* qb = q1 ? y + h->L1.off_p : nullptr;
   double* qa = h->mg1_ya;
   const double* qD = q1 ? h->Md + h->L1.off_p : nullptr;
+  const int gq = q1 ? (int)(((long)L.ncl * h->L1.npl + BLK - 1) / BLK) : 0;  // one thread per L2 dof
   int n = 0;
   auto q1_smooth = [&](int sweeps, bool from_zero) -> int {
     for (int s = 0; s < sweeps; ++s) {
@@ -606,8 +608,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
       double* out = (s & 1) ? qb : qa;
       const int first = from_zero && s == 0;
       if (!first && multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
-      if (L.has_y) k1_mg_jacobi<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
-      else k1_mg_jacobi<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
+      if (L.has_y) k1_mg_jacobi<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
+      else k1_mg_jacobi<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
       ++n;
     }
     return 0;
@@ -634,8 +636,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
   if (q1) {
     RET_IF(q1_smooth(h->mg_nu, true));
     if (multi) RET_IF(mg_halo(h, qb + qpe, qpe, L.nzl));
-    if (L.has_y) k1_mg_restrict<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
-    else k1_mg_restrict<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
+    if (L.has_y) k1_mg_restrict<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
+    else k1_mg_restrict<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
     ++n;
   }
   for (int l = 0; l + 1 < nl; ++l) {
@@ -691,8 +693,8 @@ int dot_owned(impes_ctx* h, const double* a, const double* b, double* out, const
   {
     Scope sc(h, KC_DOT, 1);
     if (h->ord == 1) {
-      if (h->L.has_y) k1_dot_owned<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
-      else k1_dot_owned<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
+      if (h->L.has_y) k1_dot_owned<true><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
+      else k1_dot_owned<false><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
     } else
       k_dot_owned<<<h->grid_cells, BLK, 0, h->stream>>>(h->L, a, b, h->partial, out, h->ticket, st);
   }
@@ -1165,6 +1167,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     for (int a = 0; a < 2; ++a)
       for (int i = 0; i < 3; ++i) h->rc.Bv[a][i] = -(G[a][i] * wt);
     h->rc.wflux = wt;
+    h->grid_dofs1 = (int)(((long)L.ncl * Q.npl + BLK - 1) / BLK);
   }
   h->ph.two_phase = d.two_phase; h->ph.Sor = d.Sor; h->ph.Swc = d.Swc; h->ph.mu_w = d.mu_w; h->ph.mu_o = d.mu_o;
   h->ph.den = 1. - d.Sor - d.Swc; h->ph.rden = 1.0 / h->ph.den; h->ph.rmu_w = 1.0 / d.mu_w; h->ph.rmu_o = 1.0 / d.mu_o;
@@ -1384,7 +1387,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
       nx = (nx + 1) / 2; ny = ny > 1 ? (ny + 1) / 2 : 1; nzg = (nzg + 1) / 2;
     }
   }
-  RET_IF(dev_alloc(h, &h->partial, L.nblk + 8));
+  RET_IF(dev_alloc(h, &h->partial, std::max(L.nblk, h->grid_dofs1) + 8));
   RET_IF(dev_alloc(h, &h->scal, 8));
   CK(cudaMalloc((void**)&h->ticket, sizeof(unsigned) * 4));
   CK(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned) * 4, h->stream));

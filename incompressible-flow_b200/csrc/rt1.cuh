@@ -38,6 +38,10 @@ struct Rt1Const {
   double wflux;  // weight of one face node in the face flux: 1/4 (3-D), 1/2 (2-D)
 };
 
+// Bv[a][i] with a possibly run-time a: a select between two constant-bank operands (a dynamically indexed
+// kernel parameter would be copied to local memory)
+#define BV(a, i) ((a) ? C.Bv[1][i] : C.Bv[0][i])
+
 struct Cell1 {
   int i, j, kl, k, c, pb;  // c: cvec index (ghost plane below included), pb: index of the cell's first p dof
   bool ok;
@@ -159,141 +163,159 @@ __global__ void __launch_bounds__(BLK) k1_node_coeff(Lay1 L, Rt1Const C, const d
 
 // ---------------------------------------------------------------------------------------
 // K1 (RT1): y = [M(S) B^T; B 0] x, matrix-free, boundary rows/cols eliminated [REF src/pressure_solver.cpp:47-74];
-// optional fused <x, y>.  One thread per owned cell computes, per line, the rows of closed nodes 0 (lower
-// face) and 1 (interior) -- node 2 only on the upper boundary -- and the cell's pressure rows: gather form,
-// no atomics; sums in the oracle's CSR column order (M row, then the B^T row added to it).
+// optional fused <x, y>.  One thread per L2 dof (2^dim consecutive lanes per cell, see owned_dof1): the thread
+// with local index (a0, a1, a2) computes its pressure row and, on each of its three lines, the row of closed
+// node a_d (0 = the cell's lower face node, 1 = its interior node; node 2 only on the upper boundary) -- 8 x 3
+// = the 24 velocity rows a cell owns.  Gather form, no atomics; sums in the oracle's CSR column order (M row,
+// then the B^T row added to it).  The other pressure dof of a line comes from the neighbouring lane.
 // ---------------------------------------------------------------------------------------
-template <bool DOT>
-__device__ __forceinline__ void line_apply(const Rt1Const& C, const Line1& l, const double* __restrict__ m, int c,
-                                           const double* __restrict__ x, double* __restrict__ y, int pb, double pc0,
-                                           double pc1, double& yp0, double& yp1, double& acc) {
-  const double mR = m[c];
-  const double x0 = x[l.base], x1 = x[l.base + l.sd], x2 = x[l.base + 2 * l.sd];
-  if (l.cd > 0) {  // shared face node: lower cell's node 2 = this cell's node 0
-    const double mL = m[c - l.cstride];
-    double s = 0.0;
-    if (l.cd - 1 > 0) s += (mL * C.CW[2][0]) * x[l.base - 2 * l.sd];
-    s += (mL * C.CW[2][1]) * x[l.base - l.sd];
-    s += (mL * C.CW[2][2] + mR * C.CW[0][0]) * x0;
-    s += (mR * C.CW[0][1]) * x1;
-    if (l.cd + 1 < l.nd) s += (mR * C.CW[0][2]) * x2;
-    const double* pL = x + (pb - l.pdn + l.lp);
-    double t = 0.0;
-    t += C.Bv[0][2] * pL[0];
-    t += C.Bv[1][2] * pL[l.ps];
-    t += C.Bv[0][0] * pc0;
-    t += C.Bv[1][0] * pc1;
-    const double yf = s + t;
-    y[l.base] = yf;
-    if (DOT) acc += x0 * yf;
-  } else {  // eliminated boundary row: identity
-    y[l.base] = x0;
-    if (DOT) acc += x0 * x0;
-  }
-  {
-    double s = 0.0;
-    if (l.cd > 0) s += (mR * C.CW[1][0]) * x0;
-    s += (mR * C.CW[1][1]) * x1;
-    if (l.cd + 1 < l.nd) s += (mR * C.CW[1][2]) * x2;
-    double t = 0.0;
-    t += C.Bv[0][1] * pc0;
-    t += C.Bv[1][1] * pc1;
-    const double y1 = s + t;
-    y[l.base + l.sd] = y1;
-    if (DOT) acc += x1 * y1;
-  }
-  if (l.cd + 1 == l.nd) {
-    y[l.base + 2 * l.sd] = x2;
-    if (DOT) acc += x2 * x2;
-  }
-  if (l.cd > 0) { yp0 += C.Bv[0][0] * x0; yp1 += C.Bv[1][0] * x0; }
-  yp0 += C.Bv[0][1] * x1; yp1 += C.Bv[1][1] * x1;
-  if (l.cd + 1 < l.nd) { yp0 += C.Bv[0][2] * x2; yp1 += C.Bv[1][2] * x2; }
+struct Dof1 {
+  Cell1 q;
+  int l;
+};
+template <bool HY>
+__device__ __forceinline__ Dof1 owned_dof1(const Lay1& L) {
+  constexpr int NPL = HY ? 8 : 4;
+  Dof1 d;
+  const unsigned t = blockIdx.x * (unsigned)BLK + threadIdx.x;
+  const unsigned cell = t / NPL;
+  d.l = (int)(t % NPL);
+  Cell1& q = d.q;
+  q.ok = cell < (unsigned)L.ncl;
+  const unsigned tt = q.ok ? cell : 0u;
+  const unsigned r = tt / (unsigned)L.NX;
+  q.i = (int)(tt - r * (unsigned)L.NX);
+  q.kl = (int)(r / (unsigned)L.NY);
+  q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
+  q.k = q.kl + L.zlo;
+  q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+  q.pb = q.c * NPL;  // p-part relative (callers add L.off_p for dvec1 addressing)
+  return d;
 }
 
+// Branch-free: every load is unconditional (addresses clamped into the cell's own line where the neighbour does
+// not exist) so that the compiler issues all of a thread's loads up front -- one memory round trip instead of
+// one per branch region (SASS of the branchy form: 6 dependent LDG groups) -- and the skipped CSR entries
+// become `+ 0.0`, which leaves every partial sum bit-identical.
+struct LineData {
+  double mR, mL, x0, x1, x2, xm1, xm2, pL0, pL1;
+};
+__device__ __forceinline__ LineData line_load(const Line1& l, const double* __restrict__ m, int c,
+                                              const double* __restrict__ x, int pb) {
+  const bool lo = l.cd > 0;
+  LineData v;
+  v.mR = m[c];
+  v.mL = m[lo ? c - l.cstride : c];
+  v.x0 = x[l.base]; v.x1 = x[l.base + l.sd]; v.x2 = x[l.base + 2 * l.sd];
+  v.xm1 = x[lo ? l.base - l.sd : l.base];
+  v.xm2 = x[lo ? l.base - 2 * l.sd : l.base];
+  const double* pL = x + (pb - (lo ? l.pdn : 0) + l.lp);
+  v.pL0 = pL[0]; v.pL1 = pL[l.ps];
+  return v;
+}
+template <bool DOT>
+__device__ __forceinline__ void line_rows_dof(const Rt1Const& C, const Line1& l, const LineData& v, int a,
+                                              double* __restrict__ y, double p_lo, double p_hi, bool ok, double& yp,
+                                              double& acc) {
+  const bool lo = l.cd > 0, lo2 = l.cd > 1, hi = l.cd + 1 < l.nd;
+  const double mR = v.mR, mL = v.mL, x0 = v.x0, x1 = v.x1, x2 = v.x2;
+  const bool fa = a == 0;  // face row (closed node 0) or interior row (closed node 1)
+  // M row, ascending columns: x(-2), x(-1) [lower cell, face rows only], x0, x1, x2
+  const double c3 = fa ? (mL * C.CW[2][2] + mR * C.CW[0][0]) : (mR * C.CW[1][0]);
+  const double c4 = mR * (fa ? C.CW[0][1] : C.CW[1][1]);
+  const double c5 = mR * (fa ? C.CW[0][2] : C.CW[1][2]);
+  double s = 0.0;
+  s += (fa && lo2) ? (mL * C.CW[2][0]) * v.xm2 : 0.0;
+  s += fa ? (mL * C.CW[2][1]) * v.xm1 : 0.0;
+  s += lo ? c3 * x0 : 0.0;
+  s += c4 * x1;
+  s += hi ? c5 * x2 : 0.0;
+  // B^T row: lower cell's two dofs (face rows only), then this cell's two
+  double t = 0.0;
+  t += fa ? C.Bv[0][2] * v.pL0 : 0.0;
+  t += fa ? C.Bv[1][2] * v.pL1 : 0.0;
+  t += (fa ? C.Bv[0][0] : C.Bv[0][1]) * p_lo;
+  t += (fa ? C.Bv[1][0] : C.Bv[1][1]) * p_hi;
+  const double xa = fa ? x0 : x1;
+  const double ya = (fa && !lo) ? x0 : s + t;  // eliminated boundary row: identity
+  if (ok) y[l.base + (fa ? 0 : l.sd)] = ya;
+  if (DOT) acc += xa * ya;
+  if (!fa && !hi) {  // upper boundary node: identity row
+    if (ok) y[l.base + 2 * l.sd] = x2;
+    if (DOT) acc += x2 * x2;
+  }
+  yp += lo ? BV(a, 0) * x0 : 0.0;
+  yp += BV(a, 1) * x1;
+  yp += hi ? BV(a, 2) * x2 : 0.0;
+}
+
+// Branch-free: every load is unconditional (addresses clamped into the cell's own line where the neighbour does
+// not exist) and all of a thread's loads are issued before any arithmetic -- one memory round trip instead of
+// one per line / branch region (SASS of the branchy form: 6 dependent LDG groups).  Skipped CSR entries become
+// `+ 0.0`, which leaves every partial sum bit-identical.
 template <bool HY, bool DOT>
 __global__ void __launch_bounds__(BLK) k1_darcy_apply(Lay1 L, Rt1Const C, const double* __restrict__ mx,
                                                       const double* __restrict__ my, const double* __restrict__ mz,
                                                       const double* __restrict__ x, double* __restrict__ y,
                                                       double* partial, double* out, unsigned* ticket,
                                                       const MinresState* st) {
-  constexpr int oy = HY ? 2 : 1;
-  constexpr int NPL = 4 * oy;
   if (st && st->done) return;
-  const Cell1 q = owned_cell1(L);
-  double acc = 0.0;
-  if (q.ok) {
-    double pc[NPL], yp[NPL];
-#pragma unroll
-    for (int l = 0; l < NPL; ++l) { pc[l] = x[q.pb + l]; yp[l] = 0.0; }
-#pragma unroll
-    for (int t2 = 0; t2 < 2; ++t2)
-#pragma unroll
-      for (int t1 = 0; t1 < oy; ++t1) {
-        const Line1 l = line_x<HY>(L, q, t1, t2);
-        const int lp = 2 * t1 + 2 * oy * t2;
-        line_apply<DOT>(C, l, mx, q.c, x, y, q.pb, pc[lp], pc[lp + 1], yp[lp], yp[lp + 1], acc);
-      }
-    if constexpr (HY) {
-#pragma unroll
-      for (int t2 = 0; t2 < 2; ++t2)
-#pragma unroll
-        for (int t0 = 0; t0 < 2; ++t0) {
-          const Line1 l = line_y(L, q, t0, t2);
-          const int lp = t0 + 4 * t2;
-          line_apply<DOT>(C, l, my, q.c, x, y, q.pb, pc[lp], pc[lp + 2], yp[lp], yp[lp + 2], acc);
-        }
-    }
-#pragma unroll
-    for (int t1 = 0; t1 < oy; ++t1)
-#pragma unroll
-      for (int t0 = 0; t0 < 2; ++t0) {
-        const Line1 l = line_z<HY>(L, q, t0, t1);
-        const int lp = t0 + 2 * t1;
-        line_apply<DOT>(C, l, mz, q.c, x, y, q.pb, pc[lp], pc[lp + 2 * oy], yp[lp], yp[lp + 2 * oy], acc);
-      }
-#pragma unroll
-    for (int l = 0; l < NPL; ++l) {
-      y[q.pb + l] = yp[l];
-      if (DOT) acc += pc[l] * yp[l];
-    }
+  const Dof1 d = owned_dof1<HY>(L);
+  const Cell1& q = d.q;
+  const int l = d.l;
+  const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
+  const int pb = L.off_p + q.pb;
+  const bool ok = q.ok;
+  const Line1 lx = line_x<HY>(L, q, a1, a2);
+  const Line1 lz = line_z<HY>(L, q, a0, a1);
+  Line1 ly = lx;
+  if constexpr (HY) ly = line_y(L, q, a0, a2);
+  // ---- load phase
+  const double pc = x[pb + l];
+  const LineData vx = line_load(lx, mx, q.c, x, pb);
+  LineData vy = vx;
+  if constexpr (HY) vy = line_load(ly, my, q.c, x, pb);
+  const LineData vz = line_load(lz, mz, q.c, x, pb);
+  // ---- compute phase
+  const double px = __shfl_xor_sync(0xffffffffu, pc, 1);
+  const double py = HY ? __shfl_xor_sync(0xffffffffu, pc, 2) : 0.0;
+  const double pz = __shfl_xor_sync(0xffffffffu, pc, HY ? 4 : 2);
+  double acc = 0.0, yp = 0.0;
+  line_rows_dof<DOT>(C, lx, vx, a0, y, a0 ? px : pc, a0 ? pc : px, ok, yp, acc);
+  if constexpr (HY) line_rows_dof<DOT>(C, ly, vy, a1, y, a1 ? py : pc, a1 ? pc : py, ok, yp, acc);
+  line_rows_dof<DOT>(C, lz, vz, a2, y, a2 ? pz : pc, a2 ? pc : pz, ok, yp, acc);
+  if (ok) y[pb + l] = yp;
+  if (DOT) {
+    acc += pc * yp;
+    finish_dot(ok ? acc : 0.0, partial, out, ticket);
   }
-  if (DOT) finish_dot(acc, partial, out, ticket);
 }
 
-// Canonical dot <a, b> over the dofs each cell owns, in the order k1_darcy_apply visits them.
-__device__ __forceinline__ void line_dot(const Line1& l, const double* __restrict__ a, const double* __restrict__ b,
-                                         double& acc) {
-  acc += a[l.base] * b[l.base];
-  acc += a[l.base + l.sd] * b[l.base + l.sd];
-  if (l.cd + 1 == l.nd) acc += a[l.base + 2 * l.sd] * b[l.base + 2 * l.sd];
+// Canonical dot <a, b> over the dofs each thread of k1_darcy_apply owns, in the order it visits them.
+__device__ __forceinline__ void line_dot_dof(const Line1& l, int a, const double* __restrict__ u,
+                                             const double* __restrict__ v, double& acc) {
+  if (a == 0) acc += u[l.base] * v[l.base];
+  else {
+    acc += u[l.base + l.sd] * v[l.base + l.sd];
+    if (l.cd + 1 == l.nd) acc += u[l.base + 2 * l.sd] * v[l.base + 2 * l.sd];
+  }
 }
 template <bool HY>
 __global__ void __launch_bounds__(BLK) k1_dot_owned(Lay1 L, const double* __restrict__ a, const double* __restrict__ b,
                                                     double* partial, double* out, unsigned* ticket,
                                                     const MinresState* st) {
-  constexpr int oy = HY ? 2 : 1;
-  constexpr int NPL = 4 * oy;
   if (st && st->done) return;
-  const Cell1 q = owned_cell1(L);
+  const Dof1 d = owned_dof1<HY>(L);
+  const Cell1& q = d.q;
+  const int l = d.l;
+  const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
   double acc = 0.0;
   if (q.ok) {
-#pragma unroll
-    for (int t2 = 0; t2 < 2; ++t2)
-#pragma unroll
-      for (int t1 = 0; t1 < oy; ++t1) line_dot(line_x<HY>(L, q, t1, t2), a, b, acc);
-    if constexpr (HY) {
-#pragma unroll
-      for (int t2 = 0; t2 < 2; ++t2)
-#pragma unroll
-        for (int t0 = 0; t0 < 2; ++t0) line_dot(line_y(L, q, t0, t2), a, b, acc);
-    }
-#pragma unroll
-    for (int t1 = 0; t1 < oy; ++t1)
-#pragma unroll
-      for (int t0 = 0; t0 < 2; ++t0) line_dot(line_z<HY>(L, q, t0, t1), a, b, acc);
-#pragma unroll
-    for (int l = 0; l < NPL; ++l) acc += a[q.pb + l] * b[q.pb + l];
+    line_dot_dof(line_x<HY>(L, q, a1, a2), a0, a, b, acc);
+    if constexpr (HY) line_dot_dof(line_y(L, q, a0, a2), a1, a, b, acc);
+    line_dot_dof(line_z<HY>(L, q, a0, a1), a2, a, b, acc);
+    const int p = L.off_p + q.pb + l;
+    acc += a[p] * b[p];
   }
   finish_dot(acc, partial, out, ticket);
 }
@@ -309,9 +331,9 @@ __global__ void __launch_bounds__(BLK) k1_dot_owned(Lay1 L, const double* __rest
 // ---------------------------------------------------------------------------------------
 // in-cell partner entry for the row with line index a (partner 1-a)
 __device__ __forceinline__ double s_in(const Rt1Const& C, int a, double T0, double T1, double T2) {
-  double v = C.Bv[a][0] * (C.Bv[1 - a][0] * T0);
-  v += C.Bv[a][1] * (C.Bv[1 - a][1] * T1);
-  v += C.Bv[a][2] * (C.Bv[1 - a][2] * T2);
+  double v = BV(a, 0) * (BV(1 - a, 0) * T0);
+  v += BV(a, 1) * (BV(1 - a, 1) * T1);
+  v += BV(a, 2) * (BV(1 - a, 2) * T2);
   return v;
 }
 
@@ -321,8 +343,8 @@ __device__ __forceinline__ void sgs_lower(const Rt1Const& C, const Line1& l, int
   if (l.cd > 0) {
     const double T0 = T[l.base];
     const double* yl = yp + (pb - l.pdn + l.lp);
-    sum += yl[0] * (C.Bv[a][0] * (C.Bv[0][2] * T0));
-    sum += yl[l.ps] * (C.Bv[a][0] * (C.Bv[1][2] * T0));
+    sum += yl[0] * (BV(a, 0) * (C.Bv[0][2] * T0));
+    sum += yl[l.ps] * (BV(a, 0) * (C.Bv[1][2] * T0));
   }
 }
 __device__ __forceinline__ void sgs_upper(const Rt1Const& C, const Line1& l, int a, const double* __restrict__ T,
@@ -330,8 +352,8 @@ __device__ __forceinline__ void sgs_upper(const Rt1Const& C, const Line1& l, int
   if (l.cd + 1 < l.nd) {
     const double T2 = T[l.base + 2 * l.sd];
     const double* yu = yp + (pb + l.pdn + l.lp);
-    sum += yu[0] * (C.Bv[a][2] * (C.Bv[0][0] * T2));
-    sum += yu[l.ps] * (C.Bv[a][2] * (C.Bv[1][0] * T2));
+    sum += yu[0] * (BV(a, 2) * (C.Bv[0][0] * T2));
+    sum += yu[l.ps] * (BV(a, 2) * (C.Bv[1][0] * T2));
   }
 }
 __device__ __forceinline__ double sgs_in(const Rt1Const& C, const Line1& l, int a, const double* __restrict__ T) {
@@ -486,31 +508,79 @@ __global__ void __launch_bounds__(BLK) k1_face_flux(Lay1 L1, Lay L0, Rt1Const C,
 // one coarse unknown) onto the cell-level two-point hierarchy of mg.cuh.  All arrays here are p-parts
 // (index cell*npl + local, ghost plane below included).
 // ---------------------------------------------------------------------------------------
+// One thread per L2 dof (2^dim consecutive lanes per cell): every array access is coalesced and the cell's
+// other dofs come through warp shuffles.  Same terms in the same order as q1_row_sum<HY, true>, so the result
+// is bit-identical to the one-thread-per-cell form (ncu: that form was L1/LSU bound, 95 % l1tex throughput at
+// 18 % DRAM, because each lane walked its own 64-byte block with 8-byte loads).
+// Branch-free neighbour terms for the per-dof kernels: T is stored as 0 on eliminated boundary nodes, so a
+// missing neighbour contributes y * (b (b' 0)) = +-0 with y loaded from a clamped (own-cell) address.
+__device__ __forceinline__ void nb_lower(const Rt1Const& C, const Line1& l, int a, double T0, const double* y, int pb,
+                                         double& sum) {
+  const double* yl = y + (pb - (l.cd > 0 ? l.pdn : 0) + l.lp);
+  sum += yl[0] * (BV(a, 0) * (C.Bv[0][2] * T0));
+  sum += yl[l.ps] * (BV(a, 0) * (C.Bv[1][2] * T0));
+}
+__device__ __forceinline__ void nb_upper(const Rt1Const& C, const Line1& l, int a, double T2, const double* y, int pb,
+                                         double& sum) {
+  const double* yu = y + (pb + (l.cd + 1 < l.nd ? l.pdn : 0) + l.lp);
+  sum += yu[0] * (BV(a, 2) * (C.Bv[0][0] * T2));
+  sum += yu[l.ps] * (BV(a, 2) * (C.Bv[1][0] * T2));
+}
+// off-diagonal part of row l (all columns); ys = y of this dof; all 32 lanes must call
+template <bool HY>
+__device__ __forceinline__ double q1_row_sum_dof(const Lay1& L, const Rt1Const& C, const Dof1& d,
+                                                 const double* __restrict__ T, const double* __restrict__ y, double ys) {
+  const Cell1& q = d.q;
+  const int l = d.l;
+  const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
+  const double yx = __shfl_xor_sync(0xffffffffu, ys, 1);
+  const double yy = HY ? __shfl_xor_sync(0xffffffffu, ys, 2) : 0.0;
+  const double yz = __shfl_xor_sync(0xffffffffu, ys, HY ? 4 : 2);
+  const Line1 lx = line_x<HY>(L, q, a1, a2);
+  const Line1 lz = line_z<HY>(L, q, a0, a1);
+  Line1 ly = lx;
+  if constexpr (HY) ly = line_y(L, q, a0, a2);
+  const double Tx0 = T[lx.base], Tx1 = T[lx.base + lx.sd], Tx2 = T[lx.base + 2 * lx.sd];
+  const double Ty0 = HY ? T[ly.base] : 0.0, Ty1 = HY ? T[ly.base + ly.sd] : 0.0, Ty2 = HY ? T[ly.base + 2 * ly.sd] : 0.0;
+  const double Tz0 = T[lz.base], Tz1 = T[lz.base + lz.sd], Tz2 = T[lz.base + 2 * lz.sd];
+  const double Sx = s_in(C, a0, Tx0, Tx1, Tx2), Sz = s_in(C, a2, Tz0, Tz1, Tz2);
+  const double Sy = HY ? s_in(C, a1, Ty0, Ty1, Ty2) : 0.0;
+  double sum = 0.0;
+  // lower cells, ascending cell index: z-, y-, x-
+  nb_lower(C, lz, a2, Tz0, y, q.pb, sum);
+  if constexpr (HY) nb_lower(C, ly, a1, Ty0, y, q.pb, sum);
+  nb_lower(C, lx, a0, Tx0, y, q.pb, sum);
+  // in-cell partners: smaller local index (flip a2, a1, a0 from 1 to 0), then larger (flip a0, a1, a2 from 0 to 1)
+  sum += a2 ? yz * Sz : 0.0;
+  if constexpr (HY) sum += a1 ? yy * Sy : 0.0;
+  sum += a0 ? yx * Sx : 0.0;
+  sum += a0 ? 0.0 : yx * Sx;
+  if constexpr (HY) sum += a1 ? 0.0 : yy * Sy;
+  sum += a2 ? 0.0 : yz * Sz;
+  // upper cells: x+, y+, z+
+  nb_upper(C, lx, a0, Tx2, y, q.pb, sum);
+  if constexpr (HY) nb_upper(C, ly, a1, Ty2, y, q.pb, sum);
+  nb_upper(C, lz, a2, Tz2, y, q.pb, sum);
+  return sum;
+}
+
 template <bool HY>
 __global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
                                                     const double* __restrict__ Dp, const double* __restrict__ rp,
                                                     const double* __restrict__ yin, double* __restrict__ yout,
                                                     double omega, int first, const MinresState* st) {
-  constexpr int NPL = HY ? 8 : 4;
   if (st && st->done) return;
-  Cell1 q = owned_cell1(L);
-  if (!q.ok) return;
-  q.pb = q.c * NPL;
+  const Dof1 d = owned_dof1<HY>(L);
+  const int p = d.q.pb + d.l;
   if (first) {
-#pragma unroll
-    for (int l = 0; l < NPL; ++l) yout[q.pb + l] = omega * (rp[q.pb + l] / Dp[q.pb + l]);
+    if (d.q.ok) yout[p] = omega * (rp[p] / Dp[p]);
     return;
   }
-  double yl[NPL];
-#pragma unroll
-  for (int l = 0; l < NPL; ++l) yl[l] = yin[q.pb + l];
-#pragma unroll
-  for (int l = 0; l < NPL; ++l) {
-    const double sum = q1_row_sum<HY, true>(L, C, q, T, yin, yl, l);
-    const double d = Dp[q.pb + l];
-    const double sy = d * yl[l] + sum;
-    yout[q.pb + l] = yl[l] + omega * ((rp[q.pb + l] - sy) / d);
-  }
+  const double ys = yin[p];
+  const double sum = q1_row_sum_dof<HY>(L, C, d, T, yin, ys);
+  const double dd = Dp[p];
+  const double sy = dd * ys + sum;
+  if (d.q.ok) yout[p] = ys + omega * ((rp[p] - sy) / dd);
 }
 
 // cell rhs = sum over the cell's dofs (local order) of the residual r - S y
@@ -521,19 +591,17 @@ __global__ void __launch_bounds__(BLK) k1_mg_restrict(Lay1 L, Rt1Const C, const 
                                                       const MinresState* st) {
   constexpr int NPL = HY ? 8 : 4;
   if (st && st->done) return;
-  Cell1 q = owned_cell1(L);
-  if (!q.ok) return;
-  q.pb = q.c * NPL;
-  double yl[NPL];
-#pragma unroll
-  for (int l = 0; l < NPL; ++l) yl[l] = y[q.pb + l];
+  const Dof1 d = owned_dof1<HY>(L);
+  const int p = d.q.pb + d.l;
+  const double ys = y[p];
+  const double sum = q1_row_sum_dof<HY>(L, C, d, T, y, ys);
+  const double res = rp[p] - (Dp[p] * ys + sum);
+  // ordered sum over the cell's lanes: ((0 + res_0) + res_1) + ...
+  const int lane0 = (threadIdx.x & 31) & ~(NPL - 1);
   double acc = 0.0;
 #pragma unroll
-  for (int l = 0; l < NPL; ++l) {
-    const double sum = q1_row_sum<HY, true>(L, C, q, T, y, yl, l);
-    acc += rp[q.pb + l] - (Dp[q.pb + l] * yl[l] + sum);
-  }
-  rc[q.i + L.NX * (q.j + L.NY * q.kl)] = acc;
+  for (int l = 0; l < NPL; ++l) acc += __shfl_sync(0xffffffffu, res, lane0 + l);
+  if (d.q.ok && d.l == 0) rc[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)] = acc;
 }
 
 template <bool HY>

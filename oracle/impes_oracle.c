@@ -274,39 +274,38 @@ static double canon_dot(const orc *o, const double *a, const double *b) {
   return tree256(v);
 }
 
-/* Canonical dot for RT1/Q1 Darcy vectors (csrc/rt1.cuh k1_darcy_apply / k1_dot_owned): blocks of 256
- * consecutive cells; each cell adds, per direction d (x, y, z), per transverse open-node pair (second
- * transverse direction outer, first inner), the products of its closed nodes 0 (lower face), 1 (interior)
- * and, on the upper boundary only, 2; then its pressure dofs in local order. */
+/* Canonical dot for RT1/Q1 Darcy vectors (csrc/rt1.cuh k1_darcy_apply / k1_dot_owned): one "thread" per L2 dof,
+ * blocks of 256 consecutive dofs (cell-major).  The thread of local index (a_0, a_1, a_2) adds, per direction
+ * d = x, y, z, the product of closed node a_d (0 = lower face node, 1 = interior node) of its line through the
+ * open nodes (a_e, e != d) -- and of node 2 when a_d = 1 on the upper boundary --, then its own pressure dof. */
 static inline long vidx(const orc *o, int d, int i0, int i1, int i2);
 static double canon_dot_rt1(const orc *o, const double *a, const double *b) {
-  const int dim = o->dim;
-  const long ncl = o->ncell, nblk = (ncl + 255) / 256;
+  const int dim = o->dim, npl = o->npl;
+  const long nd = o->ncell * npl, nblk = (nd + 255) / 256;
   double *partial = (double *)malloc(sizeof(double) * nblk);
   for (long blk = 0; blk < nblk; ++blk) {
     double v[256];
     for (int t = 0; t < 256; ++t) {
-      const long c = blk * 256 + t;
+      const long gt = blk * 256 + t;
       double acc = 0.0;
-      if (c < ncl) {
+      if (gt < nd) {
+        const long c = gt / npl;
+        const int l = (int)(gt % npl);
         const int cc[3] = {(int)(c % o->n[0]), (int)((c / o->n[0]) % o->n[1]), (int)(c / ((long)o->n[0] * o->n[1]))};
+        const int al[3] = {l & 1, (l >> 1) & 1, (l >> 2) & 1};
         for (int d = 0; d < dim; ++d) {
-          int tr[2], nt = 0;
-          for (int e = 0; e < dim; ++e) if (e != d) tr[nt++] = e;
-          for (int tf = 0; tf < (nt == 2 ? 2 : 1); ++tf)
-            for (int te = 0; te < 2; ++te) {
-              int g[3] = {0, 0, 0};
-              g[tr[0]] = 2 * cc[tr[0]] + te;
-              if (nt == 2) g[tr[1]] = 2 * cc[tr[1]] + tf;
-              const int ni = cc[d] + 1 == o->n[d] ? 3 : 2;
-              for (int i = 0; i < ni; ++i) {
-                g[d] = 2 * cc[d] + i;
-                const long f = vidx(o, d, g[0], g[1], g[2]);
-                acc += a[f] * b[f];
-              }
-            }
+          int g[3] = {0, 0, 0};
+          for (int e = 0; e < dim; ++e) g[e] = 2 * cc[e] + al[e];
+          long f = vidx(o, d, g[0], g[1], g[2]);
+          acc += a[f] * b[f];
+          if (al[d] == 1 && cc[d] + 1 == o->n[d]) {
+            g[d] = 2 * cc[d] + 2;
+            f = vidx(o, d, g[0], g[1], g[2]);
+            acc += a[f] * b[f];
+          }
         }
-        for (int l = 0; l < o->npl; ++l) { const long f = o->nv + c * o->npl + l; acc += a[f] * b[f]; }
+        const long f = o->nv + gt;
+        acc += a[f] * b[f];
       }
       v[t] = acc;
     }
