@@ -14,6 +14,24 @@ def slab_range(n_layers, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def slab_range_mg(n_layers, rank, world):
+    """Slabs of the multi-GPU multigrid mode (IMPES_SCHUR_MG, world > 1): cut in units of 2^m layers, m the
+    largest value (<= 6) with n_layers / 2^m >= world, so that the multigrid aggregates of the first m levels
+    never straddle two GPUs (csrc/api.cu create_impl).  256 layers on 8 GPUs -> m = 5, 32 layers each;
+    85 layers on 8 GPUs -> m = 3, units of 8 -> 16,16,16,8,8,8,8,5."""
+    if world == 1:
+        return 0, n_layers
+    m = 0
+    while m < 6 and (n_layers >> (m + 1)) >= world:
+        m += 1
+    unit = 1 << m
+    nu = (n_layers + unit - 1) // unit
+    base, rem = divmod(nu, world)
+    ulo = rank * base + min(rank, rem)
+    uhi = ulo + base + (1 if rank < rem else 0)
+    return ulo * unit, min(uhi * unit, n_layers)
+
+
 def owned_ranges(dim, nx, ny, nz, rank, world, order=0, slab=None):
     """Index ranges this rank owns in the native host layout (include/impes_b200.h):
     -> (ranges in a Darcy vector [V | P], ranges in a cell / saturation vector).

@@ -47,8 +47,9 @@ def test_driver_usage_and_exit_codes(host_bins):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("order", [0, 1])   # 1 = the reference's default spaces RT1 / L2-Q1 (-ov 1 -op 1 -os 0)
 @pytest.mark.parametrize("dim", [2, 3])
-def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim):
+def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim, order):
     """A whole run of the run_serial-compatible driver (K from a float32 file, 3 global steps) reproduces the
     oracle's loop: same MINRES iteration counts in the log, saturation dumps equal to float32 precision."""
     from incompressible_flow_b200 import workloads
@@ -61,7 +62,7 @@ def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim):
     dtg, dtl = (20.0, 1.0) if dim == 2 else (2.0, 0.125)
     h = 100.0 / nx
     common = ["-d", str(dim), "-nx", str(nx), "-ny", str(ny), "-nz", str(nz), "-sx", "100", "-sy", "100", "-sz", "100",
-              "-ov", "0", "-op", "0", "-os", "0", "-two-phase", "-tf", str(3 * dtg), "-dtg", str(dtg), "-dtl", str(dtl), "-vsg", "0",
+              "-ov", str(order), "-op", str(order), "-os", "0", "-two-phase", "-tf", str(3 * dtg), "-dtg", str(dtg), "-dtl", str(dtl), "-vsg", "0",
               "-K-file-x", str(kfile), "-K-file-y", str(kfile), "-K-file-z", str(kfile), "-outdir", str(out),
               "-extra", "t", "-darcy-maxiter", "5000"]
     if dim == 2:
@@ -74,7 +75,7 @@ def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim):
     its = [int(m) for m in re.findall(r"Darcy solver converged\. Iter = (\d+)", o.stdout)]
     assert "Number of global time steps: 3" in o.stdout and o.stdout.count("is done") == 3
     # oracle loop on the same inputs
-    d = workloads.make_desc(dim, nx, ny, nz, sx=100, sy=100, sz=100, maxiter=5000)
+    d = workloads.make_desc(dim, nx, ny, nz, sx=100, sy=100, sz=100, maxiter=5000, order=order, order_s=0)
     for w, c, r in ((d.injection, (0, 0, 0), h), (d.production, (100, 100 if dim == 2 else 0, 100), h)):
         w.center[0], w.center[1], w.center[2] = c
         w.radius, w.height = r, 100.0

@@ -134,7 +134,8 @@ def test_mass_cg_equals_diagonal_inverse(pkg, orc):
     assert rel(Sb, Sa) < 1e-14
 
 
-@pytest.mark.parametrize("cfg", [dict(dim=2, nx=40, ny=30), dict(dim=3, nx=12, ny=10, nz=8)])
+@pytest.mark.parametrize("cfg", [dict(dim=2, nx=40, ny=30), dict(dim=3, nx=12, ny=10, nz=8),
+                                 dict(dim=2, nx=14, ny=11, order=1, order_s=0), dict(dim=3, nx=6, ny=5, nz=4, order=1, order_s=0)])
 def test_arithmetic_modes_agree(pkg, orc, cfg):
     """The canonical arithmetic (closed-form RT0 element matrices, fixed dot tree) is the same algorithm as
     the MFEM-like one (quadrature-assembled, sequential sums): operators agree to round-off, iteration
@@ -203,7 +204,9 @@ def test_well_boxes_3d(pkg, orc):
     assert np.count_nonzero(g) == 10 and abs(g.sum()) == 0.0
 
 
-@pytest.mark.parametrize("cfg,lo,hi", [(dict(dim=2, nx=128, ny=128), 35, 50), (dict(dim=3, nx=32, ny=32, nz=16), 35, 50)])
+@pytest.mark.parametrize("cfg,lo,hi", [(dict(dim=2, nx=128, ny=128), 35, 50), (dict(dim=3, nx=32, ny=32, nz=16), 35, 50),
+                                       (dict(dim=2, nx=48, ny=48, order=1, order_s=0), 35, 50),
+                                       (dict(dim=3, nx=12, ny=12, nz=12, order=1, order_s=0), 33, 50)])
 def test_multigrid_preconditioner_mesh_independent(pkg, orc, cfg, lo, hi):
     """Throughput-mode oracle restatement (orc_mg.inc): the V-cycle is a symmetric positive operator, MINRES
     needs ~40 iterations where the reference's Gauss-Seidel preconditioner needs hundreds, and both converge
@@ -224,3 +227,23 @@ def test_multigrid_preconditioner_mesh_independent(pkg, orc, cfg, lo, hi):
     x2, st2, _ = o2.pressure_solve(S)
     assert st2.iterations > 4 * st.iterations
     assert rel(x[:o.nv], x2[:o.nv]) < 1e-4
+
+
+def test_rt1_discrete_divergence_and_mass_balance(pkg, orc):
+    """Appendix C.2/C.3 for the reference's default spaces (RT1 / L2-Q1, DG_0 saturation): sum g = 0, the
+    discrete divergence equation B u = -g holds to solver tolerance, and the DG_0 saturation driven by the
+    RT1 face fluxes conserves mass to round-off."""
+    d, o = build(pkg, orc, dim=2, nx=16, ny=16, K="lognormal", order=1, order_s=0, rtol=1e-10)
+    n = o.n_cells
+    g = o.rhs()[o.nv:]
+    assert abs(g.sum()) < 1e-12 * abs(g).max()
+    o.set_arith(1)
+    S0 = np.zeros(n)
+    x, st, rc = o.pressure_solve(S0)
+    assert rc == 0
+    B = o.csr("B")
+    assert np.linalg.norm(B @ x[:o.nv] - g) < 1e-7 * np.linalg.norm(g)
+    vol = (d.sx / d.nx) * (d.sy / d.ny)
+    S1, nsub = o.saturation_advance(x[:o.nv], S0, 10.0, 0.5)
+    # every sub-step adds saturation_source * |injection cells| * dt (one well cell here), boundary fluxes vanish
+    assert nsub == 20 and abs(S1.sum() * vol - 1.0 * vol * 10.0) < 1e-10 * vol * 10.0

@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, dim, nx, ny, nz, q):
+def _worker(rank, world, port, dim, nx, ny, nz, order, mg, q):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -27,12 +27,19 @@ def _worker(rank, world, port, dim, nx, ny, nz, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    darcy, cells = pkg.partition.owned_ranges(dim, nx, ny, nz, rank, world)
     n = nx * ny * (nz if dim == 3 else 1)
     nlay = nz if dim == 3 else ny
+    slab = pkg.partition.slab_range_mg(nlay, rank, world) if mg else None
+    darcy, cells = pkg.partition.owned_ranges(dim, nx, ny, nz, rank, world, order=order, slab=slab)
     plane = n // nlay
-    nv = (nx + 1) * ny * (nz if dim == 3 else 1) + (nx * (ny + 1) * nz if dim == 3 else 0) + plane * (nlay + 1)
-    ref_x = np.arange(nv + n, dtype=np.float64) + 1.0
+    if order == 0:
+        nv = (nx + 1) * ny * (nz if dim == 3 else 1) + (nx * (ny + 1) * nz if dim == 3 else 0) + plane * (nlay + 1)
+        np_ = n
+    else:   # RT1 node grids: 2n+1 closed nodes along the component, 2n open nodes across; 2^dim L2 dofs per cell
+        k = (2 * nz) if dim == 3 else 1
+        nv = (2 * nx + 1) * 2 * ny * k + 2 * nx * (2 * ny + 1) * k + (4 * nx * ny * (2 * nz + 1) if dim == 3 else 0)
+        np_ = n * 2 ** dim
+    ref_x = np.arange(nv + np_, dtype=np.float64) + 1.0
     ref_s = np.arange(n, dtype=np.float64) * 0.5 + 3.0
     ok = True
     for ref, own in ((ref_x, darcy), (ref_s, cells)):
@@ -53,13 +60,15 @@ def _worker(rank, world, port, dim, nx, ny, nz, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,dim,nx,ny,nz", [(2, 3, 5, 4, 7), (3, 2, 6, 8, 1), (2, 2, 4, 3, 1)])
-def test_slab_gather(world, dim, nx, ny, nz):
+@pytest.mark.parametrize("world,dim,nx,ny,nz,order,mg", [(2, 3, 5, 4, 7, 0, 0), (3, 2, 6, 8, 1, 0, 0), (2, 2, 4, 3, 1, 0, 0),
+                                                         (2, 3, 3, 4, 5, 1, 0), (3, 2, 5, 7, 1, 1, 0), (2, 3, 4, 3, 9, 1, 1),
+                                                         (3, 2, 6, 21, 1, 0, 1)])
+def test_slab_gather(world, dim, nx, ny, nz, order, mg):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dim, nx, ny, nz, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dim, nx, ny, nz, order, mg, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
@@ -73,3 +82,14 @@ def test_slab_ranges_balanced(pkg):
     r = [pkg.partition.slab_range(85, k, 8) for k in range(8)]
     assert [hi - lo for lo, hi in r] == [11, 11, 11, 11, 11, 10, 10, 10]
     assert r[0][0] == 0 and r[-1][1] == 85 and all(r[i][1] == r[i + 1][0] for i in range(7))
+
+
+def test_slab_ranges_multigrid_aligned(pkg):
+    """Multi-GPU multigrid mode: slabs in units of 2^m layers (aggregates never straddle GPUs)."""
+    r = [pkg.partition.slab_range_mg(256, k, 8) for k in range(8)]
+    assert [hi - lo for lo, hi in r] == [32] * 8
+    r = [pkg.partition.slab_range_mg(85, k, 8) for k in range(8)]
+    assert [hi - lo for lo, hi in r] == [16, 16, 16, 8, 8, 8, 8, 5]
+    assert r[0][0] == 0 and r[-1][1] == 85 and all(r[i][1] == r[i + 1][0] for i in range(7))
+    assert all(lo % 8 == 0 for lo, _ in r)
+    assert pkg.partition.slab_range_mg(21, 0, 2) == (0, 16) and pkg.partition.slab_range_mg(21, 1, 2) == (16, 21)
