@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "mg.cuh"
 #include "rt1.cuh"
+#include "rt1q.cuh"
 #include "nccl_shim.h"
 
 using namespace impes;
@@ -46,6 +47,11 @@ struct impes_ctx {
   int vec_n = 0, vec_offp = 0;  // length and p-offset of a Darcy-sized device vector in the active layout
   double* flux0 = nullptr;      // ord == 1: face fluxes of x in the RT0 dvec layout (input of K6)
   double* mg1_ya = nullptr;     // ord == 1: second iterate buffer of the Q1 multigrid level (p-part)
+  int os = 0, nsl = 1;          // saturation order (DG_os) and dofs per cell; os == 1 needs ord == 1 (rt1q.cuh)
+  QTab qt;
+  double* rlam = nullptr;       // os == 1: w_q / lambda(S(x_q)) at the mass-rule points, ncv x NQP
+  double* yup = nullptr;        // os == 1: upper-face-node element contributions of K1 pass A, ncv x NUP
+  int nqp = 0, nup = 0;
   Phys ph;
   SatParam sp;
   int dev = 0;
@@ -175,17 +181,19 @@ int dev_alloc(impes_ctx* h, double** p, long n) {
 // ---- host (global, native) <-> device (slab local) transfers -------------------------------
 
 // cvec (cell array with ghost planes) from a global cell array
-int upload_cells(impes_ctx* h, const double* host, double* dev) {
+// mult: dofs per cell (1 for cell arrays, nsl for a DG-Q1 saturation vector)
+int upload_cells(impes_ctx* h, const double* host, double* dev, int mult = 1) {
   const Lay& L = h->L;
   const int k0 = std::max(L.zlo - 1, 0), k1 = std::min(L.zhi + 1, L.NZ);
-  CK(cudaMemcpyAsync(dev + L.plane * (k0 - L.zlo + 1), host + L.plane * k0, sizeof(double) * L.plane * (k1 - k0),
+  const long pl = (long)L.plane * mult;
+  CK(cudaMemcpyAsync(dev + pl * (k0 - L.zlo + 1), host + pl * k0, sizeof(double) * pl * (k1 - k0),
                      cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
-int download_cells_owned(impes_ctx* h, const double* dev, double* host) {
+int download_cells_owned(impes_ctx* h, const double* dev, double* host, int mult = 1) {
   const Lay& L = h->L;
-  CK(cudaMemcpyAsync(host + L.plane * L.zlo, dev + L.plane, sizeof(double) * L.plane * L.nzl, cudaMemcpyDeviceToHost,
-                     h->stream));
+  const long pl = (long)L.plane * mult;
+  CK(cudaMemcpyAsync(host + pl * L.zlo, dev + pl, sizeof(double) * pl * L.nzl, cudaMemcpyDeviceToHost, h->stream));
   return 0;
 }
 
@@ -271,21 +279,22 @@ int download_dvec_owned(impes_ctx* h, const double* dev, double* host_v, double*
 
 // ---- halo exchange (world_size > 1): grouped ncclSend/Recv of whole planes ---------------------
 // up = towards rank+1.  Each (ptr, plane index) pair names a plane inside a (nzl+2)-plane region.
-int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool send_down_bottom_owned) {
+int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool send_down_bottom_owned, int mult = 1) {
   // send_up_top_owned:   my plane index nzl   (top owned)    -> upper rank's plane 0      (ghost below)
   // send_down_bottom_owned: my plane index 1 (bottom owned)  -> lower rank's plane nzl+1  (ghost above)
   if (h->L.nranks == 1) return 0;
   const Lay& L = h->L;
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
+  const size_t pl = (size_t)L.plane * mult;
   Scope sc(h, KC_COMM, 1);
   NK(h->nccl.GroupStart());
   if (send_up_top_owned) {
-    if (up >= 0) NK(h->nccl.Send(base + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
-    if (dn >= 0) NK(h->nccl.Recv(base, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
+    if (up >= 0) NK(h->nccl.Send(base + pl * L.nzl, pl, ncclFloat64, up, h->comm, h->stream));
+    if (dn >= 0) NK(h->nccl.Recv(base, pl, ncclFloat64, dn, h->comm, h->stream));
   }
   if (send_down_bottom_owned) {
-    if (dn >= 0) NK(h->nccl.Send(base + L.plane, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
-    if (up >= 0) NK(h->nccl.Recv(base + L.plane * (L.nzl + 1), (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
+    if (dn >= 0) NK(h->nccl.Send(base + pl, pl, ncclFloat64, dn, h->comm, h->stream));
+    if (up >= 0) NK(h->nccl.Recv(base + pl * (L.nzl + 1), pl, ncclFloat64, up, h->comm, h->stream));
   }
   NK(h->nccl.GroupEnd());
   return 0;
@@ -345,7 +354,20 @@ int mg_gather(impes_ctx* h, double* full, size_t pe);
 MgLevel mg_view(const impes_ctx* h, const MgLevel& v);
 int update_coeff(impes_ctx* h) {
   const Lay& L = h->L;
-  RET_IF(exchange_planes(h, h->S[h->scur], true, true));
+  RET_IF(exchange_planes(h, h->S[h->scur], true, true, h->nsl));
+  if (h->os == 1) {  // S in DG-Q1: 1/lambda at the mass-rule points, diag(M) by quadrature, Schur diagonal
+    Scope sc(h, KC_COEFF, 3);
+    const int g = (int)((L.ncv + BLK - 1) / BLK);
+    if (L.has_y) {
+      k1q_rlam<true><<<g, BLK, 0, h->stream>>>(L, h->ph, h->qt, h->S[h->scur], h->rlam);
+      k1q_md<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], h->Md, h->T);
+      k1_schur_diag<true><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, h->Md);
+    } else {
+      k1q_rlam<false><<<g, BLK, 0, h->stream>>>(L, h->ph, h->qt, h->S[h->scur], h->rlam);
+      k1q_md<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], h->Md, h->T);
+      k1_schur_diag<false><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, h->Md);
+    }
+  } else
   {
     Scope sc(h, KC_COEFF, 2);
     const int g = (int)((L.ncv + BLK - 1) / BLK);
@@ -394,6 +416,31 @@ int update_coeff(impes_ctx* h) {
 
 // ---- K1 ----------------------------------------------------------------------------------------
 int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState* st) {
+  if (h->os == 1) {  // variable coefficient inside the cells: element products (A), then face-node completion (B)
+    RET_IF(halo_darcy1(h, x));
+    {
+      Scope sc(h, KC_DARCY, 1);
+#define KQA(HY, DOT)                                                                                              \
+  k1q_apply_a<HY, DOT><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], \
+                                                             h->geo[0], h->geo[1], h->geo[2], x, y, h->yup, h->partial, \
+                                                             h->scal + 5, h->ticket, st)
+      if (h->L.has_y) { if (dot) KQA(true, true); else KQA(true, false); }
+      else { if (dot) KQA(false, true); else KQA(false, false); }
+#undef KQA
+    }
+    RET_IF(exchange_planes(h, h->yup, true, false, h->nup));  // the lower rank's top-plane contributions
+    {
+      Scope sc(h, KC_DARCY, 1);
+#define KQB(HY, DOT)                                                                                               \
+  k1q_apply_b<HY, DOT><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, x, y, h->yup, h->partial, h->scal + 0, h->scal + 5, \
+                                                             h->ticket, st)
+      if (h->L.has_y) { if (dot) KQB(true, true); else KQB(true, false); }
+      else { if (dot) KQB(false, true); else KQB(false, false); }
+#undef KQB
+    }
+    if (dot) RET_IF(allreduce_scalar(h, h->scal + 0));
+    return 0;
+  }
   if (h->ord == 1) {
     RET_IF(halo_darcy1(h, x));
     {
@@ -842,6 +889,10 @@ int n_substeps(const impes_ctx* h, double global_dt, double dt) {
 // f(S) over the whole cvec (after the ghost planes of S are in place)
 int launch_frac(impes_ctx* h, const double* S, double* F) {
   Scope sc(h, KC_SAT, 1);
+  if (h->os == 1) {
+    k_frac_flat<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv * h->nsl, h->ph, h->sp.two_phase, S, F);
+    return 0;
+  }
   const int g = (int)((h->L.ncv + BLK - 1) / BLK);
   k_frac_flow<<<g, BLK, 0, h->stream>>>(h->L, h->ph, h->sp.two_phase, S, F);
   return 0;
@@ -854,6 +905,16 @@ int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout, const d
   Scope sc(h, KC_SAT, 1);
   const Lay& L = h->L;
   const double* satv = h->ord == 1 ? h->flux0 : h->x;  // face fluxes in the RT0 dvec layout
+  if (h->os == 1) {  // DG-Q1: volume + face terms straight from the RT1 dofs (rt1q.cuh)
+    if (L.has_y) {
+      if (rate) k1q_sat<true, true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      else k1q_sat<true, false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+    } else {
+      if (rate) k1q_sat<false, true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      else k1q_sat<false, false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+    }
+    return 0;
+  }
   if (h->sat_mode == 0) {
     if (rate) k_sat_stream<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
     else k_sat_stream<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
@@ -877,7 +938,7 @@ int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout, const d
 }
 
 int sat_rate(impes_ctx* h, double* Sin, double* out) {  // out = M_phi^-1 (Kt f(Sin) + b)
-  RET_IF(exchange_planes(h, Sin, true, true));
+  RET_IF(exchange_planes(h, Sin, true, true, h->nsl));
   if (h->sat_mode == 0) {
     RET_IF(launch_frac(h, Sin, h->F[0]));
     return launch_sat(h, true, Sin, out, h->F[0], nullptr);
@@ -886,12 +947,12 @@ int sat_rate(impes_ctx* h, double* Sin, double* out) {  // out = M_phi^-1 (Kt f(
 }
 int axpby(impes_ctx* h, double a, const double* x, double b, const double* y, double* out) {
   Scope sc(h, KC_SAT, 1);
-  k_axpby<<<h->grid_vec, BLK, 0, h->stream>>>(h->L.ncv, a, x, b, y, out);
+  k_axpby<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv * h->nsl, a, x, b, y, out);
   return 0;
 }
 int xpby(impes_ctx* h, const double* x, double b, const double* y, double* out) {
   Scope sc(h, KC_SAT, 1);
-  k_xpby<<<h->grid_vec, BLK, 0, h->stream>>>(h->L.ncv, x, b, y, out);
+  k_xpby<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv * h->nsl, x, b, y, out);
   return 0;
 }
 
@@ -899,7 +960,7 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
   const int nt = n_substeps(h, global_dt, dt);
   if (nsub) *nsub = nt;
   h->sp.dt = dt;
-  if (h->ord == 1) {  // RT1 velocity -> face fluxes once per call (the velocity is frozen during the sub-steps)
+  if (h->ord == 1 && h->os == 0) {  // RT1 velocity -> face fluxes once per call (the velocity is frozen during the sub-steps)
     Scope sc(h, KC_SAT, 1);
     if (h->L.has_y) k1_face_flux<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
     else k1_face_flux<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
@@ -913,7 +974,7 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
   }
   if (ode != 1)
     for (int s = 0; s < 4; ++s)
-      if (!h->stage[s]) RET_IF(dev_alloc(h, &h->stage[s], h->L.ncv));
+      if (!h->stage[s]) RET_IF(dev_alloc(h, &h->stage[s], (long)h->L.ncv * h->nsl));
   for (int ti = 1; ti <= nt; ++ti) {
     double* S = h->S[h->scur];
     double* Sn = h->S[h->scur ^ 1];
@@ -921,10 +982,10 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
       if (h->sat_mode == 0) {
         // f(S) travels with S: F[scur] = f(S[scur]); only its ghost planes are exchanged per sub-step
         if (ti == 1) {
-          RET_IF(exchange_planes(h, S, true, true));
+          RET_IF(exchange_planes(h, S, true, true, h->nsl));
           RET_IF(launch_frac(h, S, h->F[h->scur]));
         } else {
-          RET_IF(exchange_planes(h, h->F[h->scur], true, true));
+          RET_IF(exchange_planes(h, h->F[h->scur], true, true, h->nsl));
         }
         RET_IF(launch_sat(h, false, S, Sn, h->F[h->scur], h->F[h->scur ^ 1]));
       } else {
@@ -1035,7 +1096,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   for (double* b : h->mg_bufs)
@@ -1058,10 +1119,13 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   if (!Kx || !Ky || (d.dim == 3 && !Kz)) { h->err = "permeability arrays missing"; return IMPES_ERR_BAD_ARG; }
   if (d.order_v == 0 && d.order_p == 0 && d.order_s == 0) h->ord = 0;
   else if (d.order_v == 1 && d.order_p == 1 && d.order_s == 0) h->ord = 1;
+  else if (d.order_v == 1 && d.order_p == 1 && d.order_s == 1) { h->ord = 1; h->os = 1; }
   else {
-    h->err = "GPU path implements -ov 0 -op 0 -os 0 (RT0/P0/P0) and -ov 1 -op 1 -os 0 (RT1/Q1/P0, the reference default)";
+    h->err = "GPU path implements -ov 0 -op 0 -os 0 (RT0/P0/P0), -ov 1 -op 1 -os 0 (RT1/Q1/P0, the reference default) "
+             "and -ov 1 -op 1 -os 1 (RT1/Q1/DG-Q1)";
     return IMPES_ERR_UNSUPPORTED;
   }
+  h->nsl = h->os == 1 ? (d.dim == 3 ? 8 : 4) : 1;
   if (d.world_size < 1 || d.rank < 0 || d.rank >= d.world_size) { h->err = "bad rank/world_size"; return IMPES_ERR_BAD_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1168,6 +1232,46 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
       for (int i = 0; i < 3; ++i) h->rc.Bv[a][i] = -(G[a][i] * wt);
     h->rc.wflux = wt;
     h->grid_dofs1 = (int)(((long)L.ncl * Q.npl + BLK - 1) / BLK);
+  }
+  if (h->os == 1) {  // quadrature and basis tables of rt1q.cuh
+    QTab& t = h->qt;
+    memset(&t, 0, sizeof t);
+    const int nq = d.dim == 3 ? 4 : 3, nf = d.dim == 3 ? 3 : 2;
+    double gx[4], gwt[4], fx[3];
+    auto gauss = [](int n, double* x, double* w) {  // Gauss-Legendre on [0,1], ascending
+      if (n == 2) { const double a = 0.5 / sqrt(3.0); x[0] = 0.5 - a; x[1] = 0.5 + a; w[0] = w[1] = 0.5; }
+      else if (n == 3) { const double a = 0.5 * sqrt(0.6); x[0] = 0.5 - a; x[1] = 0.5; x[2] = 0.5 + a; w[0] = w[2] = 5.0 / 18.0; w[1] = 8.0 / 18.0; }
+      else {
+        const double r = sqrt(1.2), a = 0.5 * sqrt((3.0 - 2.0 * r) / 7.0), b = 0.5 * sqrt((3.0 + 2.0 * r) / 7.0);
+        const double wa = (18.0 + sqrt(30.0)) / 72.0, wb = (18.0 - sqrt(30.0)) / 72.0;
+        x[0] = 0.5 - b; x[1] = 0.5 - a; x[2] = 0.5 + a; x[3] = 0.5 + b; w[0] = w[3] = wb; w[1] = w[2] = wa;
+      }
+    };
+    gauss(nq, gx, gwt);
+    gauss(nf, fx, t.fw);
+    const double g1 = 0.5 / sqrt(3.0), on[2] = {0.5 - g1, 0.5 + g1}, cn[3] = {0.0, 0.5, 1.0};
+    auto lagr = [](const double* nodes, int nn, int a, double x) {
+      double v = 1.0;
+      for (int m = 0; m < nn; ++m) if (m != a) v *= (x - nodes[m]) / (nodes[a] - nodes[m]);
+      return v;
+    };
+    for (int q = 0; q < nq; ++q) {
+      t.gw[q] = gwt[q];
+      for (int i = 0; i < 3; ++i) t.C[q][i] = lagr(cn, 3, i, gx[q]);
+      for (int a = 0; a < 2; ++a) t.O[q][a] = lagr(on, 2, a, gx[q]);
+    }
+    for (int q = 0; q < nf; ++q)
+      for (int a = 0; a < 2; ++a) t.OF[q][a] = lagr(on, 2, a, fx[q]);
+    for (int a = 0; a < 2; ++a) {
+      for (int i = 0; i < 3; ++i) t.LC[a][i] = lagr(cn, 3, i, on[a]);
+      t.E0[a] = lagr(on, 2, a, 0.0);
+      t.E1[a] = lagr(on, 2, a, 1.0);
+      t.sn[a] = on[a];
+    }
+    t.dl[0] = 1.0 / (on[0] - on[1]); t.dl[1] = 1.0 / (on[1] - on[0]);
+    t.wv = d.dim == 3 ? 0.125 : 0.25;
+    h->nqp = d.dim == 3 ? 64 : 9;
+    h->nup = d.dim == 3 ? 12 : 4;
   }
   h->ph.two_phase = d.two_phase; h->ph.Sor = d.Sor; h->ph.Swc = d.Swc; h->ph.mu_w = d.mu_w; h->ph.mu_o = d.mu_o;
   h->ph.den = 1. - d.Sor - d.Swc; h->ph.rden = 1.0 / h->ph.den; h->ph.rmu_w = 1.0 / d.mu_w; h->ph.rmu_o = 1.0 / d.mu_o;
@@ -1333,10 +1437,15 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     RET_IF(upload_cells(h, ph.data(), h->phi));
     CK(cudaStreamSynchronize(h->stream));
   }
-  RET_IF(dev_alloc(h, &h->S[0], L.ncv));
-  RET_IF(dev_alloc(h, &h->S[1], L.ncv));
-  RET_IF(dev_alloc(h, &h->F[0], L.ncv));
-  RET_IF(dev_alloc(h, &h->F[1], L.ncv));
+  RET_IF(dev_alloc(h, &h->S[0], (long)L.ncv * h->nsl));
+  RET_IF(dev_alloc(h, &h->S[1], (long)L.ncv * h->nsl));
+  RET_IF(dev_alloc(h, &h->F[0], (long)L.ncv * h->nsl));
+  RET_IF(dev_alloc(h, &h->F[1], (long)L.ncv * h->nsl));
+  if (h->os == 1) {
+    RET_IF(dev_alloc(h, &h->rlam, (long)L.ncv * h->nqp));
+    RET_IF(dev_alloc(h, &h->yup, (long)L.ncv * h->nup));
+    h->sat_mode = 0;  // the DG-Q1 kernel always carries f(S)
+  }
   double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
   for (double** v : vecs) RET_IF(dev_alloc(h, v, h->vec_n));
   if (h->ord == 1) RET_IF(dev_alloc(h, &h->flux0, L.ntot));
@@ -1461,7 +1570,7 @@ API int impes_get_dims(impes_handle h, impes_dims* out) {
   if (!h || !out) return IMPES_ERR_BAD_ARG;
   memset(out, 0, sizeof *out);
   out->n_cells = h->g_ncell;
-  out->n_v = h->g_nv; out->n_p = h->g_np; out->n_s = h->g_ncell;
+  out->n_v = h->g_nv; out->n_p = h->g_np; out->n_s = h->g_ncell * h->nsl;
   out->n_v_comp[0] = h->g_nvx;
   if (h->d.dim == 3) { out->n_v_comp[1] = h->g_nvy; out->n_v_comp[2] = h->g_nvz; }
   else { out->n_v_comp[1] = h->g_nvz; out->n_v_comp[2] = 0; }
@@ -1492,7 +1601,7 @@ API int impes_set_field(impes_handle h, int which, const double* host) {
   RET_IF(check_handle(h));
   if (!host) return IMPES_ERR_BAD_ARG;
   switch (which) {
-    case IMPES_FIELD_SATURATION: RET_IF(upload_cells(h, host, h->S[h->scur])); h->coeff_valid = false; break;
+    case IMPES_FIELD_SATURATION: RET_IF(upload_cells(h, host, h->S[h->scur], h->nsl)); h->coeff_valid = false; break;
     case IMPES_FIELD_VELOCITY: RET_IF(upload_dvec(h, host, nullptr, h->x)); break;
     case IMPES_FIELD_PRESSURE: RET_IF(upload_dvec(h, nullptr, host, h->x)); break;
     case IMPES_FIELD_DARCY_X: RET_IF(upload_dvec(h, host, host + h->g_nv, h->x)); break;
@@ -1506,7 +1615,7 @@ API int impes_get_field(impes_handle h, int which, double* host) {
   RET_IF(check_handle(h));
   if (!host) return IMPES_ERR_BAD_ARG;
   switch (which) {
-    case IMPES_FIELD_SATURATION: RET_IF(download_cells_owned(h, h->S[h->scur], host)); break;
+    case IMPES_FIELD_SATURATION: RET_IF(download_cells_owned(h, h->S[h->scur], host, h->nsl)); break;
     case IMPES_FIELD_VELOCITY: RET_IF(download_dvec_owned(h, h->x, host, nullptr)); break;
     case IMPES_FIELD_PRESSURE: RET_IF(download_dvec_owned(h, h->x, nullptr, host)); break;
     case IMPES_FIELD_DARCY_X: RET_IF(download_dvec_owned(h, h->x, host, host + h->g_nv)); break;
@@ -1529,7 +1638,7 @@ API int impes_pressure_solve(impes_handle h, const double* S_host, double* x_hos
   if (!stats) stats = &loc;
   memset(stats, 0, sizeof *stats);
   auto t0 = std::chrono::steady_clock::now();
-  if (S_host) RET_IF(upload_cells(h, S_host, h->S[h->scur]));
+  if (S_host) RET_IF(upload_cells(h, S_host, h->S[h->scur], h->nsl));
   const int rc = pressure_solve_device(h, stats);
   if (rc && rc != IMPES_ERR_NOT_CONVERGED) return rc;
   if (x_host) {
@@ -1546,9 +1655,9 @@ API int impes_saturation_advance(impes_handle h, const double* V_host, double* S
   RET_IF(check_handle(h));
   if (!(dt_local > 0)) { h->err = "dt_local must be > 0"; return IMPES_ERR_BAD_ARG; }
   if (V_host) RET_IF(upload_dvec(h, V_host, nullptr, h->x));
-  if (S_inout) RET_IF(upload_cells(h, S_inout, h->S[h->scur]));
+  if (S_inout) RET_IF(upload_cells(h, S_inout, h->S[h->scur], h->nsl));
   RET_IF(saturation_device(h, global_dt, dt_local, n_substeps_out));
-  if (S_inout) RET_IF(download_cells_owned(h, h->S[h->scur], S_inout));
+  if (S_inout) RET_IF(download_cells_owned(h, h->S[h->scur], S_inout, h->nsl));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1558,7 +1667,11 @@ API int impes_guards(impes_handle h, int64_t* n_nonfinite, double* s_max) {
   CK(cudaMemsetAsync(h->guard, 0, sizeof(unsigned long long) * 2, h->stream));
   {
     Scope sc(h, KC_MISC, 1);
-    k_guards<<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->S[h->scur], h->guard, h->guard + 1);
+    if (h->os == 1)
+      k_guards_flat<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncl * h->nsl, h->S[h->scur] + (long)h->L.plane * h->nsl,
+                                                        h->guard, h->guard + 1);
+    else
+      k_guards<<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->S[h->scur], h->guard, h->guard + 1);
   }
   unsigned long long hg[2];
   CK(cudaMemcpyAsync(hg, h->guard, sizeof hg, cudaMemcpyDeviceToHost, h->stream));

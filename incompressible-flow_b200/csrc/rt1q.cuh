@@ -1,0 +1,535 @@
+// rt1q.cuh -- sm_100a kernels for `-ov 1 -op 1 -os 1` (RT1 / L2-Q1 velocity-pressure, saturation in DG-Q1:
+// BASELINE config C5).  With S in DG-Q1 the mobility varies inside a cell, so
+//   * the RT1 mass matrix loses its line structure: M_d|cell = (geo_d / K_d) Phi^T diag(w_q / lambda(S(x_q))) Phi
+//     is a dense 12x12 block per direction and the quadrature rule (4^3 Gauss points in 3-D, 3^2 in 2-D:
+//     order OrderW + 2 el.order [MFEM-recall]) is part of the operator's definition;
+//   * the saturation operator gets a volume term and face integrals with upwinding per face quadrature point
+//     (SURVEY A.5): Kt = Convection(v,1)^T - DGTrace(v,1,1/2) [REF src/saturation_solver.cpp:32-35,53-55].
+// B, the right-hand side, S = B diag(M)^-1 B^T and both Schur preconditioners keep the structure of rt1.cuh:
+// only diag(M) (hence T = 1/diag(M)) changes.
+//
+// Parity: these kernels evaluate the operators matrix-free in sum-factorised form, the oracle assembles element
+// matrices entry by entry; the two agree to round-off (tests: 1e-13 relative per operator application), not bit
+// for bit -- a canonical-arithmetic restatement of this path does not exist yet.
+// FMA contraction is off for the file (arithmetic contract of kernels.cuh); the dense element products below use
+// explicit __fma_rn because they are not part of a bit-exact contract.
+#pragma once
+#include "rt1.cuh"
+
+namespace impes {
+
+struct QTab {
+  double gw[4];      // mass rule on [0,1]: 4 points (3-D) / 3 points (2-D)
+  double C[4][3];    // closed basis (Gauss-Lobatto nodes 0, 1/2, 1) at the mass-rule points
+  double O[4][2];    // open / L2 / DG basis (the 2 Gauss nodes) at the mass-rule points
+  double fw[3];      // face rule of the DG trace integrator: 3 points (3-D) / 2 points (2-D)
+  double OF[3][2];   // open basis at the face-rule points
+  double LC[2][3];   // closed basis at the two DG nodes (volume term: collocated 2-point rule, exact here)
+  double E0[2], E1[2];  // open basis at xi = 0 and xi = 1 (element traces)
+  double dl[2];      // derivative of the open basis (constant): -sqrt 3, +sqrt 3
+  double sn[2];      // the DG / L2 nodes 1/2 -+ 1/(2 sqrt 3)
+  double wv;         // weight of a DG node in the collocated rule: (1/2)^dim
+};
+
+template <bool HY>
+struct QD {
+  static constexpr int NQ = HY ? 4 : 3;     // mass-rule points per direction
+  static constexpr int NQY = HY ? 4 : 1;
+  static constexpr int NQP = NQ * NQY * NQ; // per cell
+  static constexpr int NSL = HY ? 8 : 4;    // DG-Q1 / L2-Q1 dofs per cell
+  static constexpr int NL = HY ? 4 : 2;     // lines per direction and cell
+  static constexpr int NDIR = HY ? 3 : 2;
+  static constexpr int NUP = NDIR * NL;     // upper-face-node contributions per cell
+  static constexpr int NF = HY ? 3 : 2;     // face-rule points per transverse direction
+};
+
+// open-basis value / weight along internal direction `dir` (2-D: the absent y direction has one node, basis 1)
+template <bool HY>
+__device__ __forceinline__ double ob(const QTab& tb, int dir, int q, int t) { return (!HY && dir == 1) ? 1.0 : tb.O[q][t]; }
+
+// ---------------------------------------------------------------------------------------
+// K4 (os = 1): w_q / lambda(S(x_q)) at the mass-rule points of every cell (ghost planes included)
+// CWVectorCoefficient::Eval with a DG-Q1 GridFunctionCoefficient [REF src/param.hpp:246-261]
+// ---------------------------------------------------------------------------------------
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1q_rlam(Lay L, Phys ph, QTab tb, const double* __restrict__ S,
+                                                double* __restrict__ rlam) {
+  using Q = QD<HY>;
+  const int c = blockIdx.x * BLK + threadIdx.x;
+  if (c >= L.ncv) return;
+  const int k = c / L.plane - 1 + L.zlo;
+  double* out = rlam + (long)c * Q::NQP;
+  if (k < 0 || k >= L.NZ) {
+    for (int q = 0; q < Q::NQP; ++q) out[q] = 0.0;
+    return;
+  }
+  double s[Q::NSL];
+#pragma unroll
+  for (int m = 0; m < Q::NSL; ++m) s[m] = S[(long)c * Q::NSL + m];
+  for (int q2 = 0; q2 < Q::NQ; ++q2)
+    for (int q1 = 0; q1 < Q::NQY; ++q1)
+      for (int q0 = 0; q0 < Q::NQ; ++q0) {
+        double sq = 0.0;
+#pragma unroll
+        for (int m = 0; m < Q::NSL; ++m) {
+          const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
+          sq += s[m] * (tb.O[q0][m0] * ob<HY>(tb, 1, q1, m1) * tb.O[q2][m2]);
+        }
+        const double w = tb.gw[q0] * (HY ? tb.gw[q1] : 1.0) * tb.gw[q2];
+        out[q0 + Q::NQ * (q1 + Q::NQY * q2)] = w / lambda_of(ph, sq);
+      }
+}
+
+// transverse directions (e < f) of direction D and the stride of a mass-rule point index along each direction
+template <bool HY, int D>
+struct QDir {
+  static constexpr int E = D == 0 ? 1 : 0, F = D == 2 ? 1 : 2;
+  __host__ __device__ static constexpr int nq(int dir) { return dir == 1 ? QD<HY>::NQY : QD<HY>::NQ; }
+  __host__ __device__ static constexpr int sq(int dir) { return dir == 0 ? 1 : (dir == 1 ? QD<HY>::NQ : QD<HY>::NQ * QD<HY>::NQY); }
+  __host__ __device__ static constexpr int no(int dir) { return (dir == 1 && !HY) ? 1 : 2; }  // open nodes along a transverse direction
+};
+
+template <bool HY, int D>
+__device__ __forceinline__ Line1 line_of(const Lay1& L, const Cell1& q, int te, int tf) {
+  if constexpr (D == 0) return line_x<HY>(L, q, te, tf);
+  else if constexpr (D == 1) return line_y(L, q, te, tf);
+  else return line_z<HY>(L, q, te, tf);
+}
+
+// sum over the cell's mass-rule points of c_q phi_(i,te,tf)(q)^2
+template <bool HY, int D>
+__device__ __forceinline__ double q_diag(const QTab& tb, const double* __restrict__ rl, int i, int te, int tf) {
+  using R = QDir<HY, D>;
+  double s = 0.0;
+  for (int qf = 0; qf < R::nq(R::F); ++qf)
+    for (int qe = 0; qe < R::nq(R::E); ++qe) {
+      const double oe = ob<HY>(tb, R::E, qe, te), of = ob<HY>(tb, R::F, qf, tf);
+      const double oo = (oe * oe) * (of * of);
+      for (int qd = 0; qd < QD<HY>::NQ; ++qd) {
+        const double cb = tb.C[qd][i];
+        s += rl[qd * R::sq(D) + qe * R::sq(R::E) + qf * R::sq(R::F)] * (cb * cb) * oo;
+      }
+    }
+  return s;
+}
+
+// diag(M) and T = 1/diag(M) per velocity node of direction D (1 / 0 on eliminated boundary nodes)
+template <bool HY, int D>
+__device__ __forceinline__ void q_md_dir(const Lay1& L, const Cell1& q, const QTab& tb, const double* __restrict__ rlam,
+                                         const double* __restrict__ K, double geo, double* __restrict__ Md,
+                                         double* __restrict__ T) {
+  using R = QDir<HY, D>;
+  using Q = QD<HY>;
+  const double* rl = rlam + (long)q.c * Q::NQP;
+  const double sc = geo / K[q.c];
+  for (int tf = 0; tf < R::no(R::F); ++tf)
+    for (int te = 0; te < R::no(R::E); ++te) {
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      if (l.cd > 0) {
+        const int cl = q.c - l.cstride;
+        const double md = (geo / K[cl]) * q_diag<HY, D>(tb, rlam + (long)cl * Q::NQP, 2, te, tf) + sc * q_diag<HY, D>(tb, rl, 0, te, tf);
+        Md[l.base] = md; T[l.base] = 1.0 / md;
+      } else { Md[l.base] = 1.0; T[l.base] = 0.0; }
+      const double md1 = sc * q_diag<HY, D>(tb, rl, 1, te, tf);
+      Md[l.base + l.sd] = md1; T[l.base + l.sd] = 1.0 / md1;
+      if (l.cd + 1 == l.nd) { Md[l.base + 2 * l.sd] = 1.0; T[l.base + 2 * l.sd] = 0.0; }
+      else if (D == 2 && q.k == L.zhi - 1) {  // ghost-above node plane of a slab: needed by the Schur kernels
+        const int cu = q.c + l.cstride;
+        const double md = sc * q_diag<HY, D>(tb, rl, 2, te, tf) + (geo / K[cu]) * q_diag<HY, D>(tb, rlam + (long)cu * Q::NQP, 0, te, tf);
+        Md[l.base + 2 * l.sd] = md; T[l.base + 2 * l.sd] = 1.0 / md;
+      }
+    }
+}
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1q_md(Lay1 L, QTab tb, const double* __restrict__ rlam,
+                                              const double* __restrict__ Kx, const double* __restrict__ Ky,
+                                              const double* __restrict__ Kz, double gx, double gy, double gz,
+                                              double* __restrict__ Md, double* __restrict__ T) {
+  const Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  q_md_dir<HY, 0>(L, q, tb, rlam, Kx, gx, Md, T);
+  if constexpr (HY) q_md_dir<HY, 1>(L, q, tb, rlam, Ky, gy, Md, T);
+  q_md_dir<HY, 2>(L, q, tb, rlam, Kz, gz, Md, T);
+}
+
+// diagonal of S = B diag(M)^-1 B^T per L2 dof from T (p-part of Md); same terms and order as line_coeff
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1_schur_diag(Lay1 L, Rt1Const C, const double* __restrict__ T,
+                                                     double* __restrict__ Md) {
+  const Dof1 d = owned_dof1<HY>(L);
+  if (!d.q.ok) return;
+  const Cell1& q = d.q;
+  const int l = d.l;
+  const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
+  double D = 0.0;
+  {
+    const Line1 ln = line_x<HY>(L, q, a1, a2);
+    if (ln.cd > 0) D += BV(a0, 0) * (BV(a0, 0) * T[ln.base]);
+    D += BV(a0, 1) * (BV(a0, 1) * T[ln.base + ln.sd]);
+    if (ln.cd + 1 < ln.nd) D += BV(a0, 2) * (BV(a0, 2) * T[ln.base + 2 * ln.sd]);
+  }
+  if constexpr (HY) {
+    const Line1 ln = line_y(L, q, a0, a2);
+    if (ln.cd > 0) D += BV(a1, 0) * (BV(a1, 0) * T[ln.base]);
+    D += BV(a1, 1) * (BV(a1, 1) * T[ln.base + ln.sd]);
+    if (ln.cd + 1 < ln.nd) D += BV(a1, 2) * (BV(a1, 2) * T[ln.base + 2 * ln.sd]);
+  }
+  {
+    const Line1 ln = line_z<HY>(L, q, a0, a1);
+    if (ln.cd > 0) D += BV(a2, 0) * (BV(a2, 0) * T[ln.base]);
+    D += BV(a2, 1) * (BV(a2, 1) * T[ln.base + ln.sd]);
+    if (ln.cd + 1 < ln.nd) D += BV(a2, 2) * (BV(a2, 2) * T[ln.base + 2 * ln.sd]);
+  }
+  Md[L.off_p + q.pb + l] = D;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 (os = 1), pass A: one thread per owned cell applies its three dense element blocks
+//   y_loc = (geo_d / K_d) Phi^T diag(c_q) Phi x_loc          (c_q = w_q / lambda_q from k1q_rlam)
+// in sum-factorised form (per transverse point pair: collapse the open directions, run the 4-point line along d,
+// expand back), adds the line-structured B^T p terms, computes the pressure rows, and writes
+//   interior-node rows: complete;  lower-face-node rows: own element + B^T (the lower cell's element part is added
+//   by pass B);  upper-face-node contributions: to yup[cell][dir][line] for the upper neighbour's pass B.
+// Eliminated boundary nodes enter with x = 0 and keep identity rows [REF src/pressure_solver.cpp:56-61].
+// ---------------------------------------------------------------------------------------
+template <bool HY, int D>
+__device__ __forceinline__ void elem_apply(const QTab& tb, const double* __restrict__ rl, const double (&xl)[12],
+                                           double (&yl)[12]) {
+  using R = QDir<HY, D>;
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F);
+#pragma unroll
+  for (int n = 0; n < 12; ++n) yl[n] = 0.0;
+  for (int qf = 0; qf < R::nq(R::F); ++qf)
+    for (int qe = 0; qe < R::nq(R::E); ++qe) {
+      double oo[NOE * NOF], v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+        for (int te = 0; te < NOE; ++te) {
+          const double o2 = ob<HY>(tb, R::E, qe, te) * ob<HY>(tb, R::F, qf, tf);
+          oo[te + NOE * tf] = o2;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) v[i] = __fma_rn(o2, xl[i + 3 * (te + NOE * tf)], v[i]);
+        }
+      double r[3] = {0.0, 0.0, 0.0};
+      const double* rq = rl + qe * R::sq(R::E) + qf * R::sq(R::F);
+#pragma unroll
+      for (int qd = 0; qd < QD<HY>::NQ; ++qd) {
+        const double u = __fma_rn(tb.C[qd][2], v[2], __fma_rn(tb.C[qd][1], v[1], tb.C[qd][0] * v[0]));
+        const double cu = rq[qd * R::sq(D)] * u;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = __fma_rn(tb.C[qd][i], cu, r[i]);
+      }
+#pragma unroll
+      for (int t = 0; t < NOE * NOF; ++t)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) yl[i + 3 * t] = __fma_rn(oo[t], r[i], yl[i + 3 * t]);
+    }
+}
+
+template <bool HY, int D, bool DOT>
+__device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, const Rt1Const& C, const QTab& tb,
+                                            const double* __restrict__ rlam, const double* __restrict__ K, double geo,
+                                            const double* __restrict__ x, double* __restrict__ y,
+                                            double* __restrict__ yup, const double (&pc)[QD<HY>::NSL],
+                                            double (&yp)[QD<HY>::NSL], double& acc) {
+  using R = QDir<HY, D>;
+  using Q = QD<HY>;
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F);
+  constexpr int DI = HY ? D : (D == 0 ? 0 : 1);  // index of the direction among the present ones
+  double xl[12], yl[12], x0r[4], x2r[4];
+  int cd = 0, nd = 1;
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      const int t = te + NOE * tf;
+      cd = l.cd; nd = l.nd;
+      x0r[t] = x[l.base]; x2r[t] = x[l.base + 2 * l.sd];
+      xl[0 + 3 * t] = l.cd > 0 ? x0r[t] : 0.0;
+      xl[1 + 3 * t] = x[l.base + l.sd];
+      xl[2 + 3 * t] = l.cd + 1 < l.nd ? x2r[t] : 0.0;
+    }
+#pragma unroll
+  for (int n = 3 * NOE * NOF; n < 12; ++n) xl[n] = 0.0;
+  elem_apply<HY, D>(tb, rlam + (long)q.c * Q::NQP, xl, yl);
+  const double sc = geo / K[q.c];
+  const int pb = q.pb;  // owned_cell1: dvec1 index of the cell's first pressure dof
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      const int t = te + NOE * tf;
+      const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
+      const int ps = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));
+      const double pc0 = pc[lp], pc1 = pc[lp + ps];
+      const double x0 = xl[3 * t], x1 = xl[1 + 3 * t], x2 = xl[2 + 3 * t];
+      {  // interior node
+        double tt = 0.0;
+        tt += C.Bv[0][1] * pc0; tt += C.Bv[1][1] * pc1;
+        const double y1 = sc * yl[1 + 3 * t] + tt;
+        y[l.base + l.sd] = y1;
+        if (DOT) acc += x1 * y1;
+      }
+      if (cd > 0) {  // lower face node: own element part + B^T; completed by pass B
+        const double* pL = x + (pb - l.pdn + lp);
+        double tt = 0.0;
+        tt += C.Bv[0][2] * pL[0]; tt += C.Bv[1][2] * pL[ps]; tt += C.Bv[0][0] * pc0; tt += C.Bv[1][0] * pc1;
+        y[l.base] = sc * yl[3 * t] + tt;
+      } else {
+        y[l.base] = x0r[t];
+        if (DOT) acc += x0r[t] * x0r[t];
+      }
+      if (cd + 1 < nd) yup[(long)q.c * Q::NUP + DI * Q::NL + t] = sc * yl[2 + 3 * t];
+      else {
+        y[l.base + 2 * l.sd] = x2r[t];
+        if (DOT) acc += x2r[t] * x2r[t];
+      }
+      // pressure rows (eliminated columns carry x = 0)
+      yp[lp] += C.Bv[0][0] * x0; yp[lp] += C.Bv[0][1] * x1; yp[lp] += C.Bv[0][2] * x2;
+      yp[lp + ps] += C.Bv[1][0] * x0; yp[lp + ps] += C.Bv[1][1] * x1; yp[lp + ps] += C.Bv[1][2] * x2;
+    }
+}
+
+template <bool HY, bool DOT>
+__global__ void __launch_bounds__(BLK) k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam,
+                                                   const double* __restrict__ Kx, const double* __restrict__ Ky,
+                                                   const double* __restrict__ Kz, double gx, double gy, double gz,
+                                                   const double* __restrict__ x, double* __restrict__ y,
+                                                   double* __restrict__ yup, double* partial, double* out,
+                                                   unsigned* ticket, const MinresState* st) {
+  using Q = QD<HY>;
+  if (st && st->done) return;
+  const Cell1 q = owned_cell1(L);
+  double acc = 0.0;
+  if (q.ok) {
+    double pc[Q::NSL], yp[Q::NSL];
+    const int pb = q.pb;
+#pragma unroll
+    for (int l = 0; l < Q::NSL; ++l) { pc[l] = x[pb + l]; yp[l] = 0.0; }
+    q_apply_dir<HY, 0, DOT>(L, q, C, tb, rlam, Kx, gx, x, y, yup, pc, yp, acc);
+    if constexpr (HY) q_apply_dir<HY, 1, DOT>(L, q, C, tb, rlam, Ky, gy, x, y, yup, pc, yp, acc);
+    q_apply_dir<HY, 2, DOT>(L, q, C, tb, rlam, Kz, gz, x, y, yup, pc, yp, acc);
+#pragma unroll
+    for (int l = 0; l < Q::NSL; ++l) {
+      y[pb + l] = yp[l];
+      if (DOT) acc += pc[l] * yp[l];
+    }
+  }
+  if (DOT) finish_dot(acc, partial, out, ticket);
+}
+
+// pass B: lower-face-node rows += the lower cell's element contribution; the dot gets their products and the
+// partial result of pass A
+template <bool HY, int D, bool DOT>
+__device__ __forceinline__ void q_face_dir(const Lay1& L, const Cell1& q, const double* __restrict__ x,
+                                           double* __restrict__ y, const double* __restrict__ yup, double& acc) {
+  using R = QDir<HY, D>;
+  using Q = QD<HY>;
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F);
+  constexpr int DI = HY ? D : (D == 0 ? 0 : 1);
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      if (l.cd > 0) {
+        const double yv = y[l.base] + yup[(long)(q.c - l.cstride) * Q::NUP + DI * Q::NL + te + NOE * tf];
+        y[l.base] = yv;
+        if (DOT) acc += x[l.base] * yv;
+      }
+    }
+}
+template <bool HY, bool DOT>
+__global__ void __launch_bounds__(BLK) k1q_apply_b(Lay1 L, const double* __restrict__ x, double* __restrict__ y,
+                                                   const double* __restrict__ yup, double* partial, double* out,
+                                                   const double* prev, unsigned* ticket, const MinresState* st) {
+  if (st && st->done) return;
+  const Cell1 q = owned_cell1(L);
+  double acc = 0.0;
+  if (q.ok) {
+    q_face_dir<HY, 0, DOT>(L, q, x, y, yup, acc);
+    if constexpr (HY) q_face_dir<HY, 1, DOT>(L, q, x, y, yup, acc);
+    q_face_dir<HY, 2, DOT>(L, q, x, y, yup, acc);
+  }
+  if (DOT) {
+    __shared__ double sm[BLK / 32];
+    __shared__ int is_last;
+    const double s = block_tree_256(acc, sm);
+    if (threadIdx.x == 0) {
+      partial[blockIdx.x] = s;
+      __threadfence();
+      is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double a = 0.0;
+      for (unsigned j = threadIdx.x; j < gridDim.x; j += BLK) a += __ldcg(partial + j);
+      __syncthreads();
+      const double tot = block_tree_256(a, sm);
+      if (threadIdx.x == 0) {
+        *out = *prev + tot;
+        *ticket = 0u;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6 (os = 1): one explicit stage of the DG-Q1 saturation equation, fused:
+//   rate = M_phi^-1 (Kt f(S) + b),   Kt = Convection(v,1)^T - DGTrace(v,1,1/2)   (see the file header)
+//   RATE ? Sout = rate : Sout = Sin + dt rate,  Fout = f(Sout)            [REF src/saturation_solver.cpp:74-92]
+// One thread per owned cell.  Volume term with the 2-point Gauss rule collocated at the DG nodes (exact for this
+// integrand; MFEM's rule has more points, same value); face terms with the DG trace integrator's own rule
+// because (v.n)+- is only piecewise polynomial; upwinding per face point with a = un/2, b = |un|/2 like
+// DGTraceIntegrator [MFEM-recall].  M_phi and the Gauss-node Lagrange basis are diagonal.
+// F = f(S) (or S in single-phase mode) travels with S, ghost planes included.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double sat_source_at(const SatParam& sp, double px, double py, double pz) {
+  // SaturationSourceCoefficient::eval2D/eval3D [REF src/param.hpp:382-406]; internal coordinates (2-D: y -> z)
+  if (sp.well_2d) return (fabs(px - sp.inj_c0) <= sp.inj_r && fabs(pz - sp.inj_c1) <= sp.inj_r) ? sp.src : 0.;
+  return (fabs(px - sp.inj_c0) <= sp.inj_r && fabs(pz - sp.inj_c2) <= sp.inj_r && py >= sp.inj_c1 &&
+          py <= sp.inj_c1 + sp.inj_h) ? sp.src : 0.;
+}
+
+template <bool HY, int D>
+__device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const QTab& tb, const double* __restrict__ x,
+                                          const double* __restrict__ Fin, const double (&g)[QD<HY>::NSL],
+                                          double (&r)[QD<HY>::NSL]) {
+  using R = QDir<HY, D>;
+  using Q = QD<HY>;
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F), NT = NOE * NOF;
+  constexpr int NFE = (R::E == 1 && !HY) ? 1 : Q::NF, NFF = (R::F == 1 && !HY) ? 1 : Q::NF;
+  double ulo[NT], uhi[NT], go0[NT], go1[NT], gn_lo[NT], gn_hi[NT];
+  int mlo[NT], ps = 1, cd = 0, nd = 1, cs = 1;
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      const int t = te + NOE * tf;
+      const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
+      ps = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));
+      cd = l.cd; nd = l.nd; cs = l.cstride;
+      mlo[t] = lp;
+      const double u0 = x[l.base], u1 = x[l.base + l.sd], u2 = x[l.base + 2 * l.sd];
+      ulo[t] = u0; uhi[t] = u2;
+      const double g0 = g[lp], g1 = g[lp + ps];
+      // volume term: sum over the two DG nodes of the line of  w g vhat dpsi_i/dxi_d
+      const double vh0 = tb.LC[0][0] * u0 + tb.LC[0][1] * u1 + tb.LC[0][2] * u2;
+      const double vh1 = tb.LC[1][0] * u0 + tb.LC[1][1] * u1 + tb.LC[1][2] * u2;
+      const double vol = tb.wv * (g0 * vh0 + g1 * vh1);
+      r[lp] += tb.dl[0] * vol;
+      r[lp + ps] += tb.dl[1] * vol;
+      // traces of g on the two faces: own side, and the neighbour's side
+      go0[t] = tb.E0[0] * g0 + tb.E0[1] * g1;
+      go1[t] = tb.E1[0] * g0 + tb.E1[1] * g1;
+      const long nl = (long)(q.c - (l.cd > 0 ? l.cstride : 0)) * Q::NSL + lp;
+      const long nh = (long)(q.c + (l.cd + 1 < l.nd ? l.cstride : 0)) * Q::NSL + lp;
+      gn_lo[t] = tb.E1[0] * Fin[nl] + tb.E1[1] * Fin[nl + ps];   // lower cell, its xi_d = 1 face
+      gn_hi[t] = tb.E0[0] * Fin[nh] + tb.E0[1] * Fin[nh + ps];   // upper cell, its xi_d = 0 face
+    }
+  (void)cs;
+  double cl[NT], ch[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) { cl[t] = 0.0; ch[t] = 0.0; }
+  for (int qf = 0; qf < NFF; ++qf)
+    for (int qe = 0; qe < NFE; ++qe) {
+      double oo[NT];
+      double unl = 0.0, unh = 0.0, g1l = 0.0, g2l = 0.0, g1h = 0.0, g2h = 0.0;
+#pragma unroll
+      for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+        for (int te = 0; te < NOE; ++te) {
+          const int t = te + NOE * tf;
+          const double oe = (NFE == 1) ? 1.0 : tb.OF[qe][te], of = (NFF == 1) ? 1.0 : tb.OF[qf][tf];
+          oo[t] = oe * of;
+          unl += ulo[t] * oo[t]; unh += uhi[t] * oo[t];
+          g1l += gn_lo[t] * oo[t]; g2l += go0[t] * oo[t];   // lower face: element 1 = lower cell, element 2 = this cell
+          g1h += go1[t] * oo[t]; g2h += gn_hi[t] * oo[t];   // upper face: element 1 = this cell
+        }
+      const double w = ((NFE == 1) ? 1.0 : tb.fw[qe]) * ((NFF == 1) ? 1.0 : tb.fw[qf]);
+      {
+        const double a = 0.5 * unl, b = 0.5 * fabs(unl);
+        const double fl = (w * (a + b)) * g1l - (w * (b - a)) * g2l;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) cl[t] += fl * oo[t];
+      }
+      {
+        const double a = 0.5 * unh, b = 0.5 * fabs(unh);
+        const double fh = (w * (a + b)) * g1h - (w * (b - a)) * g2h;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) ch[t] += fh * oo[t];
+      }
+    }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    if (cd > 0) {  // rows of element 2 of the lower face: + flux * psi_i(xi_d = 0)
+      r[mlo[t]] += tb.E0[0] * cl[t];
+      r[mlo[t] + ps] += tb.E0[1] * cl[t];
+    }
+    if (cd + 1 < nd) {  // rows of element 1 of the upper face: - flux * psi_i(xi_d = 1)
+      r[mlo[t]] -= tb.E1[0] * ch[t];
+      r[mlo[t] + ps] -= tb.E1[1] * ch[t];
+    }
+  }
+}
+
+template <bool HY, bool RATE>
+__global__ void __launch_bounds__(BLK) k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x,
+                                               const double* __restrict__ phi, const double* __restrict__ Sin,
+                                               const double* __restrict__ Fin, double* __restrict__ Sout,
+                                               double* __restrict__ Fout) {
+  using Q = QD<HY>;
+  const Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  double g[Q::NSL], r[Q::NSL];
+  const long sb = (long)q.c * Q::NSL;
+#pragma unroll
+  for (int m = 0; m < Q::NSL; ++m) { g[m] = Fin[sb + m]; r[m] = 0.0; }
+  q_sat_dir<HY, 0>(L, q, tb, x, Fin, g, r);
+  if constexpr (HY) q_sat_dir<HY, 1>(L, q, tb, x, Fin, g, r);
+  q_sat_dir<HY, 2>(L, q, tb, x, Fin, g, r);
+  const double wm = sp.vol * tb.wv;
+  const double mphi = phi[q.c] * wm;
+#pragma unroll
+  for (int m = 0; m < Q::NSL; ++m) {
+    const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
+    const double px = (q.i + tb.sn[m0]) * sp.hx, py = (q.j + tb.sn[m1]) * sp.hy, pz = (q.k + tb.sn[m2]) * sp.hz;
+    const double z = r[m] + sat_source_at(sp, px, py, pz) * wm;
+    double yv = z / mphi;
+    double so;
+    if (RATE) so = yv;
+    else {
+      yv *= sp.dt;
+      so = Sin[sb + m] + yv;
+    }
+    Sout[sb + m] = so;
+    if (!RATE) Fout[sb + m] = sp.two_phase ? frac_flow_of(ph, so) : so;
+  }
+}
+
+// f(S) over a flat dof range (ghost planes included)
+__global__ void __launch_bounds__(BLK) k_frac_flat(long n, Phys ph, int two_phase, const double* __restrict__ S,
+                                                   double* __restrict__ F) {
+  for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
+    const double s = S[i];
+    F[i] = two_phase ? frac_flow_of(ph, s) : s;
+  }
+}
+// guards over a flat owned dof range
+__global__ void __launch_bounds__(BLK) k_guards_flat(long n, const double* __restrict__ S, unsigned long long* n_bad,
+                                                     unsigned long long* max_bits) {
+  for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
+    const double s = S[i];
+    if (!isfinite(s)) { atomicAdd(n_bad, 1ull); continue; }
+    unsigned long long b = (unsigned long long)__double_as_longlong(s);
+    b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    atomicMax(max_bits, b);
+  }
+}
+
+}  // namespace impes

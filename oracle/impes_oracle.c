@@ -981,7 +981,167 @@ static void frac_flow(const orc *o, const double *S, double *fs, long n) {
  *   (Kt g)_i = - sum_F [ (v.n)+ g_1 + (v.n)- g_2 ] (w_i1 - w_i2),   n from element 1 to element 2,
  * with  int_F v.n = the RT0 dof of F (RT_k: sum over the face's open-node dofs with Gauss weights).
  * b_i = (R, w_i) [REF :41-44]; M_phi = (phi w, s) [REF :28-31]. */
+/* Reference-element RT_kv velocity component d at xi (all dofs +d oriented; contravariant Piola factors cancel
+ * against the geometry in both the volume and the face terms, see assemble_saturation_q1) */
+static double vhat(const orc *o, const double *u, const int *cc, int d, const double *xi) {
+  const int kv = o->kv, dim = o->dim;
+  int cnt[3];
+  for (int e = 0; e < 3; ++e) cnt[e] = e >= dim ? 1 : (e == d ? kv + 2 : kv + 1);
+  double v = 0.0;
+  for (int a2 = 0; a2 < cnt[2]; ++a2)
+    for (int a1 = 0; a1 < cnt[1]; ++a1)
+      for (int a0 = 0; a0 < cnt[0]; ++a0) {
+        const int aa[3] = {a0, a1, a2};
+        int gi[3];
+        double bs = 1.0;
+        for (int e = 0; e < 3; ++e) {
+          gi[e] = e < dim ? cc[e] * (kv + 1) + aa[e] : 0;
+          if (e < dim) bs *= (e == d) ? lag(o->cnode, kv + 2, aa[e], xi[e]) : lag(o->onode, kv + 1, aa[e], xi[e]);
+        }
+        v += u[vidx(o, d, gi[0], gi[1], gi[2])] * bs;
+      }
+  return v;
+}
+
+/* DG_1 (Q1 at the Gauss nodes) saturation operator, assembled by quadrature like MFEM's integrators:
+ *   Kt = -(Convection(v,-1) + Transpose(DGTrace(v,1,1/2)))^T = Convection(v,1)^T - DGTrace(v,1,1/2)
+ * [REF src/saturation_solver.cpp:32-35,53-55] ([MFEM-recall]):
+ *   Convection(Q,a)_ij = a int phi_i (Q . grad phi_j): adj(J) Q = the reference-element velocity, so the element
+ *     matrix is mesh independent; rule order = OrderGrad + Order + el.order = dim + 2 ks - 1;
+ *   DGTrace(u,1,1/2): a = un/2, b = |un|/2 with un = u . (area-scaled normal from element 1 to 2) = the
+ *     reference normal component, u evaluated from element 1; blocks  (1,1) += w(a+b) s1 s1, (2,1) -= w(a+b) s2 s1,
+ *     (2,2) += w(b-a) s2 s2, (1,2) -= w(b-a) s1 s2;  rule order = OrderW + 2 ks = dim - 1 + 2 ks.
+ * b = (R, w) with DomainLFIntegrator's rule of order 2 ks; M_phi = (phi w, s) is diagonal in this basis (A.6). */
+static int assemble_saturation_q1(orc *o, const double *u, csr *Kt, double *b, double *Mphi) {
+  const int dim = o->dim, ks = o->ks, n1 = ks + 1, nsl = o->nsl;
+  qrule qv, qf, qb;
+  gauss01((dim + 2 * ks - 1) / 2 + 1, &qv);
+  gauss01((dim - 1 + 2 * ks) / 2 + 1, &qf);
+  gauss01(ks + 1, &qb);
+  qrule one = {1, {0.5}, {1.0}};
+  const long cap = o->ncell * (long)nsl * nsl * (1 + 4 * dim);
+  long *ri = (long *)malloc(sizeof(long) * cap);
+  int *ci = (int *)malloc(sizeof(int) * cap);
+  double *vv = (double *)malloc(sizeof(double) * cap);
+  if (!ri || !ci || !vv) return -1;
+  long nnz = 0;
+  double sh[8], dsh[8][3], el[8][8];
+  /* volume term: Kt_ij += sum_q w_q psi_j(q) (vhat(q) . grad psi_i(q)) */
+  const qrule *QV[3] = {&qv, &qv, dim == 3 ? &qv : &one};
+  for (int cz = 0; cz < o->n[2]; ++cz)
+    for (int cy = 0; cy < o->n[1]; ++cy)
+      for (int cx = 0; cx < o->n[0]; ++cx) {
+        const int cc[3] = {cx, cy, cz};
+        const long cell = cx + (long)o->n[0] * (cy + (long)o->n[1] * cz);
+        memset(el, 0, sizeof el);
+        for (int q2 = 0; q2 < QV[2]->nq; ++q2)
+          for (int q1 = 0; q1 < QV[1]->nq; ++q1)
+            for (int q0 = 0; q0 < QV[0]->nq; ++q0) {
+              const double xi[3] = {QV[0]->x[q0], QV[1]->x[q1], QV[2]->x[q2]};
+              const double w = QV[0]->w[q0] * QV[1]->w[q1] * QV[2]->w[q2];
+              double vh[3] = {0, 0, 0};
+              for (int d = 0; d < dim; ++d) vh[d] = vhat(o, u, cc, d, xi);
+              for (int m = 0; m < nsl; ++m) {
+                const int mm[3] = {m % n1, (m / n1) % n1, m / (n1 * n1)};
+                sh[m] = 1.0;
+                for (int e = 0; e < dim; ++e) sh[m] *= lag(o->snode, n1, mm[e], xi[e]);
+                for (int d = 0; d < dim; ++d) {
+                  double g = 1.0;
+                  for (int e = 0; e < dim; ++e) g *= (e == d) ? dlag(o->snode, n1, mm[e], xi[e]) : lag(o->snode, n1, mm[e], xi[e]);
+                  dsh[m][d] = g;
+                }
+              }
+              for (int i = 0; i < nsl; ++i) {
+                double vg = 0.0;
+                for (int d = 0; d < dim; ++d) vg += vh[d] * dsh[i][d];
+                for (int j = 0; j < nsl; ++j) el[i][j] += w * sh[j] * vg;
+              }
+            }
+        for (int i = 0; i < nsl; ++i)
+          for (int j = 0; j < nsl; ++j) { ri[nnz] = cell * nsl + i; ci[nnz] = (int)(cell * nsl + j); vv[nnz] = el[i][j]; ++nnz; }
+      }
+  /* interior faces: Kt -= DGTrace */
+  const qrule *QF2 = dim == 3 ? &qf : &one;
+  for (int d = 0; d < dim; ++d) {
+    int tr[2], nt = 0;
+    for (int e = 0; e < dim; ++e) if (e != d) tr[nt++] = e;
+    for (int cz = 0; cz < o->n[2]; ++cz)
+      for (int cy = 0; cy < o->n[1]; ++cy)
+        for (int cx = 0; cx < o->n[0]; ++cx) {
+          const int c2c[3] = {cx, cy, cz};
+          if (c2c[d] == 0) continue; /* boundary faces omitted [REF :36-39] */
+          int c1c[3] = {cx, cy, cz};
+          c1c[d] -= 1;
+          const long cell2 = cx + (long)o->n[0] * (cy + (long)o->n[1] * cz);
+          const long stride = d == 0 ? 1 : (d == 1 ? o->n[0] : (long)o->n[0] * o->n[1]);
+          const long cell1 = cell2 - stride;
+          double e11[8][8], e12[8][8], e21[8][8], e22[8][8];
+          memset(e11, 0, sizeof e11); memset(e12, 0, sizeof e12); memset(e21, 0, sizeof e21); memset(e22, 0, sizeof e22);
+          for (int qb2 = 0; qb2 < QF2->nq; ++qb2)
+            for (int qa = 0; qa < qf.nq; ++qa) {
+              double xi1[3] = {0, 0, 0}, xi2[3] = {0, 0, 0};
+              xi1[d] = 1.0; xi2[d] = 0.0;
+              xi1[tr[0]] = xi2[tr[0]] = qf.x[qa];
+              double w = qf.w[qa];
+              if (nt == 2) { xi1[tr[1]] = xi2[tr[1]] = QF2->x[qb2]; w *= QF2->w[qb2]; }
+              const double un = vhat(o, u, c1c, d, xi1); /* velocity from element 1, reference normal component */
+              const double a = 0.5 * un, bb = 0.5 * fabs(un);
+              double s1[8], s2[8];
+              for (int m = 0; m < nsl; ++m) {
+                const int mm[3] = {m % n1, (m / n1) % n1, m / (n1 * n1)};
+                s1[m] = s2[m] = 1.0;
+                for (int e = 0; e < dim; ++e) { s1[m] *= lag(o->snode, n1, mm[e], xi1[e]); s2[m] *= lag(o->snode, n1, mm[e], xi2[e]); }
+              }
+              const double wp = w * (a + bb), wm = w * (bb - a);
+              for (int i = 0; i < nsl; ++i)
+                for (int j = 0; j < nsl; ++j) {
+                  if (wp != 0.0) { e11[i][j] += wp * s1[i] * s1[j]; e21[i][j] -= wp * s2[i] * s1[j]; }
+                  if (wm != 0.0) { e22[i][j] += wm * s2[i] * s2[j]; e12[i][j] -= wm * s1[i] * s2[j]; }
+                }
+            }
+          for (int i = 0; i < nsl; ++i)
+            for (int j = 0; j < nsl; ++j) {
+              ri[nnz] = cell1 * nsl + i; ci[nnz] = (int)(cell1 * nsl + j); vv[nnz] = -e11[i][j]; ++nnz;
+              ri[nnz] = cell1 * nsl + i; ci[nnz] = (int)(cell2 * nsl + j); vv[nnz] = -e12[i][j]; ++nnz;
+              ri[nnz] = cell2 * nsl + i; ci[nnz] = (int)(cell1 * nsl + j); vv[nnz] = -e21[i][j]; ++nnz;
+              ri[nnz] = cell2 * nsl + i; ci[nnz] = (int)(cell2 * nsl + j); vv[nnz] = -e22[i][j]; ++nnz;
+            }
+        }
+  }
+  if (coo_to_csr(o->ns, o->ns, nnz, ri, ci, vv, Kt)) return -1;
+  free(ri); free(ci); free(vv);
+  /* b and the (diagonal) mass matrix */
+  const qrule *QB[3] = {&qb, &qb, dim == 3 ? &qb : &one};
+  for (int cz = 0; cz < o->n[2]; ++cz)
+    for (int cy = 0; cy < o->n[1]; ++cy)
+      for (int cx = 0; cx < o->n[0]; ++cx) {
+        const int cc[3] = {cx, cy, cz};
+        const long cell = cx + (long)o->n[0] * (cy + (long)o->n[1] * cz);
+        for (int m = 0; m < nsl; ++m) {
+          const int mm[3] = {m % n1, (m / n1) % n1, m / (n1 * n1)};
+          double sb = 0.0, sm = 0.0;
+          for (int q2 = 0; q2 < QB[2]->nq; ++q2)
+            for (int q1 = 0; q1 < QB[1]->nq; ++q1)
+              for (int q0 = 0; q0 < QB[0]->nq; ++q0) {
+                const int qq[3] = {q0, q1, q2};
+                double w = o->vol, psi = 1.0, p[3] = {0, 0, 0};
+                for (int e = 0; e < dim; ++e) {
+                  w *= QB[e]->w[qq[e]];
+                  psi *= lag(o->snode, n1, mm[e], QB[e]->x[qq[e]]);
+                  p[e] = (cc[e] + QB[e]->x[qq[e]]) * o->h[e];
+                }
+                sb += w * sat_R(&o->d, p) * psi;
+                sm += w * o->phi[cell] * psi * psi; /* exact: the basis is orthogonal under the (ks+1)-point Gauss rule */
+              }
+          b[cell * nsl + m] = sb;
+          Mphi[cell * nsl + m] = sm;
+        }
+      }
+  return 0;
+}
+
 static int assemble_saturation(orc *o, const double *u, csr *Kt, double *b, double *Mphi) {
+  if (o->ks == 1) return assemble_saturation_q1(o, u, Kt, b, Mphi);
   if (o->ks != 0) { snprintf(o->err, sizeof o->err, "oracle: order_s=%d saturation not restated yet", o->ks); return -1; }
   const int dim = o->dim, kv = o->kv;
   long nf = 0;

@@ -1,0 +1,133 @@
+"""GPU parity tests for `-ov 1 -op 1 -os 1` (RT1 / L2-Q1 / DG-Q1: the spaces of BASELINE config C5) through the C ABI
+against the CPU oracle.
+
+With S in DG-Q1 the mobility varies inside a cell: the GPU applies the dense RT1 element blocks matrix-free in
+sum-factorised form (csrc/rt1q.cuh) while the oracle assembles them entry by entry with MFEM's quadrature rules, so
+the two agree to round-off, not bit for bit.  Tolerances (fp64, written here on purpose):
+  operator applications (K1, preconditioner, one saturation stage)   <= 1e-12 relative L2;
+  MINRES solves: iteration counts within +-2, solution within the Krylov drift bound 1e-6
+  (tests/test_oracle_invariants.py::test_krylov_drift: round-off level perturbations move a rtol=1e-6 solve by
+  1e-8..1e-7, which is why the bit-exact paths exist for -os 0).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    dict(dim=2, nx=9, ny=7),
+    dict(dim=2, nx=24, ny=20),
+    dict(dim=3, nx=6, ny=5, nz=4),
+    dict(dim=3, nx=3, ny=40, nz=5),
+    dict(dim=2, nx=1, ny=4),
+]
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+def make(pkg, orc, cfg, K="lognormal", **kw):
+    from incompressible_flow_b200 import workloads
+    d, Kx, Ky, Kz, phi = workloads.build(K=K, sigma=1.0, order=1, order_s=1, **cfg, **kw)
+    rng = np.random.default_rng(7)
+    n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
+    phi = rng.uniform(0.1, 0.4, n)
+    o = orc.Oracle(d, Kx, Ky, Kz, phi)
+    s = pkg.Solver(d, Kx, Ky, Kz, phi)
+    return d, o, s, n
+
+
+@pytest.mark.parametrize("cfg", CASES)
+def test_q1_dims(pkg, orc, native_lib, cfg):
+    d, o, s, n = make(pkg, orc, cfg)
+    assert (s.nv, s.np_, s.ns) == (o.nv, o.np_, o.ns) and s.ns == n * 2 ** d.dim
+    o.set_arith(1)
+    assert np.array_equal(s.rhs(), o.rhs())
+    s.close()
+
+
+@pytest.mark.parametrize("cfg", CASES)
+@pytest.mark.parametrize("two_phase", [True, False])
+def test_q1_darcy_apply_and_prec(pkg, orc, native_lib, cfg, two_phase):
+    d, o, s, n = make(pkg, orc, cfg, two_phase=two_phase)
+    rng = np.random.default_rng(3)
+    S = rng.uniform(0.05, 0.95, o.ns)          # rough inside the cells on purpose: exercises the quadrature
+    x = rng.standard_normal(o.nv + o.np_)
+    s.update_coefficients(S)
+    yg = s.darcy_apply(x)
+    zg = s.prec_apply(x)
+    for arith in (0, 1):
+        o.set_arith(arith)
+        o.update_coefficients(S)
+        assert rel(yg, o.darcy_apply(x)) < 1e-12
+        assert rel(zg, o.prec_apply(x)) < 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("cfg", CASES[:4])
+@pytest.mark.parametrize("mg", [False, True])
+def test_q1_pressure_solve(pkg, orc, native_lib, cfg, mg):
+    from incompressible_flow_b200 import abi
+    d, o, s, n = make(pkg, orc, cfg, schur_prec=abi.SCHUR_MG if mg else abi.SCHUR_SGS_LEX)
+    S = np.random.default_rng(5).uniform(0.0, 0.9, o.ns)
+    o.set_arith(1)
+    xo, sto, rco = o.pressure_solve(S)
+    xg, stg = s.pressure_solve(S)
+    assert stg.converged == 1 and sto.converged == 1
+    assert abs(stg.iterations - sto.iterations) <= 2
+    assert rel(xg[:o.nv], xo[:o.nv]) < 1e-6
+    s.close()
+
+
+@pytest.mark.parametrize("cfg", CASES[:4])
+@pytest.mark.parametrize("two_phase", [True, False])
+def test_q1_saturation_substeps(pkg, orc, native_lib, cfg, two_phase):
+    """DG-Q1 upwind stages: volume term + face integrals with per-point upwinding, velocity frozen."""
+    d, o, s, n = make(pkg, orc, cfg, two_phase=two_phase)
+    o.set_arith(1)
+    rng = np.random.default_rng(11)
+    S0 = rng.uniform(0.0, 0.6, o.ns)
+    xo, _, _ = o.pressure_solve(S0)
+    So, nso = o.saturation_advance(xo[:o.nv], S0, 0.4, 0.05)
+    Sg, nsg = s.saturation_advance(xo[:o.nv], S0, 1, 0.4, 0.05)
+    assert nso == nsg == 8
+    assert rel(Sg, So) < 1e-12
+    bad, mx = s.guards()
+    assert bad == 0 and abs(mx - So.max()) <= 1e-12 * abs(So.max())
+    s.close()
+
+
+@pytest.mark.parametrize("ode", [2, 3, 4])
+def test_q1_rk_stages(pkg, orc, native_lib, ode):
+    """MPI-path time integrators on the DG-Q1 operator [REF src/par_saturation_solver.cpp:113-124]."""
+    from incompressible_flow_b200 import abi
+    d, o, s, n = make(pkg, orc, dict(dim=2, nx=12, ny=10), substep_rule=abi.SUBSTEPS_PARALLEL, ode_solver_type=ode)
+    o.set_arith(1)
+    S0 = np.random.default_rng(2).uniform(0.0, 0.6, o.ns)
+    xo, _, _ = o.pressure_solve(S0)
+    So, nso = o.saturation_advance(xo[:o.nv], S0, 0.5, 0.1)
+    Sg, nsg = s.saturation_advance(xo[:o.nv], S0, 1, 0.5, 0.1)
+    assert nso == nsg == 5
+    assert rel(Sg, So) < 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("cfg", [CASES[1], CASES[2]])
+def test_q1_impes_loop(pkg, orc, native_lib, cfg):
+    """2 IMPES steps with resident state: iteration counts within +-2, fields within the drift bound."""
+    from incompressible_flow_b200 import abi
+    d, o, s, n = make(pkg, orc, cfg)
+    o.set_arith(1)
+    So = np.zeros(o.ns)
+    s.set_field(abi.FIELD_SATURATION, So)
+    for step in range(2):
+        xo, sto, _ = o.pressure_solve(So)
+        So, _ = o.saturation_advance(xo[:o.nv], So, 1.0, 0.1)
+        _, stg = s.pressure_solve(None, want_x=False)
+        s.saturation_advance(None, None, step + 1, 1.0, 0.1)
+        assert abs(stg.iterations - sto.iterations) <= 2
+    assert rel(s.get_field(abi.FIELD_SATURATION), So) < 1e-6
+    assert rel(s.get_field(abi.FIELD_VELOCITY), xo[:o.nv]) < 1e-6
+    s.close()
