@@ -32,11 +32,13 @@ def slab_range_mg(n_layers, rank, world):
     return ulo * unit, min(uhi * unit, n_layers)
 
 
-def owned_ranges(dim, nx, ny, nz, rank, world, order=0, slab=None):
+def owned_ranges(dim, nx, ny, nz, rank, world, order=0, slab=None, order_s=0):
     """Index ranges this rank owns in the native host layout (include/impes_b200.h):
     -> (ranges in a Darcy vector [V | P], ranges in a cell / saturation vector).
     order = 0: RT0/P0; order = 1: RT1/L2-Q1 (node grids of 2n+1 closed / 2n open nodes, 2^dim L2 dofs per cell).
-    slab: explicit (lo, hi) cell-layer range (impes_get_dims slab_lo/slab_hi) overriding the balanced rule."""
+    slab: explicit (lo, hi) cell-layer range (impes_get_dims slab_lo/slab_hi) overriding the balanced rule.
+    order_s = 1: DG-Q1 saturation, 2^dim dofs per cell (cell-major)."""
+    nsl = 2 ** dim if order_s == 1 else 1
     if order == 1:
         if dim == 2:
             n_layers, px, py, pz, npl = ny, 2 * nx + 1, 0, 2 * nx, 4
@@ -53,7 +55,7 @@ def owned_ranges(dim, nx, ny, nz, rank, world, order=0, slab=None):
             darcy.append((nvx + py * 2 * lo, nvx + py * 2 * hi))
         darcy.append((nvx + nvy + pz * 2 * lo, nvx + nvy + pz * (2 * hi + top)))
         darcy.append((nv + plane * npl * lo, nv + plane * npl * hi))
-        return darcy, [(plane * lo, plane * hi)]
+        return darcy, [(plane * nsl * lo, plane * nsl * hi)]
     if dim == 2:
         n_layers, plane, px, py = ny, nx, nx + 1, 0
         nvx, nvy = (nx + 1) * ny, 0

@@ -53,7 +53,7 @@ def test_driver_run_matches_oracle(pkg, orc, host_bins, tmp_path, dim, order):
     """A whole run of the run_serial-compatible driver (K from a float32 file, 3 global steps) reproduces the
     oracle's loop: same MINRES iteration counts in the log, saturation dumps equal to float32 precision."""
     from incompressible_flow_b200 import workloads
-    nx, ny, nz = (20, 16, 1) if dim == 2 else (9, 8, 6)
+    nx, ny, nz = (20, 16, 1) if dim == 2 else (9, 8, 9)   # hx == hz: the well box r = h covers exactly one cell column
     n = nx * ny * nz
     K32 = np.exp(np.random.default_rng(3).standard_normal(n)).astype(np.float32)
     kfile = tmp_path / "K.bin"
