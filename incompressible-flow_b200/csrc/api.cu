@@ -773,7 +773,9 @@ int minres_pair(impes_ctx* h) {
 }
 
 int build_minres_graph(impes_ctx* h) {
-  if (h->minres_exec || !h->use_graph || h->L.nranks > 1 || h->profiling) return 0;
+  // multi-GPU: NCCL send/recv/all-reduce are capturable; opt-in (IMPES_GRAPH_MULTI=1) until it has seen more testing
+  static const bool graph_multi = getenv("IMPES_GRAPH_MULTI") && atoi(getenv("IMPES_GRAPH_MULTI")) != 0;
+  if (h->minres_exec || !h->use_graph || (h->L.nranks > 1 && !graph_multi) || h->profiling) return 0;
   const int pairs = 8;
   cudaGraph_t g = nullptr;
   const long long l0 = h->launches;
@@ -1156,6 +1158,8 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   if (d.world_size > L.NZ) { h->err = "more ranks than cell planes"; return IMPES_ERR_BAD_ARG; }
   L.rank = d.rank;
   L.nranks = d.world_size;
+  L.fdx = make_fastdiv((unsigned)L.NX);
+  L.fdy = make_fastdiv((unsigned)L.NY);
   int mg_m = 0;  // multigrid mode on several GPUs: slabs are cut in units of 2^mg_m planes
   if (d.schur_prec == IMPES_SCHUR_MG && L.nranks > 1) {
     while (mg_m < 6 && (L.NZ >> (mg_m + 1)) >= L.nranks) ++mg_m;
@@ -1198,6 +1202,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   h->vec_offp = L.off_p;
   if (h->ord == 1) {  // dvec1 layout (rt1.cuh)
     Lay1& Q = h->L1;
+    Q.fdx = L.fdx; Q.fdy = L.fdy;
     Q.NX = L.NX; Q.NY = L.NY; Q.NZ = L.NZ; Q.has_y = L.has_y; Q.oy = L.has_y ? 2 : 1; Q.npl = 4 * Q.oy;
     Q.zlo = L.zlo; Q.zhi = L.zhi; Q.nzl = L.nzl; Q.rank = L.rank; Q.nranks = L.nranks;
     Q.plane = L.plane; Q.ncl = L.ncl; Q.nblk = L.nblk;

@@ -80,6 +80,10 @@ __device__ __forceinline__ double div_exact(double n, double D, double rD) {
   return __fma_rn(r, rD, q);
 }
 
+// n / D through the correctly rounded reciprocal intrinsic + the two remainder corrections above: the same bits
+// as IEEE `/` (finite, non-denormal operands) in roughly half the instructions of the division subroutine.
+__device__ __forceinline__ double div_rcp(double n, double D) { return div_exact(n, D, __drcp_rn(D)); }
+
 // ---------------------------------------------------------------------------------------
 // physics: Param::Krw / Param::Kro  [REF src/param.cpp:195-215]  (no clamping).
 // Divisions by the run-time constants (1 - Sor - Swc), mu_w, mu_o go through div_exact with host-computed
@@ -131,9 +135,9 @@ __device__ __forceinline__ CellIdx owned_cell(const Lay& L) {
   const unsigned t = blockIdx.x * (unsigned)BLK + threadIdx.x;  // owned cells per rank < 2^32 (checked at create)
   c.ok = t < (unsigned)L.ncl;
   const unsigned tt = c.ok ? t : 0u;
-  const unsigned r = tt / (unsigned)L.NX;
+  const unsigned r = fastdiv(tt, L.fdx);
   c.i = (int)(tt - r * (unsigned)L.NX);
-  c.kl = (int)(r / (unsigned)L.NY);
+  c.kl = (int)fastdiv(r, L.fdy);
   c.j = (int)(r - (unsigned)c.kl * (unsigned)L.NY);
   c.k = c.kl + L.zlo;
   return c;
@@ -1253,44 +1257,61 @@ __global__ void __launch_bounds__(BLK) k_sat_stream(Lay L, Phys ph, SatParam sp,
   const int c = ix_c(L, i, j, kk);
   const bool xl = i > 0, xh = i + 1 < L.NX, yl = L.has_y && j > 0, yh = L.has_y && j + 1 < L.NY, zl = k > 0,
              zh = k + 1 < L.NZ;
+  // Branch-free: every load is unconditional (a missing neighbour is clamped to the cell itself and its flux is
+  // replaced by +0), so all 15 loads are issued before any arithmetic; a skipped term becomes `+ 0 * f`, which
+  // leaves the partial sums bit-identical (f finite; zeros only enter sums that start from +0).
   const int fx = ix_ux(L, i, j, kl), fz = ix_uz(L, i, j, kk);
-  const double Fxl = xl ? u[fx] : 0.0, Fxh = xh ? u[fx + 1] : 0.0;
-  double Fyl = 0.0, Fyh = 0.0;
-  if (L.has_y) {
-    const int fy = ix_uy(L, i, j, kl);
-    Fyl = yl ? u[fy] : 0.0;
-    Fyh = yh ? u[fy + L.NX] : 0.0;
-  }
-  const double Fzl = zl ? u[fz] : 0.0, Fzh = zh ? u[fz + L.plane] : 0.0;
+  const int fy = L.has_y ? ix_uy(L, i, j, kl) : fx;
+  const double uxl = u[fx], uxh = u[fx + 1], uyl = u[fy], uyh = u[L.has_y ? fy + L.NX : fx], uzl = u[fz],
+               uzh = u[fz + L.plane];
   const double f_c = Fin[c];
-  // (F)+ = max(F,0), (F)- = min(F,0); identical to the compare/select form up to the sign of a zero, which
-  // cannot reach the result (zeros only enter sums that start from +0)
+  const double f_zl = Fin[zl ? c - L.plane : c], f_yl = Fin[yl ? c - L.NX : c], f_xl = Fin[xl ? c - 1 : c];
+  const double f_xh = Fin[xh ? c + 1 : c], f_yh = Fin[yh ? c + L.NX : c], f_zh = Fin[zh ? c + L.plane : c];
+  const double ph_c = phi[c];
+  const double s_c = RATE ? 0.0 : Sin[c];
+  // (F)+ = F > 0 ? F : 0 and (F)- = F < 0 ? F : 0 exactly as the oracle writes them, with the "neighbour exists"
+  // predicate folded into the comparison: one DSETP + two FSEL each (fp64 fmax/fmin cost ~8 instructions apiece
+  // because of their NaN handling -- ncu: they were a third of this kernel's instructions)
+  const double pxl = (xl && uxl > 0.0) ? uxl : 0.0, nxl = (xl && uxl < 0.0) ? uxl : 0.0;
+  const double pxh = (xh && uxh > 0.0) ? uxh : 0.0, nxh = (xh && uxh < 0.0) ? uxh : 0.0;
+  const double pyl = (yl && uyl > 0.0) ? uyl : 0.0, nyl = (yl && uyl < 0.0) ? uyl : 0.0;
+  const double pyh = (yh && uyh > 0.0) ? uyh : 0.0, nyh = (yh && uyh < 0.0) ? uyh : 0.0;
+  const double pzl = (zl && uzl > 0.0) ? uzl : 0.0, nzl = (zl && uzl < 0.0) ? uzl : 0.0;
+  const double pzh = (zh && uzh > 0.0) ? uzh : 0.0, nzh = (zh && uzh < 0.0) ? uzh : 0.0;
   double z = 0.0;
-  if (zl) z += fmax(Fzl, 0.0) * Fin[c - L.plane];
-  if (yl) z += fmax(Fyl, 0.0) * Fin[c - L.NX];
-  if (xl) z += fmax(Fxl, 0.0) * Fin[c - 1];
+  z += pzl * f_zl;
+  if (L.has_y) z += pyl * f_yl;
+  z += pxl * f_xl;
   {
     double dg = 0.0;
-    if (xl) dg += fmin(Fxl, 0.0);
-    if (xh) dg += -fmax(Fxh, 0.0);
-    if (yl) dg += fmin(Fyl, 0.0);
-    if (yh) dg += -fmax(Fyh, 0.0);
-    if (zl) dg += fmin(Fzl, 0.0);
-    if (zh) dg += -fmax(Fzh, 0.0);
+    dg += nxl;
+    dg += -pxh;
+    if (L.has_y) {
+      dg += nyl;
+      dg += -pyh;
+    }
+    dg += nzl;
+    dg += -pzh;
     z += dg * f_c;
   }
-  if (xh) z += (-fmin(Fxh, 0.0)) * Fin[c + 1];
-  if (yh) z += (-fmin(Fyh, 0.0)) * Fin[c + L.NX];
-  if (zh) z += (-fmin(Fzh, 0.0)) * Fin[c + L.plane];
+  z += (-nxh) * f_xh;
+  if (L.has_y) z += (-nyh) * f_yh;
+  z += (-nzh) * f_zh;
   z += sat_source_box(sp, i, j, k) * sp.vol;
-  double yv = z / (phi[c] * sp.vol);
+  double yv = div_rcp(z, ph_c * sp.vol);
   if (RATE) {
     Sout[c] = yv;
   } else {
     yv *= sp.dt;
-    const double sn = Sin[c] + yv;
+    const double sn = s_c + yv;
     Sout[c] = sn;
-    Fout[c] = sp.two_phase ? frac_flow_of(ph, sn) : sn;
+    double fn = sn;
+    if (sp.two_phase) {  // FS [REF src/saturation_solver.cpp:8-17]
+      double mw, mo;
+      mobilities(ph, sn, mw, mo);
+      fn = div_rcp(mw, mw + mo);
+    }
+    Fout[c] = fn;
   }
 }
 

@@ -23,6 +23,7 @@
 namespace impes {
 
 struct Lay1 {
+  FastDiv fdx, fdy;  // division by NX, NY (layout.h)
   int NX, NY, NZ, has_y, oy, npl;
   int zlo, zhi, nzl, rank, nranks;
   int plane, ncl, nblk;
@@ -51,9 +52,9 @@ __device__ __forceinline__ Cell1 owned_cell1(const Lay1& L) {
   const unsigned t = blockIdx.x * (unsigned)BLK + threadIdx.x;
   q.ok = t < (unsigned)L.ncl;
   const unsigned tt = q.ok ? t : 0u;
-  const unsigned r = tt / (unsigned)L.NX;
+  const unsigned r = fastdiv(tt, L.fdx);
   q.i = (int)(tt - r * (unsigned)L.NX);
-  q.kl = (int)(r / (unsigned)L.NY);
+  q.kl = (int)fastdiv(r, L.fdy);
   q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
   q.k = q.kl + L.zlo;
   q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
@@ -183,9 +184,9 @@ __device__ __forceinline__ Dof1 owned_dof1(const Lay1& L) {
   Cell1& q = d.q;
   q.ok = cell < (unsigned)L.ncl;
   const unsigned tt = q.ok ? cell : 0u;
-  const unsigned r = tt / (unsigned)L.NX;
+  const unsigned r = fastdiv(tt, L.fdx);
   q.i = (int)(tt - r * (unsigned)L.NX);
-  q.kl = (int)(r / (unsigned)L.NY);
+  q.kl = (int)fastdiv(r, L.fdy);
   q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
   q.k = q.kl + L.zlo;
   q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
