@@ -440,6 +440,27 @@ def main():
         big1 = dict(big, order=1, order_s=0)
         fast["C5: 256x256x256 RT1/L2-Q1/DG_0 (north_star mesh; the N>1 bench workload), 1 GPU"] = fast_run(big1, 2, 1)
 
+    # ---------------- N > 1: the same workload on ONE GPU (rank 0), the strong-scaling reference point ---------
+    one_gpu = None
+    if rank == 0 and world > 1 and not args.no_fast:
+        od, oKx, oKy, oKz, ophi = workloads.build(**bcfg)
+        od.device = local
+        with pkg.Solver(od, oKx, oKy, oKz, ophi) as osv:
+            osv.set_field(abi.FIELD_SATURATION, np.zeros(osv.ns))
+            oits = []
+            osv.pressure_solve(None, want_x=False)
+            osv.saturation_advance(None, None, 1, DT_GLOBAL, DT_LOCAL)
+            osv.event_record(0)
+            for ti in range(2):
+                _, ost = osv.pressure_solve(None, want_x=False)
+                osv.saturation_advance(None, None, ti + 2, DT_GLOBAL, DT_LOCAL)
+                oits.append(int(ost.iterations))
+            osv.event_record(1)
+            oms = osv.event_elapsed_ms(0, 1) / 2
+        one_gpu = {"ms_per_step": oms, "value": n / (oms * 1e-3), "unit": "cell-steps/s", "minres_iters_per_step": oits,
+                   "steps": 2, "warmup": 1, "note": "same workload, same code path, world_size = 1, measured by rank 0 "
+                   "after the multi-GPU run while the other ranks idle"}
+
     # ---------------- CPU baseline beside it -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -464,11 +485,13 @@ def main():
                                      "sgs_lex (parity mode: exact lexicographic symmetric Gauss-Seidel)",
                        "minres_rtol": d.darcy_rtol, "minres_iters_per_step": its,
                        "partition": f"{world} slab(s) along the slowest axis",
-                       "l2_policy": "step working set < L2 by construction of the BASELINE meshes; every step streams "
-                                    "fresh Krylov vectors; the roofline kernels run on a >=4xL2 mesh with L2 flushed"},
+                       "l2_policy": ("inputs larger than L2: every Krylov vector of this mesh is >> 126 MB per GPU"
+                                     if n * (32 if order else 4) * 8 / world > 4 * 126e6 else
+                                     "step working set < L2 by construction of the BASELINE mesh; every step streams fresh "
+                                     "Krylov vectors") + "; the roofline kernels run on a >=4xL2 mesh with L2 flushed"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_k6": roofline_k6, "roofline_k2": roofline_k2, "roofline_k1_rt1": roofline_rt1,
-            "step_breakdown": breakdown, "fast_mode": fast, "cpu_baseline": cpu,
+            "step_breakdown": breakdown, "fast_mode": fast, "same_workload_1gpu": one_gpu, "cpu_baseline": cpu,
         }
         emit(line)
     if world > 1:

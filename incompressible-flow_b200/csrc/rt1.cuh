@@ -254,8 +254,11 @@ __device__ __forceinline__ void line_rows_dof(const Rt1Const& C, const Line1& l,
 // not exist) and all of a thread's loads are issued before any arithmetic -- one memory round trip instead of
 // one per line / branch region (SASS of the branchy form: 6 dependent LDG groups).  Skipped CSR entries become
 // `+ 0.0`, which leaves every partial sum bit-identical.
+#ifndef IMPES_K1_MINB
+#define IMPES_K1_MINB 4
+#endif
 template <bool HY, bool DOT>
-__global__ void __launch_bounds__(BLK) k1_darcy_apply(Lay1 L, Rt1Const C, const double* __restrict__ mx,
+__global__ void __launch_bounds__(BLK, IMPES_K1_MINB) k1_darcy_apply(Lay1 L, Rt1Const C, const double* __restrict__ mx,
                                                       const double* __restrict__ my, const double* __restrict__ mz,
                                                       const double* __restrict__ x, double* __restrict__ y,
                                                       double* partial, double* out, unsigned* ticket,
