@@ -773,8 +773,9 @@ int minres_pair(impes_ctx* h) {
 }
 
 int build_minres_graph(impes_ctx* h) {
-  // multi-GPU: NCCL send/recv/all-reduce are capturable; opt-in (IMPES_GRAPH_MULTI=1) until it has seen more testing
-  static const bool graph_multi = getenv("IMPES_GRAPH_MULTI") && atoi(getenv("IMPES_GRAPH_MULTI")) != 0;
+  // multi-GPU: NCCL send/recv/all-reduce are capturable (validated on 2 and 8 B200: results unchanged, ~2 % faster);
+  // IMPES_GRAPH_MULTI=0 turns it off.  Every rank replays the same graph: `done` derives from all-reduced scalars.
+  static const bool graph_multi = !(getenv("IMPES_GRAPH_MULTI") && atoi(getenv("IMPES_GRAPH_MULTI")) == 0);
   if (h->minres_exec || !h->use_graph || (h->L.nranks > 1 && !graph_multi) || h->profiling) return 0;
   const int pairs = 8;
   cudaGraph_t g = nullptr;
