@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--roofline-size", default="384x384x384", help="streaming mesh for the K1/K6 roofline (>= 4x L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-serial", action="store_true", help="skip the single-thread CPU sample")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the throughput-mode (multigrid) measurements")
     ap.add_argument("--mode", default="auto", choices=["auto", "fast"],
@@ -471,6 +472,11 @@ def main():
         cpu = {"value": cn / ctimes[0], "unit": "cell-steps/s", "cores": threads, "kind": "port",
                "sample": f"1 full IMPES step (step 1, S=0) of {wname}: {cits[0]} MINRES iterations + 100 sub-steps, "
                          f"{ctimes[0]:.1f} s; CPU restatement of the reference algorithm (MFEM/HYPRE unavailable)"}
+        if not args.no_cpu_serial:
+            # (i) one thread = stand-in for run_serial, (ii) all cores = stand-in for the MPI run
+            _, cits1, ctimes1 = oracle_step(orc, built, 1, 1, 0)
+            cpu["single_thread"] = {"value": cn / ctimes1[0], "unit": "cell-steps/s", "cores": 1,
+                                    "sample": f"the same step on one thread: {cits1[0]} iterations, {ctimes1[0]:.1f} s"}
 
     if rank == 0:
         line = {

@@ -21,6 +21,13 @@
  *
  * Dof numbering: the "native" layout documented in include/impes_b200.h (the math
  * is invariant under MFEM's permutation/sign convention).
+ *
+ * Covered: RT_k / L2_k, k <= 1, with the saturation in DG_0 or DG_1 (Q1 at the Gauss nodes);
+ * DG_1 saturation operator = Convection(v,1)^T - DGTrace(v,1,1/2) with MFEM's rule orders.
+ * arith == 1 ("canonical") pins round-off-level choices so that the GPU path can be compared
+ * bit for bit: closed-form RT0 / RT1 (cell-constant coefficient) element matrices, closed-form
+ * RT1/Q1 divergence matrix and right-hand side, the GPU's dot-product tree.  The DG_1-coefficient
+ * mass matrix stays quadrature-assembled in both modes (the GPU agrees to round-off there).
  */
 #include "../include/impes_b200.h"
 
