@@ -374,7 +374,7 @@ def main():
             a1, m1 = rs.time_kernel(abi.KERNEL_DARCY_APPLY, 20, True)
             a6, m6 = rs.time_kernel(abi.KERNEL_SAT_SUBSTEP, 20, True)
             a2, m2 = rs.time_kernel(abi.KERNEL_MINRES_UPDATE, 10, True)
-            k2_b = 15 * 8 * (rs.nv + rs.np_)
+            k2_b = 13 * 8 * (rs.nv + rs.np_)
         roofline = {"kernel": "k_darcy_apply<DOT> (K1, Krylov matvec + fused <u,Au>)", "bound": "hbm",
                     "achieved": k1_b / (a1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": k1_b / (a1 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
@@ -401,7 +401,7 @@ def main():
             a11, m11 = rs.time_kernel(abi.KERNEL_DARCY_APPLY, 10, True)
             a12, m12 = rs.time_kernel(abi.KERNEL_MINRES_UPDATE, 5, True)
             k11_b = 67 * 8 * r1n
-            k12_b = 15 * 8 * (rs.nv + rs.np_)
+            k12_b = 13 * 8 * (rs.nv + rs.np_)
         roofline_rt1 = {"kernel": "k1_darcy_apply<HY,DOT> (K1 of the RT1/L2-Q1 path + fused <u,Au>)", "bound": "hbm",
                         "achieved": k11_b / (a11 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": k11_b / (a11 * 1e-3) / 1e9 / peak, "traffic": None, "mesh": "rt1:192x192x192",

@@ -1511,7 +1511,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   {
     MinresState bs;
     memset(&bs, 0, sizeof bs);
-    bs.beta = 1.0; bs.eta = 1.0; bs.gamma0 = bs.gamma1 = 1.0;
+    bs.beta = 1.0; bs.eta = 1.0; bs.gamma0 = bs.gamma1 = 1.0; bs.m0 = bs.m1 = 1.0;
     const double sc[4] = {0.0, 0.0, 0.5, 1.0};
     CK(cudaMemcpyAsync(h->st + 2, &bs, sizeof bs, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->scal, sc, sizeof sc, cudaMemcpyHostToDevice, h->stream));

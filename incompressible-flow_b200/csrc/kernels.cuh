@@ -355,10 +355,10 @@ __global__ void __launch_bounds__(BLK) k_minres_b(long n, long n_u, const double
                                                   const double* __restrict__ Md, double* q_out,
                                                   const double* alpha_p, const MinresState* st) {
   if (st->done) return;
-  const double alpha = *alpha_p, beta = st->beta;
+  const double alpha = *alpha_p, beta = st->beta, m0 = st->m0, m1 = st->m1;
   for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
-    const double t = q_in[i] + (-beta) * v0[i];
-    const double v = t + (-alpha) * v1[i];
+    const double t = q_in[i] + (-beta) * (v0[i] * m0);
+    const double v = t + (-alpha) * (v1[i] * m1);
     v0[i] = v;
     if (i < n_u) q_out[i] = v / Md[i];
   }
@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(BLK) k_minres_b(long n, long n_u, const double
 
 // pass C: scalar recurrence + w/x update + scaling of the next Lanczos pair.
 //   w0 <- (-rho3/rho1) w0 + (-rho2/rho1) w1 + (1/rho1) u1 ; x += gamma1 eta w0 ;
-//   v0 *= 1/beta_new ; q *= 1/beta_new      (become v1, u1 of the next iteration)
+//   q *= 1/beta_new (becomes u1 of the next iteration: K1 and the halo exchange read it as is);
+//   the scaling v0 *= 1/beta_new (becomes v1) is lazy: only the factor is recorded (MinresState::m1)
 __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w0, const double* __restrict__ w1,
                                                   const double* __restrict__ u1, double* __restrict__ x,
                                                   double* __restrict__ v0, double* __restrict__ q,
@@ -394,7 +395,6 @@ __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w
     const double w = t + e * u1[i];
     w0[i] = w;
     x[i] += xf * w;
-    v0[i] *= m;
     q[i] *= m;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w
     s.beta = beta; s.eta = etan;
     s.gamma0 = gamma1; s.gamma1 = gamma1n;
     s.sigma0 = sigma1; s.sigma1 = sigma1n;
+    s.m0 = st->m1; s.m1 = m;
     s.it = st->it + 1;
     s.done = (fabs(etan) <= s.norm_goal) ? 1 : (s.it >= maxiter ? 2 : 0);
     *st_next = s;
@@ -414,18 +415,16 @@ __global__ void __launch_bounds__(BLK) k_minres_init(long n, double* __restrict_
   const double beta = sqrt(*bb_p);
   const double goal = fmax(rtol * beta, atol);
   const bool done = beta <= goal;
-  if (!done) {
+  if (!done) {  // u1 /= beta; v1 /= beta lazily through m1
     const double m = 1.0 / beta;
-    for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
-      v1[i] *= m;
-      u1[i] *= m;
-    }
+    for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) u1[i] *= m;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     MinresState s;
     s.beta = beta; s.eta = beta; s.eta0 = beta;
     s.gamma0 = 1.; s.gamma1 = 1.; s.sigma0 = 0.; s.sigma1 = 0.;
     s.norm_goal = goal;
+    s.m0 = 1.0; s.m1 = done ? 1.0 : 1.0 / beta;
     s.it = 0;
     s.done = done ? 1 : 0;
     *st0 = s;

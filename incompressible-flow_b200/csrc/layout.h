@@ -81,8 +81,13 @@ IMPES_HD int ix_p(const Lay& L, int i, int j, int kk) { return L.off_p + i + L.N
 IMPES_HD int ix_c(const Lay& L, int i, int j, int kk) { return i + L.NX * (j + L.NY * kk); }
 
 // MINRES scalar recurrence state, device resident (double buffered by iteration parity).
+// Lazy scaling of the Lanczos vectors v: they are stored UNscaled and k_minres_b, their only consumer, multiplies
+// on load by m1 = 1/beta of the current v1 or m0 = 1/beta of the previous one (v0).  The product is the double the
+// explicit scaling used to store, so nothing changes numerically; one read + one write per dof and iteration are
+// gone.  (u = P v stays explicitly scaled: scaling K1's many input loads instead costs K1 ~30 %, measured.)
 struct MinresState {
   double beta, eta, gamma0, gamma1, sigma0, sigma1, norm_goal, eta0;
+  double m0, m1;
   int it;     // iterations completed
   int done;   // 0 running, 1 converged, 2 hit maxiter
 };

@@ -21,7 +21,7 @@ with pkg.Solver(d, Kx, Ky, Kz, phi) as s:
     nd = s.nv + s.np_
     for kid, name, b in ((abi.KERNEL_DARCY_APPLY, "K1 darcy_apply+dot", (88 if d.dim == 3 else 64) * n),
                          (abi.KERNEL_SAT_SUBSTEP, "K6 sat_substep", (48 if d.dim == 3 else 40) * n),
-                         (abi.KERNEL_MINRES_UPDATE, "K2 minres b+c", 15 * 8 * nd)):
+                         (abi.KERNEL_MINRES_UPDATE, "K2 minres b+c", 13 * 8 * nd)):
         for fl in (1,):
             a, m = s.time_kernel(kid, reps, fl)
             print(f"{name:22s} flush={fl}: avg {a*1e3:9.1f} us  min {m*1e3:9.1f} us -> {b/(a*1e-3)/1e9:7.0f} GB/s algorithmic "

@@ -35,7 +35,7 @@ def probe(n3, mg=True, steps=2, two_d=False):
               ", ".join(f"{NAMES[i]}={ms[i]:.1f}/{cnt[i]}" for i in range(8) if cnt[i]), flush=True)
         bpc = (67 if d.dim == 3 else 26) * 8
         for kid, kname, b in ((abi.KERNEL_DARCY_APPLY, "K1 rt1 darcy_apply", bpc * n),
-                              (abi.KERNEL_MINRES_UPDATE, "K2 minres b+c", 15 * 8 * (s.nv + s.np_)),
+                              (abi.KERNEL_MINRES_UPDATE, "K2 minres b+c", 13 * 8 * (s.nv + s.np_)),
                               (abi.KERNEL_PREC_APPLY, "K3 prec", 0)):
             for fl in (0, 1):
                 a, m = s.time_kernel(kid, 5, fl)
