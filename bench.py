@@ -386,7 +386,8 @@ def main():
                        "achieved": k6_b / (a6 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": k6_b / (a6 * 1e-3) / 1e9 / peak, "traffic": int(1056e6 / 16777216 * rn), "mesh": args.roofline_size,
                        "bytes_per_launch": k6_b, "us_per_launch": a6 * 1e3,
-                       "note": "streaming form moves 64 B/cell (carried f(S) array) for 48 B algorithmic"}
+                       "note": "streaming form moves 64 B/cell (carried f(S) array) for 48 B algorithmic: actual DRAM "
+                               "throughput is 4/3 of `achieved`"}
         roofline_k2 = {"kernel": "k_minres_b + k_minres_c (K2, fused MINRES vector passes)", "bound": "hbm",
                        "achieved": k2_b / (a2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": k2_b / (a2 * 1e-3) / 1e9 / peak, "traffic": None, "mesh": args.roofline_size,
@@ -404,7 +405,7 @@ def main():
             k12_b = 13 * 8 * (rs.nv + rs.np_)
         roofline_rt1 = {"kernel": "k1_darcy_apply<HY,DOT> (K1 of the RT1/L2-Q1 path + fused <u,Au>)", "bound": "hbm",
                         "achieved": k11_b / (a11 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": k11_b / (a11 * 1e-3) / 1e9 / peak, "traffic": None, "mesh": "rt1:192x192x192",
+                        "frac": k11_b / (a11 * 1e-3) / 1e9 / peak, "traffic": int(1094e6 / 2097152 * r1n), "mesh": "rt1:192x192x192",
                         "bytes_per_launch": k11_b, "us_per_launch": a11 * 1e3,
                         "k2_on_this_mesh": {"achieved": k12_b / (a12 * 1e-3) / 1e9, "frac": k12_b / (a12 * 1e-3) / 1e9 / peak,
                                             "us_per_launch": a12 * 1e3}}
