@@ -229,6 +229,28 @@ __global__ void __launch_bounds__(BLK) k_face_coeff(Lay L, const double* __restr
 //     faces; upper faces only on the domain boundary) and its pressure row: a gather
 //     formulation -- no atomics, fixed summation order (the CSR column order of the oracle).
 // ---------------------------------------------------------------------------------------
+// One direction of the RT0 apply for one cell, branch-free: the loads were issued by the caller (clamped where the
+// neighbour does not exist), skipped CSR entries become `+ 0.0` (bit-identical partial sums).
+//   lo / lo2: the lower face is interior / the lower cell's lower face is interior; hi: the upper face is interior
+template <bool DOT>
+__device__ __forceinline__ void rt0_dir(bool lo, bool lo2, bool hi, double mL, double mR, double xm, double xf,
+                                        double xf1, double pc, double pm, double& yf, double& yb, double& yp,
+                                        double& acc) {
+  double s = 0.0;
+  s += lo2 ? (mL * SIXTH) * xm : 0.0;
+  s += (mL * THIRD + mR * THIRD) * xf;
+  s += hi ? (mR * SIXTH) * xf1 : 0.0;
+  yf = lo ? s + (pc - pm) : xf;  // eliminated boundary row: identity
+  if (DOT) acc += xf * yf;
+  yp += lo ? xf : 0.0;
+  yb = xf1;  // identity row of the upper boundary face (stored and counted only when !hi)
+  if (!hi) {
+    if (DOT) acc += xf1 * xf1;
+  } else {
+    yp -= xf1;
+  }
+}
+
 template <bool DOT>
 __global__ void __launch_bounds__(BLK) k_darcy_apply(Lay L, const double* __restrict__ mx,
                                                      const double* __restrict__ my, const double* __restrict__ mz,
@@ -240,79 +262,36 @@ __global__ void __launch_bounds__(BLK) k_darcy_apply(Lay L, const double* __rest
   double acc = 0.0;
   if (ci.ok) {
     const int i = ci.i, j = ci.j, kl = ci.kl, k = ci.k, kk = kl + 1;
-    const long c = ix_c(L, i, j, kk);
-    const long ip = L.off_p + c;
+    const int c = ix_c(L, i, j, kk);
+    const int ip = L.off_p + c;
+    const bool xl = i > 0, xl2 = i > 1, xh = i + 1 < L.NX;
+    const bool yl = j > 0, yl2 = j > 1, yh = j + 1 < L.NY;
+    const bool zl = k > 0, zl2 = k > 1, zh = k + 1 < L.NZ;
+    const int fx = ix_ux(L, i, j, kl), fz = ix_uz(L, i, j, kk);
+    const int fy = L.has_y ? ix_uy(L, i, j, kl) : fx;
+    // ---- load phase (all unconditional)
     const double pc = x[ip];
-    double yp = 0.0;
-    {  // ---- x faces
-      const long f = ix_ux(L, i, j, kl);
-      const double xf = x[f], xf1 = x[f + 1];
-      if (i > 0) {
-        const double mL = mx[c - 1], mR = mx[c];
-        double s = 0.0;
-        if (i - 1 > 0) s += (mL * SIXTH) * x[f - 1];
-        s += (mL * THIRD + mR * THIRD) * xf;
-        if (i + 1 < L.NX) s += (mR * SIXTH) * xf1;
-        const double yf = s + (pc - x[ip - 1]);
-        y[f] = yf;
-        if (DOT) acc += xf * yf;
-        yp += xf;
-      } else {
-        y[f] = xf;
-        if (DOT) acc += xf * xf;
-      }
-      if (i + 1 < L.NX) yp -= xf1;
-      else {
-        y[f + 1] = xf1;
-        if (DOT) acc += xf1 * xf1;
-      }
+    const double pxm = x[xl ? ip - 1 : ip], pym = x[(L.has_y && yl) ? ip - L.NX : ip], pzm = x[zl ? ip - L.plane : ip];
+    const double xxf = x[fx], xxf1 = x[fx + 1], xxm = x[xl ? fx - 1 : fx];
+    const double xyf = x[fy], xyf1 = x[L.has_y ? fy + L.NX : fy], xym = x[(L.has_y && yl) ? fy - L.NX : fy];
+    const double xzf = x[fz], xzf1 = x[fz + L.plane], xzm = x[zl ? fz - L.plane : fz];
+    const double mxR = mx[c], mxL = mx[xl ? c - 1 : c];
+    const double mzR = mz[c], mzL = mz[zl ? c - L.plane : c];
+    double myR = 0.0, myL = 0.0;
+    if (L.has_y) { myR = my[c]; myL = my[yl ? c - L.NX : c]; }
+    // ---- compute phase
+    double yp = 0.0, yf, yb;
+    rt0_dir<DOT>(xl, xl2, xh, mxL, mxR, xxm, xxf, xxf1, pc, pxm, yf, yb, yp, acc);
+    y[fx] = yf;
+    if (!xh) y[fx + 1] = yb;
+    if (L.has_y) {
+      rt0_dir<DOT>(yl, yl2, yh, myL, myR, xym, xyf, xyf1, pc, pym, yf, yb, yp, acc);
+      y[fy] = yf;
+      if (!yh) y[fy + L.NX] = yb;
     }
-    if (L.has_y) {  // ---- y faces
-      const long f = ix_uy(L, i, j, kl);
-      const double xf = x[f], xf1 = x[f + L.NX];
-      if (j > 0) {
-        const double mL = my[c - L.NX], mR = my[c];
-        double s = 0.0;
-        if (j - 1 > 0) s += (mL * SIXTH) * x[f - L.NX];
-        s += (mL * THIRD + mR * THIRD) * xf;
-        if (j + 1 < L.NY) s += (mR * SIXTH) * xf1;
-        const double yf = s + (pc - x[ip - L.NX]);
-        y[f] = yf;
-        if (DOT) acc += xf * yf;
-        yp += xf;
-      } else {
-        y[f] = xf;
-        if (DOT) acc += xf * xf;
-      }
-      if (j + 1 < L.NY) yp -= xf1;
-      else {
-        y[f + L.NX] = xf1;
-        if (DOT) acc += xf1 * xf1;
-      }
-    }
-    {  // ---- z faces
-      const long f = ix_uz(L, i, j, kk);
-      const double xf = x[f], xf1 = x[f + L.plane];
-      if (k > 0) {
-        const double mL = mz[c - L.plane], mR = mz[c];
-        double s = 0.0;
-        if (k - 1 > 0) s += (mL * SIXTH) * x[f - L.plane];
-        s += (mL * THIRD + mR * THIRD) * xf;
-        if (k + 1 < L.NZ) s += (mR * SIXTH) * xf1;
-        const double yf = s + (pc - x[ip - L.plane]);
-        y[f] = yf;
-        if (DOT) acc += xf * yf;
-        yp += xf;
-      } else {
-        y[f] = xf;
-        if (DOT) acc += xf * xf;
-      }
-      if (k + 1 < L.NZ) yp -= xf1;
-      else {
-        y[f + L.plane] = xf1;
-        if (DOT) acc += xf1 * xf1;
-      }
-    }
+    rt0_dir<DOT>(zl, zl2, zh, mzL, mzR, xzm, xzf, xzf1, pc, pzm, yf, yb, yp, acc);
+    y[fz] = yf;
+    if (!zh) y[fz + L.plane] = yb;
     y[ip] = yp;
     if (DOT) acc += pc * yp;
   }
