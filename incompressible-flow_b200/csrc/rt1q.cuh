@@ -294,7 +294,7 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, const
 }
 
 template <bool HY, bool DOT>
-__global__ void __launch_bounds__(BLK) k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam,
+__global__ void __launch_bounds__(BLK, 2) k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam,
                                                    const double* __restrict__ Kx, const double* __restrict__ Ky,
                                                    const double* __restrict__ Kz, double gx, double gy, double gz,
                                                    const double* __restrict__ x, double* __restrict__ y,
@@ -479,7 +479,7 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
 }
 
 template <bool HY, bool RATE>
-__global__ void __launch_bounds__(BLK) k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x,
+__global__ void __launch_bounds__(BLK, 2) k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x,
                                                const double* __restrict__ phi, const double* __restrict__ Sin,
                                                const double* __restrict__ Fin, double* __restrict__ Sout,
                                                double* __restrict__ Fout) {
