@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "config.hpp"
 #include "param.hpp"
@@ -23,11 +24,23 @@ double seconds_since(const chrono::steady_clock::time_point& t0) {
   return chrono::duration<double>(chrono::steady_clock::now() - t0).count();
 }
 // saturation_<extra>_<dim>D_<phase>_<step>.bin, float32, one value per cell [REF src/utilities.cpp:565-582]
+// The reference fills the per-cell array through S.ProjectCoefficient(ValuesInCells(saturation))
+// [REF src/run_serial.cpp:123-127] [REF src/param.hpp:413-442]: every nodal evaluation of an element overwrites
+// the cell's entry, so the value that survives is the one of the element's LAST local dof [MFEM-recall:
+// NodalFiniteElement::Project loops over the dofs in order].  DG_0: the cell value; DG-Q1: local dof 2^dim - 1.
 void output_saturation_cells(const Param& p, const Vector& S, int ti) {
   const string phase = p.two_phase_flow ? "2phase" : "1phase";
   const string fname = string(p.outdir) + "/saturation_" + p.extra + "_" + d2s(p.spacedim) + "D_" + phase + "_" +
                        d2s(ti, 0, 0, 0, 6) + ".bin";
-  write_binary(fname.c_str(), p.get_n_cells(), S.GetData());
+  const int n = p.get_n_cells();
+  const int nsl = S.Size() / n;
+  if (nsl == 1) {
+    write_binary(fname.c_str(), n, S.GetData());
+    return;
+  }
+  std::vector<double> in_cells(n);
+  for (int c = 0; c < n; ++c) in_cells[c] = S.GetData()[(long)c * nsl + nsl - 1];
+  write_binary(fname.c_str(), n, in_cells.data());
 }
 }  // namespace
 
@@ -51,7 +64,7 @@ void run_serial(int argc, char** argv) {
     throw 1;
   }
   args.PrintOptions(cout);
-  MFEM_VERIFY(p.order_s == 0, "This driver writes one saturation value per cell (order_s = 0)");
+  MFEM_VERIFY(p.order_s == 0 || p.order_s == 1, "The GPU path implements DG_0 and DG_1 saturation");
 
   p.init_arrays();
   const string cmd = "mkdir -p " + string(p.outdir);

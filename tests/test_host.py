@@ -100,3 +100,48 @@ def test_driver_aborts_when_not_converged(host_bins, tmp_path):
                        capture_output=True, text=True, timeout=120)
     assert o.returncode != 0
     assert "Darcy solver DIDN'T converge. Iter = 3" in o.stderr and "The solver didn't converge => terminating" in o.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 3])
+def test_driver_run_dgq1(pkg, orc, host_bins, tmp_path, dim):
+    """The driver with `-os 1` (RT1 / L2-Q1 / DG-Q1): iteration counts as the oracle's loop (+-2) and the reference's
+    dump semantics -- S.ProjectCoefficient(ValuesInCells) keeps the value of each element's LAST local dof
+    [REF src/run_serial.cpp:123-127] [REF src/param.hpp:424-435] -- to float32 precision."""
+    from incompressible_flow_b200 import workloads
+    nx, ny, nz = (14, 12, 1) if dim == 2 else (6, 5, 6)
+    n = nx * ny * nz
+    K32 = np.exp(np.random.default_rng(3).standard_normal(n)).astype(np.float32)
+    kfile = tmp_path / "K.bin"
+    K32.tofile(kfile)
+    out = tmp_path / "out"
+    dtg, dtl = 0.5, 0.05
+    h = 100.0 / nx
+    common = ["-d", str(dim), "-nx", str(nx), "-ny", str(ny), "-nz", str(nz), "-sx", "100", "-sy", "100", "-sz", "100",
+              "-ov", "1", "-op", "1", "-os", "1", "-two-phase", "-tf", str(2 * dtg), "-dtg", str(dtg), "-dtl", str(dtl), "-vsg", "0",
+              "-K-file-x", str(kfile), "-K-file-y", str(kfile), "-K-file-z", str(kfile), "-outdir", str(out),
+              "-extra", "q", "-darcy-maxiter", "5000"]
+    if dim == 2:
+        wells = ["-inj-xcen", "0", "-inj-ycen", "0", "-inj-r", str(h), "-pro-xcen", "100", "-pro-ycen", "100", "-pro-r", str(h)]
+    else:
+        wells = ["-inj-xcen", "0", "-inj-zcen", "0", "-inj-ycen", "0", "-inj-h", "100", "-inj-r", str(h),
+                 "-pro-xcen", "100", "-pro-zcen", "100", "-pro-ycen", "0", "-pro-h", "100", "-pro-r", str(h)]
+    o = subprocess.run([host_bins[0]] + common + wells, capture_output=True, text=True, timeout=300)
+    assert o.returncode == 0, o.stdout + o.stderr
+    its = [int(m) for m in re.findall(r"Darcy solver converged\. Iter = (\d+)", o.stdout)]
+    assert o.stdout.count("is done") == 2 and f"dim(S)  = {n * 2 ** dim}" in o.stdout
+    d = workloads.make_desc(dim, nx, ny, nz, sx=100, sy=100, sz=100, maxiter=5000, order=1, order_s=1)
+    for w, c, r in ((d.injection, (0, 0, 0), h), (d.production, (100, 100 if dim == 2 else 0, 100), h)):
+        w.center[0], w.center[1], w.center[2] = c
+        w.radius, w.height = r, 100.0
+    K = K32.astype(np.float64)
+    oc = orc.Oracle(d, K, K, K if dim == 3 else None, np.ones(n))
+    oc.set_arith(1)
+    S, nsl = np.zeros(oc.ns), 2 ** dim
+    for ti in range(1, 3):
+        x, st, rc = oc.pressure_solve(S)
+        S, _ = oc.saturation_advance(x[:oc.nv], S, dtg, dtl)
+        assert abs(its[ti - 1] - st.iterations) <= 2
+        dump = np.fromfile(out / f"saturation_q_{dim}D_2phase_{ti:06d}.bin", dtype=np.float32)
+        want = S.reshape(n, nsl)[:, nsl - 1]
+        assert dump.shape == (n,) and np.allclose(dump, want, rtol=2e-6, atol=1e-7)
