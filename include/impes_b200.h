@@ -34,11 +34,18 @@
  *           [REF src/run_serial.cpp:66-81].
  *
  * Multi-GPU (one process per GPU): the grid is cut into slabs along the
- * slowest direction (z in 3-D, y in 2-D).  Host-side arrays passed through
- * this ABI are always GLOBAL (full-mesh) arrays in native layout, like the
- * reference where every rank holds the full K/phi arrays
- * [REF src/run_parallel.cpp:83-95]; each rank reads/writes only the part it
- * owns (impes_owned_range), see INTEGRATION.md.
+ * slowest direction (z in 3-D, y in 2-D): balanced, the first (n % P) ranks one
+ * layer more; with IMPES_SCHUR_MG in units of 2^m layers so that multigrid
+ * aggregates never straddle GPUs.  impes_get_dims reports the slab
+ * (slab_lo, slab_hi).  Host-side arrays passed through this ABI are always GLOBAL
+ * (full-mesh) arrays in native layout, like the reference where every rank holds
+ * the full K/phi arrays [REF src/run_parallel.cpp:83-95]; each rank reads/writes
+ * only the part it owns, see INTEGRATION.md.
+ *
+ * Supported spaces (anything else: impes_create -> IMPES_ERR_UNSUPPORTED):
+ *   order_v/order_p/order_s = 0/0/0   RT0 / P0 / P0
+ *                             1/1/0   RT1 / L2-Q1 / DG_0   (the reference's defaults [REF src/param.cpp:43])
+ *                             1/1/1   RT1 / L2-Q1 / DG-Q1  (BASELINE config C5)
  */
 #ifndef IMPES_B200_H
 #define IMPES_B200_H
@@ -67,7 +74,8 @@ extern "C" {
                                  [REF src/pressure_solver.cpp:83-91] -- parity mode */
 #define IMPES_SCHUR_MG      1 /* geometric multigrid V-cycle on the same S -- throughput
                                  mode (stands where the MPI reference uses BoomerAMG
-                                 [REF src/par_pressure_solver.cpp:89-90]) */
+                                 [REF src/par_pressure_solver.cpp:89-90]); distributed over
+                                 the slabs, result independent of the number of GPUs */
 
 /* sub-step count rule of the saturation loop */
 #define IMPES_SUBSTEPS_SERIAL   0 /* nt = int(global_dt/dt_local)   [REF src/saturation_solver.cpp:74-76] */
