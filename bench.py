@@ -348,6 +348,7 @@ def main():
 
     # ---------------- step breakdown on the benchmark mesh (profiled, untimed) ---------------------
     breakdown = None
+    roofline_dominant = None
     if world == 1:
         s.profile_enable(True)
         step(200)
@@ -356,6 +357,25 @@ def main():
         tot = sum(pms) or 1.0
         breakdown = {NAMES[i]: {"ms": round(pms[i], 3), "launches": int(pn[i]), "share": round(pms[i] / tot, 4)}
                      for i in range(8) if pn[i]}
+        try:
+            # the dominant kernel class of this step, against the same HBM roofline: in parity mode it is the exact
+            # lexicographic Gauss-Seidel sweep, a dependent chain -- bytes are not what bounds it
+            dom = max(breakdown, key=lambda k: breakdown[k]["ms"])
+            if dom == "schur_prec" and not fast_headline:
+                n_apply = breakdown["dot"]["launches"]            # one preconditioner application per dot <v, Pv>
+                us = 1e3 * breakdown[dom]["ms"] / max(n_apply, 1)
+                k3_b = 100 * n                                     # ~100 B/cell per application (both sweeps)
+                pk, _src = hbm_peak()
+                roofline_dominant = {
+                    "kernel": "k_sgs_tma + skew in/out (K3: one symmetric Gauss-Seidel application, both sweeps)",
+                    "share_of_step": breakdown[dom]["share"], "bound": "hbm",
+                    "achieved": k3_b / (us * 1e-6) / 1e9, "peak": pk, "unit": "GB/s",
+                    "frac": k3_b / (us * 1e-6) / 1e9 / pk, "traffic": None,
+                    "bytes_per_launch": k3_b, "us_per_launch": us,
+                    "note": "latency bound, not bandwidth bound: a chain of 2(NX+NY-2) dependent wavefront stages per "
+                            "application (~270 ns each); the HBM roofline is reported for completeness only"}
+        except Exception:
+            roofline_dominant = None
     s.close()
 
     # ---------------- roofline: K1 / K6 alone on a streaming-size mesh -----------------------------
@@ -498,6 +518,7 @@ def main():
                                      "Krylov vectors") + "; the roofline kernels run on a >=4xL2 mesh with L2 flushed"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_k6": roofline_k6, "roofline_k2": roofline_k2, "roofline_k1_rt1": roofline_rt1,
+            "roofline_dominant_kernel": roofline_dominant,
             "step_breakdown": breakdown, "fast_mode": fast, "same_workload_1gpu": one_gpu, "cpu_baseline": cpu,
         }
         emit(line)
