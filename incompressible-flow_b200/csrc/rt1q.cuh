@@ -8,11 +8,13 @@
 // B, the right-hand side, S = B diag(M)^-1 B^T and both Schur preconditioners keep the structure of rt1.cuh:
 // only diag(M) (hence T = 1/diag(M)) changes.
 //
-// Parity: these kernels evaluate the operators matrix-free in sum-factorised form, the oracle assembles element
-// matrices entry by entry; the two agree to round-off (tests: 1e-13 relative per operator application), not bit
-// for bit -- a canonical-arithmetic restatement of this path does not exist yet.
-// FMA contraction is off for the file (arithmetic contract of kernels.cuh); the dense element products below use
-// explicit __fma_rn because they are not part of a bit-exact contract.
+// Parity: these kernels evaluate the operators matrix-free in sum-factorised form, the assembled-CSR checker builds
+// element matrices entry by entry; those two agree to round-off (tests: 1e-12 relative per operator application).
+// The checker's canonical arithmetic for this path is a matrix-free mirror that performs the operations below in
+// the same order, and the tests compare against it bit for bit -- so the order of every sum in this file is part
+// of a contract: change it together with the mirror.
+// FMA contraction is off for the file (arithmetic contract of kernels.cuh); the dense element products use
+// explicit __fma_rn (mirrored by fma() on the CPU).
 #pragma once
 #include "rt1.cuh"
 

@@ -80,6 +80,10 @@ typedef struct orc {
                                   are pinned so that GPU and oracle agree bit for bit. */
   /* canonical RT1/Q1 constants (arith == 1): CW = Mc (x) Mo (x) Mo entries, Bv = -G (x) Mo (x) Mo */
   double c_wt, c_CW[3][3], c_Bv[2][3];
+  /* canonical DG-Q1 path (arith == 1, kv = kp = ks = 1): w_q / lambda(S(x_q)) per cell and the dot of the last
+   * canonical K1 application (orc_q1.inc mirrors csrc/rt1q.cuh operation by operation) */
+  double *rlam;
+  double q1_alpha;
   int threads;             /* >1: OpenMP in SpMV / vector ops (CPU baseline only) */
   int mass_cg;             /* 1: invert M_phi with Jacobi-PCG like the reference */
   /* MG hierarchy for IMPES_SCHUR_MG (restated in orc_mg.inc) */
@@ -479,7 +483,7 @@ extern void orc_mg_free(orc *o);
 ORC_API void orc_destroy(orc *o) {
   if (!o) return;
   for (int c = 0; c < 3; ++c) free(o->K[c]);
-  free(o->phi); free(o->ess); free(o->rhs); free(o->Md);
+  free(o->phi); free(o->ess); free(o->rhs); free(o->Md); free(o->rlam);
   csr_free(&o->B); csr_free(&o->BT); csr_free(&o->M); csr_free(&o->S);
   orc_mg_free(o);
   free(o);
@@ -647,6 +651,11 @@ static double sat_at(const orc *o, const double *S, long cell, const double *xi)
   return v;
 }
 
+static int q1_canonical(const orc *o) { return o->arith == 1 && o->kv == 1 && o->kp == 1 && o->ks == 1 && o->threads <= 1; }
+static void q1_coefficients(orc *o, const double *S);
+static void q1_darcy_mult(orc *o, const double *x, double *y);
+static int q1_saturation_rate(const orc *o, const double *u, const double *S, const double *F, double *out, double dt, int rate);
+
 /* M = VectorFEMassIntegrator(CWVectorCoefficient)  [REF src/pressure_solver.cpp:47,50-51]
  * with boundary rows/cols eliminated, diagonal 1 [REF :60]; then diag(M) and
  * S = B diag(M)^-1 B^T  [REF :76-81]. */
@@ -766,6 +775,7 @@ static int assemble_system(orc *o, const double *S) {
       }
     o->Md[r] = dg;
   }
+  if (q1_canonical(o)) q1_coefficients(o, S); /* canonical diag(M): the GPU's quadrature sums, bit for bit */
   /* S = B * (diag(Md)^-1 B^T): row-by-row SpGEMM, columns sorted ascending */
   {
     long cap2 = 0;
@@ -798,6 +808,7 @@ static int assemble_system(orc *o, const double *S) {
 
 /* BlockMatrix::Mult: y = 0; y_u += M x_u; y_u += BT x_p; y_p += B x_u [MFEM-recall] */
 static void darcy_mult(const orc *o, const double *x, double *y) {
+  if (q1_canonical(o)) { q1_darcy_mult((orc *)o, x, y); return; }
   csr_mult(o, &o->M, x, y, 0);
   csr_mult(o, &o->BT, x + o->nv, y, 1);
   csr_mult(o, &o->B, x, y + o->nv, 0);
@@ -865,7 +876,7 @@ static void minres(orc *o, const double *b, double *x, impes_solve_stats *st) {
       for (long i = 0; i < n; ++i) { v1[i] *= m; u1[i] *= m; }
     }
     darcy_mult(o, u1, q);
-    alpha = vdot(o, u1, q, n);
+    alpha = q1_canonical(o) ? o->q1_alpha : vdot(o, u1, q, n); /* canonical DG-Q1: the dot fused into K1 (two passes) */
     if (it > 1) {
 #pragma omp parallel for schedule(static) if (T)
       for (long i = 0; i < n; ++i) q[i] += -beta * v0[i]; /* q.Add(-beta, v0) */
@@ -1245,9 +1256,16 @@ static int n_substeps(const orc *o, double global_dt, double dt) {
 }
 
 /* F(S) = M_phi^-1 (Kt f(S) + b)   FE_Evolution::Mult [REF src/par_saturation_solver.cpp:46-62] */
+static const double *g_q1_u; /* velocity of the running orc_saturation_advance call (canonical DG-Q1 stages) */
 static void sat_rate(const orc *o, const csr *Kt, const double *b, const double *Mphi, const double *S, double *fs,
                      double *z, double *y) {
   const long n = o->ns;
+  if (q1_canonical(o)) { /* the GPU's fused stage, operation by operation (orc_q1.inc) */
+    if (o->d.two_phase) frac_flow(o, S, fs, n);
+    else memcpy(fs, S, sizeof(double) * n);
+    q1_saturation_rate(o, g_q1_u, S, fs, y, 0.0, 1);
+    return;
+  }
   if (o->d.two_phase) { frac_flow(o, S, fs, n); csr_mult(o, Kt, fs, z, 0); }
   else csr_mult(o, Kt, S, z, 0);
 #pragma omp parallel for schedule(static) if (o->threads > 1)
@@ -1259,6 +1277,7 @@ static void sat_rate(const orc *o, const csr *Kt, const double *b, const double 
  * [REF src/par_saturation_solver.cpp:113-124] ([MFEM-recall]). */
 ORC_API int orc_saturation_advance(orc *o, const double *u, double *S, double global_dt, double dt, int *nsub_out) {
   const long n = o->ns;
+  g_q1_u = u;
   csr Kt; memset(&Kt, 0, sizeof Kt);
   double *b = (double *)malloc(sizeof(double) * n), *Mphi = (double *)malloc(sizeof(double) * n);
   if (assemble_saturation(o, u, &Kt, b, Mphi)) { free(b); free(Mphi); return IMPES_ERR_UNSUPPORTED; }
@@ -1328,3 +1347,4 @@ ORC_API void orc_guards(orc *o, const double *S, long *n_nonfinite, double *s_ma
 }
 
 #include "orc_mg.inc"
+#include "orc_q1.inc"

@@ -24,7 +24,7 @@ _dp = C.POINTER(C.c_double)
 
 def build(force=False):
     so = os.path.join(_HERE, "libimpes_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("impes_oracle.c", "orc_mg.inc")] + [
+    srcs = [os.path.join(_HERE, f) for f in ("impes_oracle.c", "orc_mg.inc", "orc_q1.inc")] + [
         os.path.join(os.path.dirname(_HERE), "include", "impes_b200.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libimpes_oracle.so"], stdout=subprocess.DEVNULL)

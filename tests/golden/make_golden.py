@@ -17,12 +17,12 @@ CASES = {
     # the reference's default spaces RT1 / L2-Q1 / DG_0 (bit-exact on the GPU)
     "rt1_2d_10x8": dict(dim=2, nx=10, ny=8, K="lognormal", sigma=1.0, order=1, order_s=0),
     "rt1_3d_5x4x4": dict(dim=3, nx=5, ny=4, nz=4, K="lognormal", sigma=1.0, order=1, order_s=0),
-    # RT1 / L2-Q1 / DG-Q1 (config C5's spaces): the GPU path agrees to round-off, not bit for bit (csrc/rt1q.cuh)
+    # RT1 / L2-Q1 / DG-Q1 (config C5's spaces): canonical arithmetic = oracle/orc_q1.inc, bit-exact on the GPU too
     "rt1q_2d_8x6": dict(dim=2, nx=8, ny=6, K="lognormal", sigma=1.0, order=1, order_s=1),
 }
 # (global dt, local dt) of the two IMPES steps; DG-Q1 with forward Euler needs a small step
 DT = {"rt1q_2d_8x6": (1.0, 0.05), "rt1_3d_5x4x4": (4.0, 0.5)}   # small meshes: stay before breakthrough
-EXACT_ON_GPU = {name: not name.startswith("rt1q") for name in CASES}
+EXACT_ON_GPU = {name: True for name in CASES}
 
 if __name__ == "__main__":
     load_package()

@@ -2,8 +2,10 @@
 against the CPU oracle.
 
 With S in DG-Q1 the mobility varies inside a cell: the GPU applies the dense RT1 element blocks matrix-free in
-sum-factorised form (csrc/rt1q.cuh) while the oracle assembles them entry by entry with MFEM's quadrature rules, so
-the two agree to round-off, not bit for bit.  Tolerances (fp64, written here on purpose):
+sum-factorised form (csrc/rt1q.cuh) while the oracle's independent formulation assembles them entry by entry with
+MFEM's quadrature rules, so those two agree to round-off, not bit for bit; the oracle's canonical arithmetic
+(oracle/orc_q1.inc) mirrors the kernels' operation order and is matched bit for bit
+(test_q1_bit_exact_against_canonical_mirror).  Tolerances against the assembled form (fp64, written here on purpose):
   operator applications (K1, preconditioner, one saturation stage)   <= 1e-12 relative L2;
   MINRES solves: iteration counts within +-2, solution within the Krylov drift bound 1e-6
   (tests/test_oracle_invariants.py::test_krylov_drift: round-off level perturbations move a rtol=1e-6 solve by
@@ -151,4 +153,38 @@ def test_q1_tight_solve_meets_1e10(pkg, orc, native_lib, cfg):
     So, _ = o.saturation_advance(xo[:o.nv], S, 0.4, 0.05)
     Sg, _ = s.saturation_advance(None, S, 1, 0.4, 0.05)
     assert rel(Sg, So) < 1e-10
+    s.close()
+
+
+@pytest.mark.parametrize("cfg", CASES[:4])
+@pytest.mark.parametrize("two_phase", [True, False])
+def test_q1_bit_exact_against_canonical_mirror(pkg, orc, native_lib, cfg, two_phase):
+    """The oracle's canonical arithmetic for DG-Q1 (oracle/orc_q1.inc) performs the kernels' floating-point
+    operations in the kernels' order: K1, the preconditioner, whole MINRES solves (SGS and multigrid) and
+    saturation steps are then bit-identical, like the other spaces.  (The independent assembled formulation is
+    compared to round-off in the tests above.)"""
+    from incompressible_flow_b200 import abi
+    d, o, s, n = make(pkg, orc, cfg, two_phase=two_phase)
+    o.set_arith(1)
+    rng = np.random.default_rng(3)
+    S = rng.uniform(0.05, 0.95, o.ns)
+    x = rng.standard_normal(o.nv + o.np_)
+    s.update_coefficients(S)
+    o.update_coefficients(S)
+    assert np.array_equal(s.darcy_apply(x), o.darcy_apply(x))
+    assert np.array_equal(s.prec_apply(x), o.prec_apply(x))
+    xo, sto, _ = o.pressure_solve(S)
+    xg, stg = s.pressure_solve(S)
+    assert stg.iterations == sto.iterations and stg.final_norm == sto.final_norm
+    assert np.array_equal(xg, xo)
+    So, _ = o.saturation_advance(xo[:o.nv], S, 0.4, 0.05)
+    Sg, _ = s.saturation_advance(None, S, 1, 0.4, 0.05)
+    assert np.array_equal(Sg, So)
+    s.close()
+    # multigrid mode
+    d, o, s, n = make(pkg, orc, cfg, two_phase=two_phase, schur_prec=abi.SCHUR_MG)
+    o.set_arith(1)
+    xo, sto, _ = o.pressure_solve(S)
+    xg, stg = s.pressure_solve(S)
+    assert stg.iterations == sto.iterations and np.array_equal(xg, xo)
     s.close()
