@@ -309,3 +309,31 @@ def test_q1_canonical_matches_assembled(pkg, orc, cfg, two_phase):
     assert rel(b[0], a[0]) < 1e-13 and rel(b[1], a[1]) < 1e-13
     assert a[3] == b[3] and rel(b[2][:o.nv], a[2][:o.nv]) < 1e-7
     assert rel(b[4], a[4]) < 1e-13
+
+
+@pytest.mark.parametrize("order_s", [0, 1])
+@pytest.mark.parametrize("cfg", [dict(dim=2, nx=7, ny=6), dict(dim=3, nx=4, ny=3, nz=3)])
+def test_rt1_operator_structure(pkg, orc, cfg, order_s):
+    """Structural invariants of the RT1 / L2-Q1 system, in both arithmetic modes and for both saturation spaces:
+    the Darcy block operator is symmetric, constant pressure spans its null space (all-essential boundary:
+    B^T 1 = 0 on the non-eliminated nodes), S = B diag(M)^-1 B^T has zero row sums and is symmetric, the block
+    preconditioner is symmetric positive, and sum(g) = 0 for the benchmark wells."""
+    d, o = build(pkg, orc, K="lognormal", order=1, order_s=order_s, **cfg)
+    rng = np.random.default_rng(11)
+    S = rng.uniform(0.05, 0.95, o.ns)
+    a, b = rng.standard_normal(o.nv + o.np_), rng.standard_normal(o.nv + o.np_)
+    ones = np.concatenate([np.zeros(o.nv), np.ones(o.np_)])
+    for arith in (0, 1):
+        o.set_arith(arith)
+        o.update_coefficients(S)
+        Aa, Ab = o.darcy_apply(a), o.darcy_apply(b)
+        assert abs(b @ Aa - a @ Ab) < 1e-11 * (np.linalg.norm(a) * np.linalg.norm(Ab))
+        assert np.linalg.norm(o.darcy_apply(ones)) < 1e-12 * np.sqrt(o.np_)
+        Sc = o.csr("S")
+        assert abs(Sc.sum(axis=1)).max() < 1e-11 * abs(Sc).max()
+        assert abs(Sc - Sc.T).max() < 1e-13 * abs(Sc).max()
+        Pa, Pb = o.prec_apply(a), o.prec_apply(b)
+        assert abs(b @ Pa - a @ Pb) < 1e-10 * abs(b @ Pa) + 1e-12
+        assert a @ Pa > 0 and b @ Pb > 0
+        g = o.rhs()
+        assert not g[:o.nv].any() and abs(g[o.nv:].sum()) < 1e-12 * abs(g[o.nv:]).max()
