@@ -680,14 +680,23 @@ static int assemble_system(orc *o, const double *S) {
     for (int a = 0; a < kv + 1; ++a) O[q][a] = lag(o->onode, kv + 1, a, qm.x[q]);
   }
   const int nqt = Q[0]->nq * Q[1]->nq * Q[2]->nq;
+  /* Element loop.  Every cell writes its element-matrix entries into its own slot of the COO arrays (slot =
+   * dim*nl*nl entries, the closed forms use fewer) and the slots are compacted in cell order afterwards, so the
+   * COO sequence -- hence the CSR and every sum built from it -- is the same with one thread or many (OpenMP is
+   * only for the CPU baseline: MFEM's own assembly is element-parallel-friendly too). */
+  const long slot = (long)dim * nl * nl;
+  long *cellcnt = (long *)malloc(sizeof(long) * o->ncell);
+#pragma omp parallel if (o->threads > 1)
+  {
   double *coef = (double *)malloc(sizeof(double) * nqt);
   long *gl = (long *)malloc(sizeof(long) * nl);
   double *phi = (double *)malloc(sizeof(double) * nl * nqt);
-  for (int cz = 0; cz < o->n[2]; ++cz)
-    for (int cy = 0; cy < o->n[1]; ++cy)
-      for (int cx = 0; cx < o->n[0]; ++cx) {
+#pragma omp for schedule(static)
+  for (long cell = 0; cell < o->ncell; ++cell) {
+      {
+        const int cx = (int)(cell % o->n[0]), cy = (int)((cell / o->n[0]) % o->n[1]), cz = (int)(cell / ((long)o->n[0] * o->n[1]));
         const int cc[3] = {cx, cy, cz};
-        const long cell = cx + (long)o->n[0] * (cy + (long)o->n[1] * cz);
+        long nnz = cell * slot;
         /* total mobility at the quadrature points: CWVectorCoefficient::Eval [REF src/param.hpp:246-261] */
         int qi = 0;
         for (int q2 = 0; q2 < Q[2]->nq; ++q2)
@@ -758,8 +767,21 @@ static int assemble_system(orc *o, const double *S) {
               ri[nnz] = r; ci[nnz] = (int)c; vv[nnz] = val; ++nnz;
             }
         }
+        cellcnt[cell] = nnz - cell * slot;
       }
+  }
   free(coef); free(gl); free(phi);
+  }
+  for (long cell = 0; cell < o->ncell; ++cell) { /* compact the slots in cell order */
+    const long from = cell * slot, cnt = cellcnt[cell];
+    if (from != nnz) {
+      memmove(ri + nnz, ri + from, sizeof(long) * cnt);
+      memmove(ci + nnz, ci + from, sizeof(int) * cnt);
+      memmove(vv + nnz, vv + from, sizeof(double) * cnt);
+    }
+    nnz += cnt;
+  }
+  free(cellcnt);
   csr_free(&o->M);
   if (coo_to_csr(o->nv, o->nv, nnz, ri, ci, vv, &o->M)) return -1;
   free(ri); free(ci); free(vv);
