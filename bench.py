@@ -1,35 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- IMPES cell-steps/s on B200 (BASELINE.json metric), one JSON line on stdout.
+"""bench.py -- IMPES cell-steps/s on B200 (BASELINE.json metric), ONE compact JSON line on stdout.
 
-A "step" is one global IMPES step of the reference's loop [REF src/run_serial.cpp:109-143]:
-one PressureSolver call (mixed-Darcy MINRES solve, saturation frozen) followed by one
-SaturationSolver call (dt_global/dt_local = 100 explicit upwind sub-steps, velocity frozen).
+A "step" is one global IMPES step of the reference's loop [REF src/run_parallel.cpp:176-187]
+[REF src/run_serial.cpp:109-143]: one (Par)PressureSolver call (mixed-Darcy MINRES solve, saturation frozen)
+followed by one (Par)SaturationSolver call (dt_global/dt_local = 100 explicit upwind sub-steps, velocity frozen).
+The timed span is the reference's `global_time_loop` [REF src/run_parallel.cpp:173-174,247-260].
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C1..C4|nxXnyXnz]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C1..C5|[rt1:|q1:]nxXnyXnz]
+                  [--prec mg|sgs]
 
-Workload by GPU count (BASELINE.json configs):
-  N=1  -> C2 (2-D 512x512 log-normal, RT0/P0) with the SERIAL reference's algorithm (lexicographic symmetric
-          Gauss-Seidel Schur preconditioner, `run_serial`): parity mode, bit-identical to the oracle;
-  N>1  -> C5 (3-D 256^3 log-normal, RT1/L2-Q1; saturation in DG_0 = the reference's default `-os 0`, DG-Q1
-          saturation is not on the GPU yet) cut into N slabs, with the PARALLEL reference's structure
-          (`run_parallel`: AMG-type Schur preconditioner -> the geometric multigrid of csrc/mg.cuh, whose result
-          does not depend on N).  Strong scaling of one fixed mesh; the same workload on 1 GPU is reported under
-          `fast_mode` of the N=1 line.
-Time steps: 2-D `-dtg 100 -dtl 1`; 3-D `-dtg 50 -dtl 0.5` -- dtl = 1 is exactly CFL = 1 at the well
-cells and blows up on heterogeneous 3-D fields (S_max >> 1.1 would trip the reference's own guard
-[REF src/run_serial.cpp:138]); both give 100 sub-steps per step.
+ONE workload at every N (strong scaling of one fixed mesh): by default BASELINE.json's C5 -- 3-D 256^3, RT1 / L2-Q1 /
+DG-Q1 (`-ov 1 -op 1 -os 1`), two-phase, log-normal K -- cut into N slabs, with the structure of the PARALLEL reference
+(`run_parallel`: AMG-type Schur preconditioner -> the geometric multigrid of csrc/mg.cuh, whose result does not depend
+on N).  `--prec sgs` selects the serial reference's exact lexicographic Gauss-Seidel instead (parity mode).
+Set-up of C5 (workloads.bench_setup): `-sat-source 0.5 -dtg 25 -dtl 0.25` (100 sub-steps).  SURVEY 8d's `-sat-source 1
+-dtl 1` is not runnable with DG-Q1: forward Euler at CFL 1 is unstable for linear DG, and with source 1 the well cells
+sit at S = 1 where f(S) stops being monotone; with source 0.5 / CFL 0.25 S stays in [-O(1), 0.65] and the MINRES
+iteration count stays at 41-45 over the run.
 
-value  = n_cells * K / (device time of K steps, state resident in HBM), max over ranks.
-e2e    = the same through the drop-in C ABI with HOST (pinned) buffers: every step uploads S, downloads
-         x = [V|P], uploads V and S, downloads S -- exactly what the reference-signature adapter does.
-roofline = K1 (matrix-free Darcy block apply, the Krylov matvec) timed alone with CUDA events on a
-         streaming-size mesh (>= 4x L2, L2 flushed before every launch), algorithmic bytes / time against
-         the measured HBM peak of MEASURED_PEAKS.json.  The benchmark meshes C1-C4 are L2-resident
-         (SURVEY 8d), so their steps are latency-bound and say nothing about HBM; `step_breakdown`
-         reports where the step time goes on the benchmark mesh itself.
-cpu_baseline = the CPU oracle (restatement of the reference's algorithm: MFEM/HYPRE cannot be built in
-         this image) timed on the host cores on one step of the same workload.
---impl reference = that same oracle as the whole "reference arm" (rank 0 only).
+value    = n_cells * K / (device time of K steps, state resident in HBM), max over ranks.
+e2e      = the same through the drop-in C ABI with HOST (pinned) buffers, slab-local like the reference's
+           ParGridFunction data: every step uploads S, downloads x = [V|P], uploads V and S, downloads S.
+roofline = the kernel with the largest share of the step, from a profiled step (CUDA events around every launch
+           on the library's stream): algorithmic bytes per launch / average launch time against the measured HBM
+           peak (MEASURED_PEAKS.json); `rooflines` lists every kernel of the step the same way.  `traffic` is
+           dram bytes per launch from a committed ncu capture (profiles/r02_traffic.json, scaled by cell count, file
+           named in the record) or null.
+cpu_baseline (N=1, rank 0) = the CPU oracle (assembled-CSR restatement of the reference's algorithm; MFEM/HYPRE
+           cannot be built in this image) on all host cores on a bounded sample of the workload (a smaller mesh of
+           the same kind); the GPU runs that same mesh in the same invocation (`same_mesh`), and `parity` compares
+           the two results.
+--impl reference = that same oracle as the whole "reference arm" (rank 0 only), same config keys.
+Full per-kernel detail goes to gpurun_out/bench_full_n<N>.json when that directory exists.
 """
 import argparse
 import json
@@ -48,7 +50,7 @@ os.dup2(2, 1)
 
 
 def emit(line):
-    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.write(json.dumps(line, separators=(",", ":")) + "\n")
     _REAL_STDOUT.flush()
 
 
@@ -56,38 +58,53 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_oracle, load_package  # noqa: E402
 
-def time_steps(dim):
-    return (100.0, 1.0) if dim == 2 else (50.0, 0.5)
+
+def rnd(v, n=4):
+    return None if v is None else float(f"{v:.{n}g}")
 
 
-NAMES = ["darcy_apply", "minres_update", "schur_prec", "sat_substep", "coeff", "dot", "misc", "comm"]
-
-
-def parse_workload(name, gpus):
-    pkg = load_package()
+def parse_workload(name):
+    """-> (name, build cfg, dt_global, dt_local)"""
+    load_package()
     from incompressible_flow_b200 import workloads
     if name is None:
-        name = "C2" if gpus == 1 else "C5"
+        name = "C5"
     if name in workloads.CONFIGS:
-        c = dict(workloads.CONFIGS[name])
-        if c.get("order", 0) != 0:
-            c["order_s"] = 0   # DG_0 saturation (reference default); DG-Q1 is not on the GPU yet
-        return name, c
-    order = 0
-    if name.lower().startswith("rt1:"):
-        order, name = 1, name[4:]
-    dims = [int(v) for v in name.lower().split("x")]
-    c = dict(dim=len(dims), nx=dims[0], ny=dims[1], K="lognormal", sigma=1.0, note="custom " + name)
+        return (name,) + workloads.bench_setup(name)
+    low = name.lower()
+    order, order_s = 0, 0
+    if low.startswith("rt1:"):
+        order, low = 1, low[4:]
+    elif low.startswith("q1:"):
+        order, order_s, low = 1, 1, low[3:]
+    dims = [int(v) for v in low.split("x")]
+    c = dict(dim=len(dims), nx=dims[0], ny=dims[1], K="lognormal", sigma=1.0)
     if len(dims) == 3:
         c["nz"] = dims[2]
     if order:
-        c.update(order=1, order_s=0)
-        name = "rt1:" + name
-    return name, c
+        c.update(order=1, order_s=order_s)
+    return (name,) + workloads.bench_setup(c)
 
 
 def spaces_of(cfg):
-    return "RT1/L2-Q1/DG_0" if cfg.get("order", 0) == 1 else "RT0/P0/P0"
+    if cfg.get("order", 0) == 1:
+        return "RT1/L2-Q1/DG-Q1" if cfg.get("order_s", 1) == 1 else "RT1/L2-Q1/DG_0"
+    return "RT0/P0/P0"
+
+
+def config_of(wname, cfg, dtg, dtl, prec, gpus):
+    """The `config` object: a pure function of the command line, identical in both arms."""
+    mesh = f"{cfg['nx']}x{cfg['ny']}" + (f"x{cfg['nz']}" if cfg["dim"] == 3 else "")
+    order = cfg.get("order", 0)
+    ncell = cfg["nx"] * cfg["ny"] * cfg.get("nz", 1)
+    big = ncell * (32 if order else 4) * 8 / gpus > 4 * 126e6
+    return {"workload": wname, "mesh": mesh, "spaces": spaces_of(cfg), "two_phase": True,
+            "K": cfg.get("K", "lognormal") + (f" sigma={cfg.get('sigma', 1.0)}" if "lognormal" in cfg.get("K", "lognormal") else ""),
+            "sat_source": cfg.get("saturation_source", 1.0), "dt_global": dtg, "dt_local": dtl,
+            "substeps_per_step": int(dtg / dtl), "schur_prec": prec, "minres_rtol": 1e-6, "minres_maxiter": 20000,
+            "partition": f"{gpus} z-slab(s)",
+            "l2_policy": "inputs larger than L2 (every Krylov vector of a slab >> 126 MB)" if big else
+                         "mesh smaller than L2 by construction of this BASELINE config; kernels' rooflines are taken on C5-size meshes"}
 
 
 class ClockSampler:
@@ -146,70 +163,144 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def oracle_step(orc, built, threads, steps, warmup):
-    """Time the CPU oracle on `steps` IMPES steps after `warmup` (each a full step of the workload)."""
+def traffic_table():
+    """dram bytes per cell and launch from committed ncu captures (tools/ncu_traffic.py writes the file)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+def all_threads(orc):
+    """Every host core: torchrun exports OMP_NUM_THREADS=1, so the count is set explicitly."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def oracle_steps(orc, built, dtg, dtl, threads, steps, warmup, keep=False):
+    """Time the CPU oracle on `steps` IMPES steps after `warmup`; keep=True returns the fields of the last step."""
     d, Kx, Ky, Kz, phi = built
-    DT_GLOBAL, DT_LOCAL = time_steps(d.dim)
     o = orc.Oracle(d, Kx, Ky, Kz, phi)
-    o.set_threads(threads)
-    n = o.n_cells
-    S = np.zeros(n)
-    its, times = [], []
+    o.set_arith(1)          # closed-form element matrices (the faster of the oracle's two assembled arithmetics)
+    o.set_threads(threads)  # > 1: OpenMP over assembly / SpMV / vector operations
+    S = np.zeros(o.ns)
+    its, times, x = [], [], None
     for ti in range(warmup + steps):
         t0 = time.perf_counter()
         x, st, rc = o.pressure_solve(S)
-        S, nsub = o.saturation_advance(x[:o.nv], S, DT_GLOBAL, DT_LOCAL)
+        S, nsub = o.saturation_advance(x[:o.nv], S, dtg, dtl)
         dt = time.perf_counter() - t0
         if ti >= warmup:
             its.append(int(st.iterations))
             times.append(dt)
+    n, nv = o.n_cells, o.nv
     o.close()
-    return n, its, times
+    return n, its, times, ((x, S, nv) if keep else None)
 
 
-def run_reference(args, wname, cfg):
+def sample_cfg(cfg, m):
+    """The bounded CPU sample of a workload: the same kind of mesh (spaces, field statistics, wells, sub-steps),
+    m cells per direction where the workload has more."""
+    s = dict(cfg)
+    for k in ("nx", "ny", "nz"):
+        if k in s:
+            s[k] = min(s[k], m)
+    return s
+
+
+def run_reference(args, wname, cfg, dtg, dtl):
     """Reference arm: the CPU restatement of the reference's algorithm on all host threads (rank 0 only)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     load_package()
-    from incompressible_flow_b200 import workloads
-    from incompressible_flow_b200 import abi
+    from incompressible_flow_b200 import abi, workloads
     orc = load_oracle()
-    scfg = dict(cfg)
-    sample = f"{args.steps} full IMPES steps of {wname} after {args.warmup} warm-up steps"
-    prec = "sgs_lex (serial reference)"
-    if args.gpus > 1:
-        # the multi-GPU arm runs the parallel reference's structure (AMG-type Schur preconditioner): same here
-        scfg["schur_prec"] = abi.SCHUR_MG
-        prec = "multigrid (stands where the MPI reference uses BoomerAMG)"
+    threads = all_threads(orc)
+    m = args.cpu_sample_ref
+    if m <= 0:
+        # ~750 cell-steps/s per core for the RT1 workloads (measured: 12.0e3 on 16 cores at 48^3, 12.4e3 at 32^3),
+        # ~10x that for RT0; 240 s for the whole run
+        rate = (750.0 if cfg.get("order", 0) else 7500.0) * threads
+        m = int((240.0 * rate / max(1, args.steps + args.warmup)) ** (1.0 / cfg["dim"]))
+        m = max(16, min(64 if cfg["dim"] == 3 else 1024, m // 8 * 8))
+    scfg = sample_cfg(cfg, m)
     ncell = cfg["nx"] * cfg["ny"] * cfg.get("nz", 1)
-    if ncell > 3e5 and cfg["dim"] == 3:
-        # bounded sample: the assembled-CSR restatement cannot hold the full mesh; cell-steps/s is size-normalised
-        m = 24 if cfg.get("order", 0) == 1 else 64
-        scfg.update(nx=m, ny=m, nz=m)
-        sample = (f"{args.steps} full IMPES steps of a {m}^3 mesh of the same kind (same spaces, field statistics, wells, "
-                  f"sub-step count) after {args.warmup} warm-up steps -- the {cfg['nx']}x{cfg['ny']}x{cfg['nz']} mesh of {wname} "
-                  "does not fit an assembled-CSR CPU run; cell-steps/s is normalised by the cell count")
-    built = workloads.build(**{k: v for k, v in scfg.items() if k != "note"})
-    threads = max(1, min(orc.lib().orc_max_threads(), os.cpu_count() or 1))
-    n, its, times = oracle_step(orc, built, threads, args.steps, args.warmup)
+    sn = scfg["nx"] * scfg["ny"] * scfg.get("nz", 1)
+    what = "the full mesh" if sn == ncell else (
+        f"a {scfg['nx']}x{scfg['ny']}" + (f"x{scfg['nz']}" if cfg["dim"] == 3 else "") +
+        " mesh of the same kind (same spaces, field statistics, wells, sub-step count); the full mesh does not fit an "
+        "assembled-CSR CPU run in minutes; cell-steps/s is normalised by the cell count")
+    built = workloads.build(**scfg, schur_prec=abi.SCHUR_MG if args.prec == "mg" else abi.SCHUR_SGS_LEX)
+    n, its, times, _ = oracle_steps(orc, built, dtg, dtl, threads, args.steps, args.warmup)
     tot = sum(times)
     value = n * args.steps / tot
-    line = {
+    emit({
         "impl": "reference", "metric": "IMPES cell-steps/s", "value": value, "unit": "cell-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname, **{k: v for k, v in cfg.items() if k != "note"}, "substeps_per_step": 100,
-                   "spaces": spaces_of(cfg), "schur_prec": prec, "minres_iters_per_step": its},
+        "config": config_of(wname, cfg, dtg, dtl, args.prec, args.gpus),
+        "iters_per_step": its,
         "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": threads, "kind": "port",
-                         "sample": sample + "; "
-                                   "CPU restatement of the reference algorithm (MFEM/HYPRE unavailable in this image), "
-                                   "OpenMP in SpMV/vector ops, Gauss-Seidel sequential"},
+                         "sample": f"{args.steps} full IMPES steps after {args.warmup} warm-up steps on {what}; CPU "
+                                   "restatement of the reference algorithm (assembly every step, CSR SpMV, MINRES; "
+                                   "MFEM/HYPRE unavailable in this image), OpenMP over all host cores"},
         "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    })
+
+
+# algorithmic bytes per launch (DESIGN.md section 4; fp64, every unique dof / coefficient once per pass)
+def kernel_bytes(name, dim, ncl, ndof):
+    d3 = dim == 3
+    per_cell = {
+        "k_darcy_apply": 88 if d3 else 64,
+        "k1_darcy_apply": 536 if d3 else 208,
+        "k1q_apply_a+b": 600 if d3 else 240,           # SURVEY 8d: (24+8)*2 + 8 + 3 doubles per 3-D cell
+        "k1_mg_jacobi(first)": 192 if d3 else 96,      # r, D, out per L2 dof
+        "k1_mg_jacobi": 448 if d3 else 208,            # r, y, D, out per dof + T per velocity node
+        "k1_mg_restrict": 392 if d3 else 176,
+        "k1_mg_prolong": 136 if d3 else 72,
+        "k_sat_stream": 48 if d3 else 40,
+        "k1q_sat": 328 if d3 else 136,                 # SURVEY 8d: 8 + 24 + 1 + 8 doubles per 3-D cell
+        "k_sgs": 100,
     }
-    emit(line)
+    per_dof = {"k_minres_b+c": 104, "k_dot_owned": 16, "k_jacobi_u": 24}
+    if name in per_cell:
+        return per_cell[name] * ncl
+    if name in per_dof:
+        return per_dof[name] * ndof
+    return None
+
+
+def rooflines_from_profile(kern, dim, ncl, ndof, peak, traffic):
+    """kern: {kernel: (ms, launches)} of one profiled step -> list of per-kernel records sorted by share of the step."""
+    tot = sum(ms for ms, _ in kern.values()) or 1.0
+    merged = {}
+    for name, (ms, n) in kern.items():
+        merged[name] = [ms, n]
+    # kernels that always run as a pair per application are reported as one unit of work
+    for a, b, joint in (("k1q_apply_a", "k1q_apply_b", "k1q_apply_a+b"), ("k_minres_b", "k_minres_c", "k_minres_b+c")):
+        if a in merged and b in merged:
+            na = min(merged[a][1], merged[b][1])
+            merged[joint] = [merged[a][0] + merged[b][0], na]
+            del merged[a], merged[b]
+    out = []
+    for name, (ms, n) in merged.items():
+        b = kernel_bytes(name, dim, ncl, ndof)
+        us = 1e3 * ms / max(n, 1)
+        rec = {"k": name, "share": rnd(ms / tot, 3), "n": n, "us": rnd(us, 4)}
+        if b:
+            rec.update(B=int(b), gbs=rnd(b / (us * 1e-6) / 1e9, 4), frac=rnd(b / (us * 1e-6) / 1e9 / peak, 3))
+            t = traffic.get(name)
+            rec["traffic"] = int(t["bytes_per_cell"] * ncl) if t else None
+        out.append(rec)
+    out.sort(key=lambda r: -r["share"])
+    return out
 
 
 def main():
@@ -219,17 +310,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
-    ap.add_argument("--roofline-size", default="384x384x384", help="streaming mesh for the K1/K6 roofline (>= 4x L2)")
+    ap.add_argument("--prec", default="mg", choices=["mg", "sgs"],
+                    help="mg: multigrid Schur preconditioner (structure of run_parallel); sgs: exact lexicographic "
+                         "Gauss-Seidel (run_serial, parity mode)")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="cells per direction of the cpu_baseline sample mesh")
+    ap.add_argument("--cpu-sample-ref", type=int, default=0,
+                    help="the same for --impl reference (0: the largest multiple of 8 up to 64 that keeps the whole "
+                         "--steps/--warmup run near four minutes on this host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-cpu-serial", action="store_true", help="skip the single-thread CPU sample")
-    ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--no-fast", action="store_true", help="skip the throughput-mode (multigrid) measurements")
-    ap.add_argument("--mode", default="auto", choices=["auto", "fast"],
-                    help="auto: N=1 parity mode (serial reference), N>1 multigrid (parallel reference); fast: multigrid")
+    ap.add_argument("--no-extras", action="store_true", help="skip C2/C3/C4 extra lines and isolated kernel timings")
     args = ap.parse_args()
-    wname, cfg = parse_workload(args.workload, args.gpus)
+    wname, cfg, dtg, dtl = parse_workload(args.workload)
     if args.impl == "reference":
-        return run_reference(args, wname, cfg)
+        return run_reference(args, wname, cfg, dtg, dtl)
     if args.warmup < 3:
         print(f"note: --warmup {args.warmup} < 3 violates the timing rules; use >= 3 for reportable numbers", file=sys.stderr)
 
@@ -248,21 +341,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    bcfg = {k: v for k, v in cfg.items() if k != "note"}
-    fast_headline = world > 1 or args.mode == "fast"
-    if fast_headline:
-        bcfg["schur_prec"] = abi.SCHUR_MG
-    d, Kx, Ky, Kz, phi = workloads.build(**bcfg)
-    d.rank, d.world_size, d.device = rank, world, local
-    order = int(d.order_v)
-    DT_GLOBAL, DT_LOCAL = time_steps(d.dim)
-    n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
-    s = pkg.Solver(d, Kx, Ky, Kz, phi)
-    if world > 1:
-        uid = [s.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        s.comm_init(uid[0])
+    prec = abi.SCHUR_MG if args.prec == "mg" else abi.SCHUR_SGS_LEX
 
     def barrier():
         if world > 1:
@@ -276,63 +355,60 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def make_solver(c, w=world, r=rank):
+        d, Kx, Ky, Kz, phi = workloads.build(**c, schur_prec=prec)
+        d.rank, d.world_size, d.device = r, w, local
+        s = pkg.Solver(d, Kx, Ky, Kz, phi)
+        if w > 1:
+            uid = [s.unique_id() if r == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            s.comm_init(uid[0])
+        return s, d
+
+    def run_steps(s, steps, warm, tg, tl, ti0=0):
+        """-> (ms for `steps` steps on the device, iterations per step); state stays resident in HBM"""
+        its = []
+        for ti in range(warm):
+            s.pressure_solve(None, want_x=False)
+            s.saturation_advance(None, None, ti0 + ti + 1, tg, tl)
+        s.event_record(0)
+        for ti in range(steps):
+            _, st = s.pressure_solve(None, want_x=False)
+            s.saturation_advance(None, None, ti0 + warm + ti + 1, tg, tl)
+            its.append(int(st.iterations))
+        s.event_record(1)
+        return s.event_elapsed_ms(0, 1), its
+
     # ---------------- value: state resident in HBM --------------------------------------------------
-    s.set_field(abi.FIELD_SATURATION, np.zeros(n))
-    its = []
-
-    def step(ti):
-        _, st = s.pressure_solve(None, want_x=False)
-        s.saturation_advance(None, None, ti, DT_GLOBAL, DT_LOCAL)
-        return int(st.iterations)
-
+    s, d = make_solver(cfg)
+    n = d.nx * d.ny * (d.nz if d.dim == 3 else 1)
+    ld = s.local_dims()
+    s.set_field_local(abi.FIELD_SATURATION, np.zeros(ld.n_s))
     for ti in range(args.warmup):
-        step(ti + 1)
+        s.pressure_solve(None, want_x=False)
+        s.saturation_advance(None, None, ti + 1, dtg, dtl)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     l0 = s.launch_count()
-    s.event_record(0)
-    for ti in range(args.steps):
-        its.append(step(args.warmup + ti + 1))
-    s.event_record(1)
-    ms = s.event_elapsed_ms(0, 1)
+    ms, its = run_steps(s, args.steps, 0, dtg, dtl, ti0=args.warmup)
     barrier()
     launches = s.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     value = n * args.steps / (ms * 1e-3)
+    bad, smax = s.guards()
 
-    # ---------------- e2e: host buffers through the drop-in C ABI ----------------------------------
-    S_host = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
-    x_host = torch.empty(s.nv + s.np_, dtype=torch.float64).pin_memory().numpy()
-    S_host[:] = s.get_field(abi.FIELD_SATURATION)
-    lo, hi = s.dims.slab_lo, s.dims.slab_hi
-    nslab = d.nz if d.dim == 3 else d.ny
-    plane = n // nslab
-
-    def gather(a, owned):
-        """All ranks end up with the full host array (the reference's V.Distribute / rank-wide copies
-        [REF src/run_parallel.cpp:186]): zero what this rank does not own, sum over ranks."""
-        if world == 1:
-            return
-        m = np.zeros(a.shape[0], dtype=bool)
-        for a0, a1 in owned:
-            m[a0:a1] = True
-        a[~m] = 0.0
-        t = torch.from_numpy(a).cuda()
-        dist.all_reduce(t)
-        a[:] = t.cpu().numpy()
-
-    own_x, own_s = pkg.partition.owned_ranges(d.dim, d.nx, d.ny, d.nz, rank, world, order=order, slab=(lo, hi))
-    gather(S_host, own_s)
+    # ---------------- e2e: slab-local HOST buffers through the drop-in C ABI ------------------------
+    S_host = torch.empty(ld.n_s, dtype=torch.float64).pin_memory().numpy()
+    x_host = torch.empty(ld.n_v + ld.n_p, dtype=torch.float64).pin_memory().numpy()
+    S_host[:] = s.get_field_local(abi.FIELD_SATURATION)
     e2e_steps = 1 if n > 4e6 else max(1, min(args.steps, 2))
 
     def e2e_step(ti):
-        s.pressure_solve(S_host, out=x_host)
-        gather(x_host, own_x)
-        s.saturation_advance(x_host[:s.nv], S_host, ti, DT_GLOBAL, DT_LOCAL, inplace=True)
-        gather(S_host, own_s)
+        s.pressure_solve_local(S_host, out=x_host)                      # H2D S; D2H x = [V | P]
+        s.saturation_advance_local(x_host[:ld.n_v], S_host, ti, dtg, dtl)  # H2D V, S; D2H S
 
     e2e_step(100)  # warm the pinned path
     barrier()
@@ -341,186 +417,104 @@ def main():
         e2e_step(101 + ti)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    if True:
-        e2e = {"value": n * e2e_steps / e2e_s, "unit": "cell-steps/s",
-               "h2d_bytes_per_step": int(8 * (n + s.nv + n)), "d2h_bytes_per_step": int(8 * (s.nv + s.np_ + n)),
-               "steps": e2e_steps, "timing": "host wall clock around synchronous C-ABI calls"}
+    h2d = max_over_ranks(float(8 * (ld.n_s + ld.n_v + ld.n_s)))
+    d2h = max_over_ranks(float(8 * (ld.n_v + ld.n_p + ld.n_s)))
+    e2e = {"value": n * e2e_steps / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "bytes": "per rank (max over ranks)"}
 
-    # ---------------- step breakdown on the benchmark mesh (profiled, untimed) ---------------------
-    breakdown = None
-    roofline_dominant = None
-    if world == 1:
-        s.profile_enable(True)
-        step(200)
-        pms, pn = s.profile_read()
-        s.profile_enable(False)
-        tot = sum(pms) or 1.0
-        breakdown = {NAMES[i]: {"ms": round(pms[i], 3), "launches": int(pn[i]), "share": round(pms[i] / tot, 4)}
-                     for i in range(8) if pn[i]}
-        try:
-            # the dominant kernel class of this step, against the same HBM roofline: in parity mode it is the exact
-            # lexicographic Gauss-Seidel sweep, a dependent chain -- bytes are not what bounds it
-            dom = max(breakdown, key=lambda k: breakdown[k]["ms"])
-            if dom == "schur_prec" and not fast_headline:
-                n_apply = breakdown["dot"]["launches"]            # one preconditioner application per dot <v, Pv>
-                us = 1e3 * breakdown[dom]["ms"] / max(n_apply, 1)
-                k3_b = 100 * n                                     # ~100 B/cell per application (both sweeps)
-                pk, _src = hbm_peak()
-                roofline_dominant = {
-                    "kernel": "k_sgs_tma + skew in/out (K3: one symmetric Gauss-Seidel application, both sweeps)",
-                    "share_of_step": breakdown[dom]["share"], "bound": "hbm",
-                    "achieved": k3_b / (us * 1e-6) / 1e9, "peak": pk, "unit": "GB/s",
-                    "frac": k3_b / (us * 1e-6) / 1e9 / pk, "traffic": None,
-                    "bytes_per_launch": k3_b, "us_per_launch": us,
-                    "note": "latency bound, not bandwidth bound: a chain of 2(NX+NY-2) dependent wavefront stages per "
-                            "application (~270 ns each); the HBM roofline is reported for completeness only"}
-        except Exception:
-            roofline_dominant = None
-    s.close()
-
-    # ---------------- roofline: K1 / K6 alone on a streaming-size mesh -----------------------------
-    roofline = roofline_k6 = roofline_k2 = roofline_rt1 = None
+    # ---------------- per-kernel profile of one step on the benchmark mesh (untimed) -----------------
     peak, peak_src = hbm_peak()
-    if rank == 0 and not args.no_roofline:
-        _, rcfg = parse_workload(args.roofline_size, 1)
-        rd, rKx, rKy, rKz, rphi = workloads.build(**rcfg)
-        rd.device = local
-        rn = rd.nx * rd.ny * (rd.nz if rd.dim == 3 else 1)
-        with pkg.Solver(rd, rKx, rKy, rKz, rphi) as rs:
-            rs.set_field(abi.FIELD_SATURATION, np.full(rn, 0.3))
-            rs.set_field(abi.FIELD_DARCY_X, np.random.default_rng(0).standard_normal(rs.nv + rs.np_))
-            k1_b = (88 if rd.dim == 3 else 64) * rn     # unique fp64 words per cell x 8 B
-            k6_b = (48 if rd.dim == 3 else 40) * rn
-            a1, m1 = rs.time_kernel(abi.KERNEL_DARCY_APPLY, 20, True)
-            a6, m6 = rs.time_kernel(abi.KERNEL_SAT_SUBSTEP, 20, True)
-            a2, m2 = rs.time_kernel(abi.KERNEL_MINRES_UPDATE, 10, True)
-            k2_b = 13 * 8 * (rs.nv + rs.np_)
-        roofline = {"kernel": "k_darcy_apply<DOT> (K1, Krylov matvec + fused <u,Au>)", "bound": "hbm",
-                    "achieved": k1_b / (a1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": k1_b / (a1 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                    "mesh": args.roofline_size, "bytes_per_launch": k1_b, "us_per_launch": a1 * 1e3,
-                    "l2": "flushed before every timed launch"}
-        # traffic: dram__bytes_read+write per launch from the committed ncu captures (profiles/), scaled by cells
-        roofline["traffic"] = int(1455e6 / 16777216 * rn)
-        roofline_k6 = {"kernel": "k_sat_stream (K6, fused upwind flux + fractional flow + update; f(S) carried)", "bound": "hbm",
-                       "achieved": k6_b / (a6 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                       "frac": k6_b / (a6 * 1e-3) / 1e9 / peak, "traffic": int(1056e6 / 16777216 * rn), "mesh": args.roofline_size,
-                       "bytes_per_launch": k6_b, "us_per_launch": a6 * 1e3,
-                       "note": "streaming form moves 64 B/cell (carried f(S) array) for 48 B algorithmic: actual DRAM "
-                               "throughput is 4/3 of `achieved`"}
-        roofline_k2 = {"kernel": "k_minres_b + k_minres_c (K2, fused MINRES vector passes)", "bound": "hbm",
-                       "achieved": k2_b / (a2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                       "frac": k2_b / (a2 * 1e-3) / 1e9 / peak, "traffic": None, "mesh": args.roofline_size,
-                       "bytes_per_launch": k2_b, "us_per_launch": a2 * 1e3}
+    s.profile_enable(True)
+    s.pressure_solve(None, want_x=False)
+    s.saturation_advance(None, None, 200, dtg, dtl)
+    kern = s.profile_read_kernels()
+    s.profile_enable(False)
+    ncl = (ld.n_s // (2 ** d.dim)) if d.order_s == 1 else ld.n_s
+    rl = rooflines_from_profile(kern, d.dim, ncl, ld.n_v + ld.n_p, peak, traffic_table())
+    iso = None
+    if rank == 0 and not args.no_extras:
+        # cross-check: the same kernels alone, L2 flushed before every launch
+        iso = {}
+        for kid, nm in ((abi.KERNEL_DARCY_APPLY, "K1"), (abi.KERNEL_MINRES_UPDATE, "K2"), (abi.KERNEL_SAT_SUBSTEP, "K6")):
+            a, m = s.time_kernel(kid, 5, True)
+            iso[nm] = rnd(a * 1e3, 4)
+    s.close()
+    roofline = None
+    for r in rl:
+        if r.get("B"):
+            t = traffic_table().get(r["k"])
+            roofline = {"kernel": r["k"], "bound": "hbm", "achieved": r["gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": r["frac"], "traffic": r.get("traffic"), "share_of_step": r["share"],
+                        "bytes_per_launch": r["B"], "us_per_launch": r["us"], "peak_source": peak_src,
+                        "traffic_source": (t or {}).get("source"),
+                        "how": "profiled step on the benchmark mesh: CUDA events around every launch on the library's "
+                               "stream, average over the launches of that step"}
+            break
 
-        # K1 of the RT1/L2-Q1 path on a streaming mesh (67 fp64 words per 3-D cell)
-        r1d, r1Kx, r1Ky, r1Kz, r1phi = workloads.build(dim=3, nx=192, ny=192, nz=192, K="lognormal", order=1, order_s=0)
-        r1d.device = local
-        r1n = 192 ** 3
-        with pkg.Solver(r1d, r1Kx, r1Ky, r1Kz, r1phi) as rs:
-            rs.set_field(abi.FIELD_SATURATION, np.full(r1n, 0.3))
-            a11, m11 = rs.time_kernel(abi.KERNEL_DARCY_APPLY, 10, True)
-            a12, m12 = rs.time_kernel(abi.KERNEL_MINRES_UPDATE, 5, True)
-            k11_b = 67 * 8 * r1n
-            k12_b = 13 * 8 * (rs.nv + rs.np_)
-        roofline_rt1 = {"kernel": "k1_darcy_apply<HY,DOT> (K1 of the RT1/L2-Q1 path + fused <u,Au>)", "bound": "hbm",
-                        "achieved": k11_b / (a11 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": k11_b / (a11 * 1e-3) / 1e9 / peak, "traffic": int(1094e6 / 2097152 * r1n), "mesh": "rt1:192x192x192",
-                        "bytes_per_launch": k11_b, "us_per_launch": a11 * 1e3,
-                        "k2_on_this_mesh": {"achieved": k12_b / (a12 * 1e-3) / 1e9, "frac": k12_b / (a12 * 1e-3) / 1e9 / peak,
-                                            "us_per_launch": a12 * 1e3}}
+    # ---------------- extras: the other BASELINE configs, one line each (rank 0, single GPU) ----------
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = {}
+        for name in ("C1", "C2", "C3", "C4"):
+            if name == wname:
+                continue
+            _, c2, tg, tl = parse_workload(name)
+            es, ed = make_solver(c2, 1, 0)
+            en = ed.nx * ed.ny * (ed.nz if ed.dim == 3 else 1)
+            es.set_field(abi.FIELD_SATURATION, np.zeros(es.ns))
+            ems, eits = run_steps(es, 2, 1, tg, tl)
+            es.close()
+            extras[name] = {"value": rnd(en * 2 / (ems * 1e-3)), "ms_per_step": rnd(ems / 2), "iters": eits}
 
-    # ---------------- throughput mode (multigrid Schur preconditioner), same workload + 256^3 -------
-    fast = None
-    if rank == 0 and world == 1 and not args.no_fast and not fast_headline:
-        def fast_run(fcfg, steps, warm):
-            fd, fKx, fKy, fKz, fphi = workloads.build(**{k: v for k, v in fcfg.items() if k != "note"}, schur_prec=abi.SCHUR_MG)
-            fd.device = local
-            fn = fd.nx * fd.ny * (fd.nz if fd.dim == 3 else 1)
-            DT_GLOBAL, DT_LOCAL = time_steps(fd.dim)
-            with pkg.Solver(fd, fKx, fKy, fKz, fphi) as fs:
-                fs.set_field(abi.FIELD_SATURATION, np.zeros(fn))
-                fits = []
-                for ti in range(warm):
-                    fs.pressure_solve(None, want_x=False)
-                    fs.saturation_advance(None, None, ti + 1, DT_GLOBAL, DT_LOCAL)
-                fs.event_record(0)
-                for ti in range(steps):
-                    _, fst = fs.pressure_solve(None, want_x=False)
-                    fs.saturation_advance(None, None, warm + ti + 1, DT_GLOBAL, DT_LOCAL)
-                    fits.append(int(fst.iterations))
-                fs.event_record(1)
-                fms = fs.event_elapsed_ms(0, 1)
-            return {"value": fn * steps / (fms * 1e-3), "unit": "cell-steps/s", "ms_per_step": fms / steps,
-                    "minres_iters_per_step": fits, "steps": steps, "warmup": warm}
-        fast = {"schur_prec": "multigrid V(2,2), damped Jacobi, aggregation coarsening (IMPES_SCHUR_MG); bit-exact against "
-                              "the oracle's restatement of the same preconditioner; same discrete solution as the reference "
-                              "algorithm to solver tolerance, different iteration counts",
-                wname: fast_run(cfg, args.steps, args.warmup)}
-        big = dict(dim=3, nx=256, ny=256, nz=256, K="lognormal", sigma=1.0)
-        fast["256x256x256 RT0/P0 (north_star mesh, lowest order), 1 GPU"] = fast_run(big, 2, 1)
-        big1 = dict(big, order=1, order_s=0)
-        fast["C5: 256x256x256 RT1/L2-Q1/DG_0 (north_star mesh; the N>1 bench workload), 1 GPU"] = fast_run(big1, 2, 1)
-
-    # ---------------- N > 1: the same workload on ONE GPU (rank 0), the strong-scaling reference point ---------
-    one_gpu = None
-    if rank == 0 and world > 1 and not args.no_fast:
-        od, oKx, oKy, oKz, ophi = workloads.build(**bcfg)
-        od.device = local
-        with pkg.Solver(od, oKx, oKy, oKz, ophi) as osv:
-            osv.set_field(abi.FIELD_SATURATION, np.zeros(osv.ns))
-            oits = []
-            osv.pressure_solve(None, want_x=False)
-            osv.saturation_advance(None, None, 1, DT_GLOBAL, DT_LOCAL)
-            osv.event_record(0)
-            for ti in range(2):
-                _, ost = osv.pressure_solve(None, want_x=False)
-                osv.saturation_advance(None, None, ti + 2, DT_GLOBAL, DT_LOCAL)
-                oits.append(int(ost.iterations))
-            osv.event_record(1)
-            oms = osv.event_elapsed_ms(0, 1) / 2
-        one_gpu = {"ms_per_step": oms, "value": n / (oms * 1e-3), "unit": "cell-steps/s", "minres_iters_per_step": oits,
-                   "steps": 2, "warmup": 1, "note": "same workload, same code path, world_size = 1, measured by rank 0 "
-                   "after the multi-GPU run while the other ranks idle"}
-
-    # ---------------- CPU baseline beside it -------------------------------------------------------
-    cpu = None
+    # ---------------- CPU baseline beside it + same-mesh GPU run + parity ----------------------------
+    cpu = same = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         orc = load_oracle()
-        threads = max(1, min(orc.lib().orc_max_threads(), os.cpu_count() or 1))
-        built = workloads.build(**bcfg)
-        cn, cits, ctimes = oracle_step(orc, built, threads, 1, 0)
-        cpu = {"value": cn / ctimes[0], "unit": "cell-steps/s", "cores": threads, "kind": "port",
-               "sample": f"1 full IMPES step (step 1, S=0) of {wname}: {cits[0]} MINRES iterations + 100 sub-steps, "
-                         f"{ctimes[0]:.1f} s; CPU restatement of the reference algorithm (MFEM/HYPRE unavailable)"}
-        if not args.no_cpu_serial:
-            # (i) one thread = stand-in for run_serial, (ii) all cores = stand-in for the MPI run
-            _, cits1, ctimes1 = oracle_step(orc, built, 1, 1, 0)
-            cpu["single_thread"] = {"value": cn / ctimes1[0], "unit": "cell-steps/s", "cores": 1,
-                                    "sample": f"the same step on one thread: {cits1[0]} iterations, {ctimes1[0]:.1f} s"}
+        threads = all_threads(orc)
+        scfg = sample_cfg(cfg, args.cpu_sample)
+        built = workloads.build(**scfg, schur_prec=prec)
+        cn, cits, ctimes, (xo, So, nvo) = oracle_steps(orc, built, dtg, dtl, threads, 1, 0, keep=True)
+        mesh = f"{scfg['nx']}x{scfg['ny']}" + (f"x{scfg['nz']}" if scfg["dim"] == 3 else "")
+        cpu = {"value": rnd(cn / ctimes[0]), "unit": "cell-steps/s", "cores": threads, "kind": "port",
+               "sample": f"1 IMPES step (S = 0) of a {mesh} mesh of the workload's kind: {cits[0]} MINRES its + "
+                         f"{int(dtg / dtl)} sub-steps, {ctimes[0]:.1f} s; CPU restatement of the reference algorithm "
+                         "(assembled CSR; MFEM/HYPRE unavailable), OpenMP, all cores"}
+        gs, gd = make_solver(scfg, 1, 0)
+        xg, stg = gs.pressure_solve(np.zeros(gs.ns))
+        Sg, _ = gs.saturation_advance(None, np.zeros(gs.ns), 1, dtg, dtl)
+        gms, gits = run_steps(gs, 3, 1, dtg, dtl, ti0=1)
+        gs.close()
+        same = {"mesh": mesh, "value": rnd(cn * 3 / (gms * 1e-3)), "ms_per_step": rnd(gms / 3), "iters": gits}
+        pm = lambda a: a - a.mean()
+        parity = {"mesh": mesh, "iters_gpu": int(stg.iterations), "iters_cpu": cits[0],
+                  "rel_u": rnd(np.linalg.norm(xg[:nvo] - xo[:nvo]) / np.linalg.norm(xo[:nvo]), 3),
+                  "rel_p": rnd(np.linalg.norm(pm(xg[nvo:]) - pm(xo[nvo:])) / np.linalg.norm(pm(xo[nvo:])), 3),
+                  "rel_S": rnd(np.linalg.norm(Sg - So) / np.linalg.norm(So), 3),
+                  "what": "GPU matrix-free vs CPU assembled-CSR oracle, one IMPES step, rtol 1e-6"}
 
     if rank == 0:
+        if roofline:
+            for k in ("how", "peak_source", "traffic_source"):
+                full_note = roofline.pop(k, None)
+        # key order: the driver keeps the END of stdout, so the roofline records come last
         line = {
             "metric": "IMPES cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wname, **{k: v for k, v in cfg.items() if k not in ("note", "schur_prec")},
-                       "spaces": spaces_of(cfg), "two_phase": True, "substeps_per_step": 100,
-                       "dt_global": DT_GLOBAL, "dt_local": DT_LOCAL,
-                       "schur_prec": ("multigrid V(2,2) (throughput mode; stands where the MPI reference uses BoomerAMG; "
-                                      "result independent of the GPU count)") if fast_headline else
-                                     "sgs_lex (parity mode: exact lexicographic symmetric Gauss-Seidel)",
-                       "minres_rtol": d.darcy_rtol, "minres_iters_per_step": its,
-                       "partition": f"{world} slab(s) along the slowest axis",
-                       "l2_policy": ("inputs larger than L2: every Krylov vector of this mesh is >> 126 MB per GPU"
-                                     if n * (32 if order else 4) * 8 / world > 4 * 126e6 else
-                                     "step working set < L2 by construction of the BASELINE mesh; every step streams fresh "
-                                     "Krylov vectors") + "; the roofline kernels run on a >=4xL2 mesh with L2 flushed"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "roofline_k6": roofline_k6, "roofline_k2": roofline_k2, "roofline_k1_rt1": roofline_rt1,
-            "roofline_dominant_kernel": roofline_dominant,
-            "step_breakdown": breakdown, "fast_mode": fast, "same_workload_1gpu": one_gpu, "cpu_baseline": cpu,
+            "config": config_of(wname, cfg, dtg, dtl, args.prec, world),
+            "iters_per_step": its, "steps_per_s": rnd(1e3 * args.steps / ms), "s_max": rnd(smax), "nonfinite": int(bad),
+            "gpu_launches": int(launches), "extras": extras, "same_mesh": same, "parity": parity,
+            "isolated_us_l2_flushed": iso, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
+            "rooflines": [[r["k"], r["share"], r["us"], r.get("frac")] for r in rl[:9]],
+            "rooflines_cols": "kernel, share of the profiled step, us per launch, algorithmic-bytes / time / HBM peak",
+            "roofline": roofline,
         }
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"bench_full_n{world}.json"), "w") as f:
+                json.dump({**line, "rooflines_full": rl, "kernels_ms": kern}, f, indent=1)
+        except Exception:
+            pass
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -130,7 +130,7 @@ typedef struct impes_desc {
   int32_t rank;              /* this process' slab index, 0 .. world_size-1    */
   int32_t world_size;        /* number of slabs / GPUs (1 = single GPU)        */
   int32_t device;            /* CUDA device ordinal to use                     */
-  int32_t mg_smooth;         /* MG: pre-/post-smoothing sweeps (0 -> default 1)*/
+  int32_t mg_smooth;         /* MG: pre-/post-smoothing sweeps, rounded up to even (0 -> default 2) */
 } impes_desc;
 
 /* What the reference prints after a solve
@@ -199,6 +199,34 @@ int  impes_saturation_advance(impes_handle h, const double* V_host, double* S_in
                               int global_ti, double global_dt, double dt_local,
                               int* n_substeps_out);
 
+/* --- slab-local variants (one process per GPU, world_size > 1) --------------
+ * The MPI reference keeps only local dofs on a rank (ParGridFunction / true-dof
+ * vectors [REF src/run_parallel.cpp:97-104,118-125]) and moves shared dofs only
+ * (V.Distribute [REF src/run_parallel.cpp:186]).  These entry points are the
+ * same two solver calls with LOCAL host arrays: the native layout restricted to
+ * what the rank owns -- its cell layers [slab_lo, slab_hi) of every cell-based
+ * array and of the x / y velocity grids, and the slab-axis node/face layers it
+ * owns (a cell owns its lower faces; the last rank also owns the top boundary
+ * layer).  x_local = [ux_loc | uy_loc | uz_loc | p_loc].  Ghost layers never
+ * cross the host boundary: the library exchanges them between GPUs (NCCL).
+ * With world_size == 1 local == global. */
+typedef struct impes_local_dims {
+  int64_t n_v, n_p, n_s;       /* local dof counts                                      */
+  int64_t n_v_comp[3];         /* local size of each velocity component grid            */
+  int64_t v_comp_start[3];     /* first global index of the local part inside its global component grid */
+  int64_t p_start, s_start;    /* first global pressure / saturation dof of the local part */
+} impes_local_dims;
+int  impes_get_local_dims(impes_handle h, impes_local_dims* out);
+/* ParPressureSolver [REF src/par_pressure_solver.cpp:8-136] with local arrays (x_local plays trueX). */
+int  impes_pressure_solve_local(impes_handle h, const double* S_local, double* x_local,
+                                impes_solve_stats* stats);
+/* ParSaturationSolver [REF src/par_saturation_solver.cpp:64-177] with local arrays. */
+int  impes_saturation_advance_local(impes_handle h, const double* V_local, double* S_local_inout,
+                                    int global_ti, double global_dt, double dt_local,
+                                    int* n_substeps_out);
+int  impes_set_field_local(impes_handle h, int which, const double* host_local);
+int  impes_get_field_local(impes_handle h, int which, double* host_local);
+
 /* Guards of the global loop [REF src/run_serial.cpp:132-142]
  * [REF src/run_parallel.cpp:220-230]: number of non-finite S dofs, max S
  * (all-reduced over ranks). */
@@ -239,6 +267,9 @@ int64_t impes_launch_count(impes_handle h);
  * profiling is on (impes_profile_enable(h,1)); used for the step breakdown. */
 int  impes_profile_enable(impes_handle h, int on);
 int  impes_profile_read(impes_handle h, double* ms_by_kernel /* [8] */, int64_t* launches_by_kernel /* [8] */);
+/* The same per kernel: fills up to `cap` entries (static name strings, milliseconds, launches) and returns the
+ * number of kernel ids the library distinguishes. */
+int  impes_profile_read_kernels(impes_handle h, int cap, const char** names, double* ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

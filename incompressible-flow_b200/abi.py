@@ -68,6 +68,14 @@ class Dims(C.Structure):
     ]
 
 
+class LocalDims(C.Structure):
+    _fields_ = [
+        ("n_v", C.c_int64), ("n_p", C.c_int64), ("n_s", C.c_int64),
+        ("n_v_comp", C.c_int64 * 3), ("v_comp_start", C.c_int64 * 3),
+        ("p_start", C.c_int64), ("s_start", C.c_int64),
+    ]
+
+
 def default_desc() -> Desc:
     """Reference defaults [REF src/param.cpp:8-13,35-68]; MU_W = MU_O = 1 [REF config.hpp.in:37,43]."""
     d = Desc()

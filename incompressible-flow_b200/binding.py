@@ -21,7 +21,10 @@ EXPORTS = [
     "impes_get_dims", "impes_comm_unique_id", "impes_comm_init", "impes_pressure_solve",
     "impes_saturation_advance", "impes_guards", "impes_set_field", "impes_get_field",
     "impes_update_coefficients", "impes_darcy_apply", "impes_prec_apply", "impes_get_rhs",
+    "impes_get_local_dims", "impes_pressure_solve_local", "impes_saturation_advance_local",
+    "impes_set_field_local", "impes_get_field_local",
     "impes_time_kernel", "impes_event_record", "impes_event_elapsed_ms", "impes_launch_count", "impes_profile_enable", "impes_profile_read",
+    "impes_profile_read_kernels",
 ]
 
 
@@ -67,6 +70,11 @@ def load_library():
     L.impes_pressure_solve.argtypes = [H, _dp, _dp, C.POINTER(abi.SolveStats)]
     L.impes_saturation_advance.argtypes = [H, _dp, _dp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int)]
     L.impes_guards.argtypes = [H, C.POINTER(C.c_int64), _dp]
+    L.impes_get_local_dims.argtypes = [H, C.POINTER(abi.LocalDims)]
+    L.impes_pressure_solve_local.argtypes = [H, _dp, _dp, C.POINTER(abi.SolveStats)]
+    L.impes_saturation_advance_local.argtypes = [H, _dp, _dp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int)]
+    L.impes_set_field_local.argtypes = [H, C.c_int, _dp]
+    L.impes_get_field_local.argtypes = [H, C.c_int, _dp]
     L.impes_set_field.argtypes = [H, C.c_int, _dp]
     L.impes_get_field.argtypes = [H, C.c_int, _dp]
     L.impes_update_coefficients.argtypes = [H]
@@ -80,6 +88,7 @@ def load_library():
     L.impes_launch_count.argtypes = [H]
     L.impes_profile_enable.argtypes = [H, C.c_int]
     L.impes_profile_read.argtypes = [H, _dp, C.POINTER(C.c_int64)]
+    L.impes_profile_read_kernels.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_int64)]
     if L.impes_abi_version() != 1:
         raise RuntimeError("impes ABI version mismatch")
     _LIB = L
@@ -166,6 +175,37 @@ class Solver:
                                                   float(dt_local), C.byref(n)))
         return S, n.value
 
+    # --- slab-local variants (each rank passes only what it owns; world_size == 1: local == global)
+    def local_dims(self):
+        d = abi.LocalDims()
+        self._chk(self.L.impes_get_local_dims(self.h, C.byref(d)))
+        return d
+
+    def pressure_solve_local(self, S_local=None, out=None, allow_not_converged=False):
+        """out: local [V | P] array (n_v + n_p of local_dims) or None to keep the result on the device"""
+        st = abi.SolveStats()
+        allow = (abi.IMPES_ERR_NOT_CONVERGED,) if allow_not_converged else ()
+        self._chk(self.L.impes_pressure_solve_local(self.h, _p(_f64(S_local)), _p(out), C.byref(st)), allow)
+        return out, st
+
+    def saturation_advance_local(self, V_local=None, S_local=None, global_ti=1, global_dt=100.0, dt_local=1.0):
+        """S_local is updated in place"""
+        n = C.c_int(0)
+        self._chk(self.L.impes_saturation_advance_local(self.h, _p(_f64(V_local)), _p(S_local), int(global_ti),
+                                                        float(global_dt), float(dt_local), C.byref(n)))
+        return S_local, n.value
+
+    def set_field_local(self, which, a):
+        self._chk(self.L.impes_set_field_local(self.h, which, _p(_f64(a))))
+
+    def get_field_local(self, which):
+        d = self.local_dims()
+        n = {abi.FIELD_SATURATION: d.n_s, abi.FIELD_VELOCITY: d.n_v, abi.FIELD_PRESSURE: d.n_p,
+             abi.FIELD_DARCY_X: d.n_v + d.n_p}[which]
+        a = np.zeros(n)
+        self._chk(self.L.impes_get_field_local(self.h, which, _p(a)))
+        return a
+
     def guards(self):
         bad = C.c_int64(0)
         mx = C.c_double(0)
@@ -232,3 +272,12 @@ class Solver:
         n = (C.c_int64 * 8)()
         self._chk(self.L.impes_profile_read(self.h, ms, n))
         return list(ms), list(n)
+
+    def profile_read_kernels(self):
+        """-> {kernel name: (ms, launches)} since profile_enable (only kernels that launched)"""
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        n = (C.c_int64 * cap)()
+        k = self.L.impes_profile_read_kernels(self.h, cap, names, ms, n)
+        return {names[i].decode(): (ms[i], int(n[i])) for i in range(min(k, cap)) if n[i]}

@@ -35,6 +35,20 @@ std::string g_create_error;
 
 enum { KC_DARCY = 0, KC_MINRES = 1, KC_PREC = 2, KC_SAT = 3, KC_COEFF = 4, KC_DOT = 5, KC_MISC = 6, KC_COMM = 7, KC_N = 8 };
 
+// kernel-level accounting (impes_profile_read_kernels): one id per kernel (or family of tiny kernels)
+enum {
+  KI_DARCY_RT0 = 0, KI_DARCY_RT1, KI_DARCY_Q1A, KI_DARCY_Q1B, KI_MINRES_B, KI_MINRES_C, KI_MINRES_INIT, KI_DOT,
+  KI_JACOBI_U, KI_SGS, KI_MGQ_FIRST, KI_MGQ_JACOBI, KI_MGQ_RESTRICT, KI_MGQ_PROLONG, KI_MG_CELL, KI_SAT_P0,
+  KI_SAT_Q1, KI_SAT_AUX, KI_COEFF, KI_MISC, KI_COMM, KI_N
+};
+const char* const KI_NAME[KI_N] = {
+  "k_darcy_apply", "k1_darcy_apply", "k1q_apply_a", "k1q_apply_b", "k_minres_b", "k_minres_c", "k_minres_init",
+  "k_dot_owned", "k_jacobi_u", "k_sgs", "k1_mg_jacobi(first)", "k1_mg_jacobi", "k1_mg_restrict", "k1_mg_prolong",
+  "k_mg_cell_levels", "k_sat_stream", "k1q_sat", "sat_aux", "coeff", "misc", "nccl"};
+const int KI_CLASS[KI_N] = {KC_DARCY, KC_DARCY, KC_DARCY, KC_DARCY, KC_MINRES, KC_MINRES, KC_MINRES, KC_DOT,
+                            KC_PREC, KC_PREC, KC_PREC, KC_PREC, KC_PREC, KC_PREC, KC_PREC, KC_SAT,
+                            KC_SAT, KC_SAT, KC_COEFF, KC_MISC, KC_COMM};
+
 }  // namespace
 
 struct impes_ctx {
@@ -51,6 +65,7 @@ struct impes_ctx {
   QTab qt;
   double* rlam = nullptr;       // os == 1: w_q / lambda(S(x_q)) at the mass-rule points, ncv x NQP
   double* yup = nullptr;        // os == 1: upper-face-node element contributions of K1 pass A, ncv x NUP
+  double* accA = nullptr;       // os == 1: per-cell share of <x, Ax> from K1 pass A (reduced by pass B)
   int nqp = 0, nup = 0;
   Phys ph;
   SatParam sp;
@@ -106,6 +121,7 @@ struct impes_ctx {
   int mg_nu = 2, mg_coarse_sweeps = 16;
   long long graph_launches = 0;
   long long graph_prof_n[KC_N] = {0};
+  long long graph_ki_n[KI_N] = {0};
   // multi-GPU
   NcclShim nccl;
   ncclComm_t comm = nullptr;
@@ -114,6 +130,8 @@ struct impes_ctx {
   bool profiling = false;
   double prof_ms[KC_N] = {0};
   long long prof_n[KC_N] = {0};
+  double ki_ms[KI_N] = {0};
+  long long ki_n[KI_N] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
@@ -151,14 +169,17 @@ namespace {
 
 long pad32(long n) { return (n + 31) / 32 * 32; }
 
-// Launch accounting (+ optional per-class device timing when profiling is on).
+// Launch accounting (+ optional per-kernel device timing when profiling is on: every scope is then bracketed by
+// an event pair and synchronised, so the profiled step is slower than a timed one but its per-kernel durations
+// are those of back-to-back launches on warm data).
 struct Scope {
   impes_ctx* h;
-  int cls;
+  int ki;
   int n;
-  Scope(impes_ctx* h_, int cls_, int n_ = 1) : h(h_), cls(cls_), n(n_) {
+  Scope(impes_ctx* h_, int ki_, int n_ = 1) : h(h_), ki(ki_), n(n_) {
     h->launches += n;
-    h->prof_n[cls] += n;
+    h->prof_n[KI_CLASS[ki]] += n;
+    h->ki_n[ki] += n;
     if (h->profiling) cudaEventRecord(h->ev0, h->stream);
   }
   ~Scope() {
@@ -167,7 +188,8 @@ struct Scope {
       cudaEventSynchronize(h->ev1);
       float ms = 0;
       cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-      h->prof_ms[cls] += ms;
+      h->prof_ms[KI_CLASS[ki]] += ms;
+      h->ki_ms[ki] += ms;
     }
   }
 };
@@ -277,6 +299,58 @@ int download_dvec_owned(impes_ctx* h, const double* dev, double* host_v, double*
   return 0;
 }
 
+// ---- slab-local host arrays (impes_*_local): the native layout restricted to what this rank owns, like the
+// local dofs of a ParGridFunction [REF src/run_parallel.cpp:97-104].  Components keep the native order
+// [ux | uy | uz | p]; ghosts are never read from / written to the host (the device halo exchange fills them).
+struct LocalMap {
+  long nx, ny, nz, np, ns;      // owned entries per component
+  long gx, gy, gz, gp, gs;      // first global index of the owned part inside its global component array
+  long dx, dy, dz, dp, ds;      // device offset of the first owned entry (dvec / cvec)
+};
+LocalMap local_map(const impes_ctx* h) {
+  LocalMap m;
+  const Lay& L = h->L;
+  const bool top = L.zhi == L.NZ;
+  if (h->ord == 1) {
+    const Lay1& Q = h->L1;
+    const long px = (long)Q.gx0 * Q.gx1, py = (long)Q.gy0 * Q.gy1, pz = (long)Q.gz0 * Q.gz1, pp = (long)Q.plane * Q.npl;
+    m.nx = px * 2 * Q.nzl; m.gx = px * 2 * Q.zlo; m.dx = Q.off_x;
+    m.ny = Q.has_y ? py * 2 * Q.nzl : 0; m.gy = Q.has_y ? py * 2 * Q.zlo : 0; m.dy = Q.off_y;
+    m.nz = pz * (2 * Q.nzl + (top ? 1 : 0)); m.gz = pz * 2 * Q.zlo; m.dz = Q.off_z + pz * 2;
+    m.np = pp * Q.nzl; m.gp = pp * Q.zlo; m.dp = Q.off_p + pp;
+  } else {
+    const long px = (long)(L.NX + 1) * L.NY, py = (long)L.NX * (L.NY + 1);
+    m.nx = px * L.nzl; m.gx = px * L.zlo; m.dx = L.off_x;
+    m.ny = L.has_y ? py * L.nzl : 0; m.gy = L.has_y ? py * L.zlo : 0; m.dy = L.off_y;
+    m.nz = (long)L.plane * (L.nzl + (top ? 1 : 0)); m.gz = (long)L.plane * L.zlo; m.dz = L.off_z + L.plane;
+    m.np = (long)L.plane * L.nzl; m.gp = (long)L.plane * L.zlo; m.dp = L.off_p + L.plane;
+  }
+  m.ns = (long)L.plane * h->nsl * L.nzl; m.gs = (long)L.plane * h->nsl * L.zlo; m.ds = (long)L.plane * h->nsl;
+  return m;
+}
+// dir: cudaMemcpyHostToDevice / cudaMemcpyDeviceToHost; host_v / host_p: LOCAL arrays (either may be NULL)
+int copy_dvec_local(impes_ctx* h, double* host_v, double* host_p, double* dev, cudaMemcpyKind dir) {
+  const LocalMap m = local_map(h);
+  auto cp = [&](double* hostp, double* devp, long n) -> cudaError_t {
+    if (n <= 0) return cudaSuccess;
+    return dir == cudaMemcpyHostToDevice ? cudaMemcpyAsync(devp, hostp, sizeof(double) * n, dir, h->stream)
+                                         : cudaMemcpyAsync(hostp, devp, sizeof(double) * n, dir, h->stream);
+  };
+  if (host_v) {
+    CK(cp(host_v, dev + m.dx, m.nx));
+    CK(cp(host_v + m.nx, dev + m.dy, m.ny));
+    CK(cp(host_v + m.nx + m.ny, dev + m.dz, m.nz));
+  }
+  if (host_p) CK(cp(host_p, dev + m.dp, m.np));
+  return 0;
+}
+int copy_cells_local(impes_ctx* h, double* host, double* dev, cudaMemcpyKind dir) {
+  const LocalMap m = local_map(h);
+  if (dir == cudaMemcpyHostToDevice) CK(cudaMemcpyAsync(dev + m.ds, host, sizeof(double) * m.ns, dir, h->stream));
+  else CK(cudaMemcpyAsync(host, dev + m.ds, sizeof(double) * m.ns, dir, h->stream));
+  return 0;
+}
+
 // ---- halo exchange (world_size > 1): grouped ncclSend/Recv of whole planes ---------------------
 // up = towards rank+1.  Each (ptr, plane index) pair names a plane inside a (nzl+2)-plane region.
 int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool send_down_bottom_owned, int mult = 1) {
@@ -286,7 +360,7 @@ int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool sen
   const Lay& L = h->L;
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   const size_t pl = (size_t)L.plane * mult;
-  Scope sc(h, KC_COMM, 1);
+  Scope sc(h, KI_COMM, 1);
   NK(h->nccl.GroupStart());
   if (send_up_top_owned) {
     if (up >= 0) NK(h->nccl.Send(base + pl * L.nzl, pl, ncclFloat64, up, h->comm, h->stream));
@@ -305,7 +379,7 @@ int halo_darcy(impes_ctx* h, double* v) {
   if (h->L.nranks == 1) return 0;
   const Lay& L = h->L;
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
-  Scope sc(h, KC_COMM, 1);
+  Scope sc(h, KI_COMM, 1);
   NK(h->nccl.GroupStart());
   if (up >= 0) {
     NK(h->nccl.Send(v + L.off_p + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
@@ -327,7 +401,7 @@ int halo_darcy1(impes_ctx* h, double* v) {
   const Lay1& L = h->L1;
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   const size_t pz = (size_t)L.gz0 * L.gz1, pp = (size_t)L.plane * L.npl;
-  Scope sc(h, KC_COMM, 1);
+  Scope sc(h, KI_COMM, 1);
   NK(h->nccl.GroupStart());
   if (up >= 0) {
     NK(h->nccl.Send(v + L.off_p + pp * L.nzl, pp, ncclFloat64, up, h->comm, h->stream));
@@ -344,7 +418,7 @@ int halo_darcy1(impes_ctx* h, double* v) {
 }
 int allreduce_scalar(impes_ctx* h, double* p) {
   if (h->L.nranks == 1) return 0;
-  Scope sc(h, KC_COMM, 1);
+  Scope sc(h, KI_COMM, 1);
   NK(h->nccl.AllReduce(p, p, 1, ncclFloat64, ncclSum, h->comm, h->stream));
   return 0;
 }
@@ -356,7 +430,7 @@ int update_coeff(impes_ctx* h) {
   const Lay& L = h->L;
   RET_IF(exchange_planes(h, h->S[h->scur], true, true, h->nsl));
   if (h->os == 1) {  // S in DG-Q1: 1/lambda at the mass-rule points, diag(M) by quadrature, Schur diagonal
-    Scope sc(h, KC_COEFF, 3);
+    Scope sc(h, KI_COEFF, 3);
     const int g = (int)((L.ncv + BLK - 1) / BLK);
     if (L.has_y) {
       k1q_rlam<true><<<g, BLK, 0, h->stream>>>(L, h->ph, h->qt, h->S[h->scur], h->rlam);
@@ -369,7 +443,7 @@ int update_coeff(impes_ctx* h) {
     }
   } else
   {
-    Scope sc(h, KC_COEFF, 2);
+    Scope sc(h, KI_COEFF, 2);
     const int g = (int)((L.ncv + BLK - 1) / BLK);
     k_cell_coeff<<<g, BLK, 0, h->stream>>>(L, h->ph, h->S[h->scur], h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1],
                                            h->geo[2], h->m[0], h->m[1], h->m[2]);
@@ -381,14 +455,14 @@ int update_coeff(impes_ctx* h) {
     }
   }
   if (h->sgs_skew) {
-    Scope sc(h, KC_COEFF, 1);
+    Scope sc(h, KI_COEFF, 1);
     k_sgs_pack<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, h->T, h->Md);
   }
   if (!h->mg.empty()) {  // multigrid hierarchy of the Schur stencil (S depends on the saturation)
     auto grid_of = [](const MgLevel& v) { return (int)(((long)v.nx * v.ny * v.nz + MG_B - 1) / MG_B); };
     const bool multi = L.nranks > 1;
     {
-      Scope sc(h, KC_COEFF, 1 + 2 * ((int)h->mg.size() - 1) + (h->ord == 1 ? 1 : 0));
+      Scope sc(h, KI_COEFF, 1 + 2 * ((int)h->mg.size() - 1) + (h->ord == 1 ? 1 : 0));
       if (h->ord == 1) {
         if (L.has_y) k1_mg_copy_fine<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->mg[0], h->T);
         else k1_mg_copy_fine<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->mg[0], h->T);
@@ -419,20 +493,20 @@ int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState*
   if (h->os == 1) {  // variable coefficient inside the cells: element products (A), then face-node completion (B)
     RET_IF(halo_darcy1(h, x));
     {
-      Scope sc(h, KC_DARCY, 1);
+      Scope sc(h, KI_DARCY_Q1A, 1);
 #define KQA(HY, DOT)                                                                                              \
-  k1q_apply_a<HY, DOT><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], \
-                                                             h->geo[0], h->geo[1], h->geo[2], x, y, h->yup, h->partial, \
-                                                             h->scal + 5, h->ticket, st)
+  k1q_apply_a<HY, DOT><<<(h->L.ncl + K1Q_TC - 1) / K1Q_TC, K1QS<HY>::THREADS, sizeof(double) * K1QS<HY>::SMEM_DOUBLES, \
+                         h->stream>>>(h->L1, h->rc, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1],  \
+                                      h->geo[2], x, y, h->yup, h->accA, st)
       if (h->L.has_y) { if (dot) KQA(true, true); else KQA(true, false); }
       else { if (dot) KQA(false, true); else KQA(false, false); }
 #undef KQA
     }
     RET_IF(exchange_planes(h, h->yup, true, false, h->nup));  // the lower rank's top-plane contributions
     {
-      Scope sc(h, KC_DARCY, 1);
+      Scope sc(h, KI_DARCY_Q1B, 1);
 #define KQB(HY, DOT)                                                                                               \
-  k1q_apply_b<HY, DOT><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, x, y, h->yup, h->partial, h->scal + 0, h->scal + 5, \
+  k1q_apply_b<HY, DOT><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, x, y, h->yup, h->accA, h->partial, h->scal + 0, \
                                                              h->ticket, st)
       if (h->L.has_y) { if (dot) KQB(true, true); else KQB(true, false); }
       else { if (dot) KQB(false, true); else KQB(false, false); }
@@ -444,7 +518,7 @@ int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState*
   if (h->ord == 1) {
     RET_IF(halo_darcy1(h, x));
     {
-      Scope sc(h, KC_DARCY, 1);
+      Scope sc(h, KI_DARCY_RT1, 1);
       const int g = h->grid_dofs1;
 #define K1_LAUNCH(HY, DOT)                                                                                        \
   k1_darcy_apply<HY, DOT><<<g, BLK, 0, h->stream>>>(h->L1, h->rc, h->m[0], h->m[1], h->m[2], x, y, h->partial, \
@@ -458,7 +532,7 @@ int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState*
   }
   RET_IF(halo_darcy(h, x));
   {
-    Scope sc(h, KC_DARCY, 1);
+    Scope sc(h, KI_DARCY_RT0, 1);
     if (dot)
       k_darcy_apply<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->m[0], h->m[1], h->m[2], x, y, h->partial,
                                                                 h->scal + 0, h->ticket, st);
@@ -516,7 +590,7 @@ int launch_sgs1(impes_ctx* h, const double* r, double* y, int fwd, int bwd, cons
   Rt1Const C = h->rc;
   const double* T = h->T;
   const double* Md = h->Md;
-  Scope sc(h, KC_PREC, 1);
+  Scope sc(h, KI_SGS, 1);
   if (h->sgs_mode == 2) {
     void* args[] = {(void*)&L, (void*)&C, (void*)&T, (void*)&Md, (void*)&r, (void*)&y, (void*)&fwd, (void*)&bwd, (void*)&st};
     CK(cudaLaunchCooperativeKernel((void*)k1_sgs_wavefront<2, HY>, dim3(h->grid_sgs), dim3(h->sgs_threads), args, 0, h->stream));
@@ -545,7 +619,7 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
   const double* T = h->T;
   const double* Md = h->Md;
   if (h->sgs_skew) {
-    Scope sc(h, KC_PREC, 2 + (fwd ? 1 : 0));
+    Scope sc(h, KI_SGS, 2 + (fwd ? 1 : 0));
     if (fwd) k_sgs_skew_in<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, r, st);
     if (h->sgs_flow)
       k_sgs_flow2d<<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(L, h->pack, T, y, fwd, bwd, st);
@@ -556,7 +630,7 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
     k_sgs_skew_out<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, bwd, y, st);
     return 0;
   }
-  Scope sc(h, KC_PREC, 1);
+  Scope sc(h, KI_SGS, 1);
   if (h->sgs_mode == 2) {
     void* args[] = {(void*)&L, (void*)&T, (void*)&Md, (void*)&r, (void*)&y, (void*)&fwd, (void*)&bwd, (void*)&st};
     CK(cudaLaunchCooperativeKernel((void*)k_sgs_wavefront<2>, dim3(h->grid_sgs), dim3(h->sgs_threads), args, 0, h->stream));
@@ -585,7 +659,7 @@ int mg_halo(impes_ctx* h, double* buf, size_t pe, int nz) {
   const Lay& L = h->L;
   if (L.nranks == 1) return 0;
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
-  Scope sc(h, KC_COMM, 1);
+  Scope sc(h, KI_COMM, 1);
   NK(h->nccl.GroupStart());
   if (up >= 0) {
     NK(h->nccl.Send(buf + pe * (size_t)(nz - 1), pe, ncclFloat64, up, h->comm, h->stream));
@@ -603,7 +677,7 @@ int mg_halo(impes_ctx* h, double* buf, size_t pe, int nz) {
 int mg_gather(impes_ctx* h, double* full, size_t pe) {
   const Lay& L = h->L;
   if (L.nranks == 1) return 0;
-  Scope sc(h, KC_COMM, 1);
+  Scope sc(h, KI_COMM, 1);
   NK(h->nccl.GroupStart());
   for (int r = 0; r < L.nranks; ++r) {
     if (r == L.rank) continue;
@@ -648,16 +722,15 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
   double* qa = h->mg1_ya;
   const double* qD = q1 ? h->Md + h->L1.off_p : nullptr;
   const int gq = q1 ? (int)(((long)L.ncl * h->L1.npl + BLK - 1) / BLK) : 0;  // one thread per L2 dof
-  int n = 0;
   auto q1_smooth = [&](int sweeps, bool from_zero) -> int {
     for (int s = 0; s < sweeps; ++s) {
       double* in = (s & 1) ? qa : qb;
       double* out = (s & 1) ? qb : qa;
       const int first = from_zero && s == 0;
       if (!first && multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
+      Scope sc(h, first ? KI_MGQ_FIRST : KI_MGQ_JACOBI, 1);
       if (L.has_y) k1_mg_jacobi<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
       else k1_mg_jacobi<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
-      ++n;
     }
     return 0;
   };
@@ -675,44 +748,50 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
       double* out = (s & 1) ? v.yb : v.ya;
       const bool first = from_zero && s == 0;
       if (!first && dist(l)) RET_IF(mg_halo(h, in, (size_t)v.nx * v.ny, v.nz));
+      Scope sc(h, KI_MG_CELL, 1);
       k_mg_jacobi<<<grid_of(v), MG_B, 0, h->stream>>>(v, v.r, in, out, h->mg_omega, first, st);
-      ++n;
     }
     return 0;
   };
   if (q1) {
     RET_IF(q1_smooth(h->mg_nu, true));
     if (multi) RET_IF(mg_halo(h, qb + qpe, qpe, L.nzl));
+    Scope sc(h, KI_MGQ_RESTRICT, 1);
     if (L.has_y) k1_mg_restrict<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
     else k1_mg_restrict<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
-    ++n;
   }
   for (int l = 0; l + 1 < nl; ++l) {
     RET_IF(smooth(l, h->mg_nu, true));
     if (dist(l)) RET_IF(mg_halo(h, mg[l].yb, (size_t)mg[l].nx * mg[l].ny, mg[l].nz));
     if (multi && l + 1 == h->mg_g) {  // my planes of the first replicated level, then assemble it everywhere
       const MgLevel cv = mg_view(h, mg[l + 1]);
-      k_mg_restrict<<<grid_of(cv), MG_B, 0, h->stream>>>(mg[l], cv, mg[l].r, mg[l].yb, cv.r, st);
+      {
+        Scope sc(h, KI_MG_CELL, 1);
+        k_mg_restrict<<<grid_of(cv), MG_B, 0, h->stream>>>(mg[l], cv, mg[l].r, mg[l].yb, cv.r, st);
+      }
       RET_IF(mg_gather(h, mg[l + 1].r, (size_t)cv.nx * cv.ny));
     } else {
+      Scope sc(h, KI_MG_CELL, 1);
       k_mg_restrict<<<grid_of(mg[l + 1]), MG_B, 0, h->stream>>>(mg[l], mg[l + 1], mg[l].r, mg[l].yb, mg[l + 1].r, st);
     }
-    ++n;
   }
   RET_IF(smooth(nl - 1, h->mg_coarse_sweeps, true));
   for (int l = nl - 2; l >= 0; --l) {
     const MgLevel cv = (multi && l + 1 == h->mg_g) ? mg_view(h, mg[l + 1]) : mg[l + 1];
-    k_mg_prolong<<<grid_of(mg[l]), MG_B, 0, h->stream>>>(mg[l], cv, cv.yb, mg[l].yb, h->mg_cfac, st);
-    ++n;
+    {
+      Scope sc(h, KI_MG_CELL, 1);
+      k_mg_prolong<<<grid_of(mg[l]), MG_B, 0, h->stream>>>(mg[l], cv, cv.yb, mg[l].yb, h->mg_cfac, st);
+    }
     RET_IF(smooth(l, h->mg_nu, false));
   }
   if (q1) {
-    if (L.has_y) k1_mg_prolong<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
-    else k1_mg_prolong<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
-    ++n;
+    {
+      Scope sc(h, KI_MGQ_PROLONG, 1);
+      if (L.has_y) k1_mg_prolong<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
+      else k1_mg_prolong<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
+    }
     RET_IF(q1_smooth(h->mg_nu, false));
   }
-  Scope sc(h, KC_PREC, n);
   return 0;
 }
 
@@ -726,19 +805,19 @@ int schur_prec(impes_ctx* h, const double* r, double* y, const MinresState* st) 
   double* yp = y + h->vec_offp;
   const size_t pp = (size_t)L.plane * (h->ord == 1 ? h->L1.npl : 1);  // one cell plane of pressure dofs
   // forward: wait for the plane below, sweep, hand my top plane up
-  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp, pp, ncclFloat64, dn, h->comm, h->stream)); }
+  if (dn >= 0) { Scope sc(h, KI_COMM, 1); NK(h->nccl.Recv(yp, pp, ncclFloat64, dn, h->comm, h->stream)); }
   RET_IF(launch_sgs(h, r, y, 1, 0, st));
-  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + pp * L.nzl, pp, ncclFloat64, up, h->comm, h->stream)); }
+  if (up >= 0) { Scope sc(h, KI_COMM, 1); NK(h->nccl.Send(yp + pp * L.nzl, pp, ncclFloat64, up, h->comm, h->stream)); }
   // backward: wait for the plane above, sweep, hand my bottom plane down
-  if (up >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Recv(yp + pp * (L.nzl + 1), pp, ncclFloat64, up, h->comm, h->stream)); }
+  if (up >= 0) { Scope sc(h, KI_COMM, 1); NK(h->nccl.Recv(yp + pp * (L.nzl + 1), pp, ncclFloat64, up, h->comm, h->stream)); }
   RET_IF(launch_sgs(h, r, y, 0, 1, st));
-  if (dn >= 0) { Scope sc(h, KC_COMM, 1); NK(h->nccl.Send(yp + pp, pp, ncclFloat64, dn, h->comm, h->stream)); }
+  if (dn >= 0) { Scope sc(h, KI_COMM, 1); NK(h->nccl.Send(yp + pp, pp, ncclFloat64, dn, h->comm, h->stream)); }
   return 0;
 }
 
 int dot_owned(impes_ctx* h, const double* a, const double* b, double* out, const MinresState* st) {
   {
-    Scope sc(h, KC_DOT, 1);
+    Scope sc(h, KI_DOT, 1);
     if (h->ord == 1) {
       if (h->L.has_y) k1_dot_owned<true><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
       else k1_dot_owned<false><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, a, b, h->partial, out, h->ticket, st);
@@ -753,13 +832,13 @@ int minres_iteration(impes_ctx* h, double* u1, double* q, double* v0, double* v1
                      const MinresState* st_cur, MinresState* st_next) {
   RET_IF(darcy_apply(h, u1, q, true, st_cur));
   {
-    Scope sc(h, KC_MINRES, 1);
+    Scope sc(h, KI_MINRES_B, 1);
     k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, q, v0, v1, h->Md, q, h->scal + 0, st_cur);
   }
   RET_IF(schur_prec(h, v0, q, st_cur));
   RET_IF(dot_owned(h, v0, q, h->scal + 1, st_cur));
   {
-    Scope sc(h, KC_MINRES, 1);
+    Scope sc(h, KI_MINRES_C, 1);
     k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, w0, w1, u1, h->x, v0, q, h->scal + 0, h->scal + 1, st_cur,
                                                    st_next, h->d.darcy_maxiter);
   }
@@ -780,8 +859,9 @@ int build_minres_graph(impes_ctx* h) {
   const int pairs = 8;
   cudaGraph_t g = nullptr;
   const long long l0 = h->launches;
-  long long n0[KC_N];
+  long long n0[KC_N], k0[KI_N];
   memcpy(n0, h->prof_n, sizeof n0);
+  memcpy(k0, h->ki_n, sizeof k0);
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     h->use_graph = false;
@@ -792,8 +872,10 @@ int build_minres_graph(impes_ctx* h) {
   cudaError_t e = cudaStreamEndCapture(h->stream, &g);
   h->graph_launches = h->launches - l0;  // what one replay of the graph launches
   for (int c = 0; c < KC_N; ++c) h->graph_prof_n[c] = h->prof_n[c] - n0[c];
+  for (int c = 0; c < KI_N; ++c) h->graph_ki_n[c] = h->ki_n[c] - k0[c];
   h->launches = l0;  // capture is not execution
   memcpy(h->prof_n, n0, sizeof n0);
+  memcpy(h->ki_n, k0, sizeof k0);
   if (rc || e != cudaSuccess || !g) {
     cudaGetLastError();
     if (g) cudaGraphDestroy(g);
@@ -826,13 +908,13 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
   CK(cudaMemsetAsync(h->u1, 0, nb, h->stream));
   CK(cudaMemcpyAsync(h->v1, h->rhs, nb, cudaMemcpyDeviceToDevice, h->stream));  // v1 = b - A*0
   {
-    Scope sc(h, KC_PREC, 1);
+    Scope sc(h, KI_JACOBI_U, 1);
     k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_offp, h->v1, h->Md, h->u1);
   }
   RET_IF(schur_prec(h, h->v1, h->u1, nullptr));
   RET_IF(dot_owned(h, h->u1, h->v1, h->scal + 1, nullptr));
   {
-    Scope sc(h, KC_MINRES, 1);
+    Scope sc(h, KI_MINRES_INIT, 1);
     k_minres_init<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->v1, h->u1, h->scal + 1, h->st + 0, h->d.darcy_rtol,
                                                       h->d.darcy_atol);
   }
@@ -849,6 +931,7 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
       CK(cudaGraphLaunch(h->minres_exec, h->stream));
       h->launches += h->graph_launches;
       for (int c = 0; c < KC_N; ++c) h->prof_n[c] += h->graph_prof_n[c];
+      for (int c = 0; c < KI_N; ++c) h->ki_n[c] += h->graph_ki_n[c];
     } else {
       for (int p = 0; p < 4; ++p) RET_IF(minres_pair(h));
     }
@@ -891,7 +974,7 @@ int n_substeps(const impes_ctx* h, double global_dt, double dt) {
 
 // f(S) over the whole cvec (after the ghost planes of S are in place)
 int launch_frac(impes_ctx* h, const double* S, double* F) {
-  Scope sc(h, KC_SAT, 1);
+  Scope sc(h, KI_SAT_AUX, 1);
   if (h->os == 1) {
     k_frac_flat<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv * h->nsl, h->ph, h->sp.two_phase, S, F);
     return 0;
@@ -905,16 +988,17 @@ int launch_frac(impes_ctx* h, const double* S, double* F) {
 // Fin / Fout: f(S) arrays of the streaming form (Fin must hold f(Sin) incl. ghost planes); ignored otherwise.
 int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout, const double* Fin = nullptr,
                double* Fout = nullptr) {
-  Scope sc(h, KC_SAT, 1);
+  Scope sc(h, h->os == 1 ? KI_SAT_Q1 : KI_SAT_P0, 1);
   const Lay& L = h->L;
   const double* satv = h->ord == 1 ? h->flux0 : h->x;  // face fluxes in the RT0 dvec layout
   if (h->os == 1) {  // DG-Q1: volume + face terms straight from the RT1 dofs (rt1q.cuh)
+    const int g = (L.ncl + K1Q_TC - 1) / K1Q_TC;
     if (L.has_y) {
-      if (rate) k1q_sat<true, true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
-      else k1q_sat<true, false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      if (rate) k1q_sat<true, true><<<g, K1Q_TC * 3, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      else k1q_sat<true, false><<<g, K1Q_TC * 3, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
     } else {
-      if (rate) k1q_sat<false, true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
-      else k1q_sat<false, false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      if (rate) k1q_sat<false, true><<<g, K1Q_TC * 2, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      else k1q_sat<false, false><<<g, K1Q_TC * 2, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
     }
     return 0;
   }
@@ -949,12 +1033,12 @@ int sat_rate(impes_ctx* h, double* Sin, double* out) {  // out = M_phi^-1 (Kt f(
   return launch_sat(h, true, Sin, out);
 }
 int axpby(impes_ctx* h, double a, const double* x, double b, const double* y, double* out) {
-  Scope sc(h, KC_SAT, 1);
+  Scope sc(h, KI_SAT_AUX, 1);
   k_axpby<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv * h->nsl, a, x, b, y, out);
   return 0;
 }
 int xpby(impes_ctx* h, const double* x, double b, const double* y, double* out) {
-  Scope sc(h, KC_SAT, 1);
+  Scope sc(h, KI_SAT_AUX, 1);
   k_xpby<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv * h->nsl, x, b, y, out);
   return 0;
 }
@@ -964,7 +1048,7 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
   if (nsub) *nsub = nt;
   h->sp.dt = dt;
   if (h->ord == 1 && h->os == 0) {  // RT1 velocity -> face fluxes once per call (the velocity is frozen during the sub-steps)
-    Scope sc(h, KC_SAT, 1);
+    Scope sc(h, KI_SAT_AUX, 1);
     if (h->L.has_y) k1_face_flux<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
     else k1_face_flux<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
   }
@@ -1052,6 +1136,15 @@ double well_Q(const impes_desc& d, const double* p) {
   return 0.;
 }
 
+// dt_local > 0, both finite, and a sub-step count that fits an int (the serial rule casts global_dt/dt to int, the
+// parallel rule loops until t >= global_dt - dt/2: a NaN/inf global_dt would never terminate)
+int check_dt(impes_ctx* h, double global_dt, double dt_local) {
+  if (!(dt_local > 0) || !std::isfinite(dt_local)) { h->err = "dt_local must be finite and > 0"; return IMPES_ERR_BAD_ARG; }
+  if (!std::isfinite(global_dt)) { h->err = "global_dt must be finite"; return IMPES_ERR_BAD_ARG; }
+  if (global_dt / dt_local > 2.0e9) { h->err = "global_dt / dt_local exceeds the int range of the sub-step counter"; return IMPES_ERR_BAD_ARG; }
+  return 0;
+}
+
 int check_handle(impes_ctx* h) {
   if (!h) return IMPES_ERR_BAD_ARG;
   if (cudaSetDevice(h->dev) != cudaSuccess) {
@@ -1099,7 +1192,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup, h->accA};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   for (double* b : h->mg_bufs)
@@ -1163,8 +1256,23 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   L.fdy = make_fastdiv((unsigned)L.NY);
   int mg_m = 0;  // multigrid mode on several GPUs: slabs are cut in units of 2^mg_m planes
   if (d.schur_prec == IMPES_SCHUR_MG && L.nranks > 1) {
-    while (mg_m < 6 && (L.NZ >> (mg_m + 1)) >= L.nranks) ++mg_m;
-    if (mg_m < 1) { h->err = "IMPES_SCHUR_MG: needs at least 2 cell planes per GPU"; return IMPES_ERR_BAD_ARG; }
+    // Levels 0 .. g-1 stay distributed over the slabs (halo exchange per sweep), level g and below run replicated on
+    // every GPU after one gather.  g = the first level small enough to be cheaper replicated than exchanged
+    // (<= mg_repl_cells unknowns: a sweep over it costs less than one NCCL hand-shake), at most the largest g whose
+    // 2^g-plane units still give every GPU a unit.  (Round 1 distributed as many levels as possible: ~12 more NCCL
+    // operations per V-cycle at 8 GPUs and slabs of 16,16,16,8,8,8,8,5 planes for the 85-plane SPE10 shape.)
+    long repl = 1L << 19;
+    if (const char* e = getenv("IMPES_MG_REPL_CELLS")) repl = std::max(1L, atol(e));
+    int gmax = 0;
+    while (gmax < 6 && (L.NZ >> (gmax + 1)) >= L.nranks) ++gmax;
+    if (gmax < 1) { h->err = "IMPES_SCHUR_MG: needs at least 2 cell planes per GPU"; return IMPES_ERR_BAD_ARG; }
+    auto level_cells = [&](int l) {
+      long nx = L.NX, ny = L.NY, nz = L.NZ;
+      for (int k = 0; k < l; ++k) { nx = (nx + 1) / 2; ny = ny > 1 ? (ny + 1) / 2 : 1; nz = (nz + 1) / 2; }
+      return nx * ny * nz;
+    };
+    mg_m = 1;
+    while (mg_m < gmax && level_cells(mg_m) > repl) ++mg_m;
   }
   auto slab_of = [&](int rank, int& lo, int& hi) {
     // balanced slabs of plane units: the first (n % P) ranks get one extra unit (unit = 1 plane
@@ -1276,6 +1384,14 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     }
     t.dl[0] = 1.0 / (on[0] - on[1]); t.dl[1] = 1.0 / (on[1] - on[0]);
     t.wv = d.dim == 3 ? 0.125 : 0.25;
+    for (int qe = 0; qe < 4; ++qe)
+      for (int qf = 0; qf < 4; ++qf)
+        for (int tf = 0; tf < 2; ++tf)
+          for (int te = 0; te < 2; ++te) t.OO[qe][qf][te + 2 * tf] = t.O[qe][te] * t.O[qf][tf];
+    for (int qe = 0; qe < 3; ++qe)
+      for (int qf = 0; qf < 3; ++qf)
+        for (int tf = 0; tf < 2; ++tf)
+          for (int te = 0; te < 2; ++te) t.OOF[qe][qf][te + 2 * tf] = t.OF[qe][te] * t.OF[qf][tf];
     h->nqp = d.dim == 3 ? 64 : 9;
     h->nup = d.dim == 3 ? 12 : 4;
   }
@@ -1450,6 +1566,9 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   if (h->os == 1) {
     RET_IF(dev_alloc(h, &h->rlam, (long)L.ncv * h->nqp));
     RET_IF(dev_alloc(h, &h->yup, (long)L.ncv * h->nup));
+    RET_IF(dev_alloc(h, &h->accA, (long)L.nblk * BLK));
+    CK(cudaFuncSetAttribute(k1q_apply_a<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
+    CK(cudaFuncSetAttribute(k1q_apply_a<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
     h->sat_mode = 0;  // the DG-Q1 kernel always carries f(S)
   }
   double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
@@ -1502,7 +1621,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
       nx = (nx + 1) / 2; ny = ny > 1 ? (ny + 1) / 2 : 1; nzg = (nzg + 1) / 2;
     }
   }
-  RET_IF(dev_alloc(h, &h->partial, std::max(L.nblk, h->grid_dofs1) + 8));
+  RET_IF(dev_alloc(h, &h->partial, std::max(2 * L.nblk, h->grid_dofs1) + 8));
   RET_IF(dev_alloc(h, &h->scal, 8));
   CK(cudaMalloc((void**)&h->ticket, sizeof(unsigned) * 4));
   CK(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned) * 4, h->stream));
@@ -1659,7 +1778,7 @@ API int impes_saturation_advance(impes_handle h, const double* V_host, double* S
                                  double dt_local, int* n_substeps_out) {
   (void)global_ti;  // only names output files in the reference [REF src/saturation_solver.cpp:93-108]
   RET_IF(check_handle(h));
-  if (!(dt_local > 0)) { h->err = "dt_local must be > 0"; return IMPES_ERR_BAD_ARG; }
+  RET_IF(check_dt(h, global_dt, dt_local));
   if (V_host) RET_IF(upload_dvec(h, V_host, nullptr, h->x));
   if (S_inout) RET_IF(upload_cells(h, S_inout, h->S[h->scur], h->nsl));
   RET_IF(saturation_device(h, global_dt, dt_local, n_substeps_out));
@@ -1668,11 +1787,94 @@ API int impes_saturation_advance(impes_handle h, const double* V_host, double* S
   return 0;
 }
 
+// ---- slab-local variants: every rank passes only what it owns (ParGridFunction-style local data) ----------
+API int impes_get_local_dims(impes_handle h, impes_local_dims* out) {
+  if (!h || !out) return IMPES_ERR_BAD_ARG;
+  memset(out, 0, sizeof *out);
+  const LocalMap m = local_map(h);
+  out->n_s = m.ns; out->n_p = m.np; out->n_v = m.nx + m.ny + m.nz;
+  out->s_start = m.gs; out->p_start = m.gp;
+  if (h->d.dim == 3) {
+    out->n_v_comp[0] = m.nx; out->n_v_comp[1] = m.ny; out->n_v_comp[2] = m.nz;
+    out->v_comp_start[0] = m.gx; out->v_comp_start[1] = m.gy; out->v_comp_start[2] = m.gz;
+  } else {
+    out->n_v_comp[0] = m.nx; out->n_v_comp[1] = m.nz;
+    out->v_comp_start[0] = m.gx; out->v_comp_start[1] = m.gz;
+  }
+  return 0;
+}
+
+API int impes_pressure_solve_local(impes_handle h, const double* S_local, double* x_local, impes_solve_stats* stats) {
+  RET_IF(check_handle(h));
+  impes_solve_stats loc;
+  if (!stats) stats = &loc;
+  memset(stats, 0, sizeof *stats);
+  auto t0 = std::chrono::steady_clock::now();
+  if (S_local) RET_IF(copy_cells_local(h, const_cast<double*>(S_local), h->S[h->scur], cudaMemcpyHostToDevice));
+  const int rc = pressure_solve_device(h, stats);
+  if (rc && rc != IMPES_ERR_NOT_CONVERGED) return rc;
+  if (x_local) {
+    const LocalMap m = local_map(h);
+    RET_IF(copy_dvec_local(h, x_local, x_local + m.nx + m.ny + m.nz, h->x, cudaMemcpyDeviceToHost));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+API int impes_saturation_advance_local(impes_handle h, const double* V_local, double* S_local, int global_ti,
+                                       double global_dt, double dt_local, int* n_substeps_out) {
+  (void)global_ti;
+  RET_IF(check_handle(h));
+  RET_IF(check_dt(h, global_dt, dt_local));
+  if (V_local) {  // owned dofs from the host, ghost planes from the neighbours (V.Distribute [REF src/run_parallel.cpp:186])
+    RET_IF(copy_dvec_local(h, const_cast<double*>(V_local), nullptr, h->x, cudaMemcpyHostToDevice));
+    RET_IF(h->ord == 1 ? halo_darcy1(h, h->x) : halo_darcy(h, h->x));
+  }
+  if (S_local) RET_IF(copy_cells_local(h, S_local, h->S[h->scur], cudaMemcpyHostToDevice));
+  RET_IF(saturation_device(h, global_dt, dt_local, n_substeps_out));
+  if (S_local) RET_IF(copy_cells_local(h, S_local, h->S[h->scur], cudaMemcpyDeviceToHost));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_set_field_local(impes_handle h, int which, const double* host) {
+  RET_IF(check_handle(h));
+  if (!host) return IMPES_ERR_BAD_ARG;
+  double* hp = const_cast<double*>(host);
+  const LocalMap m = local_map(h);
+  switch (which) {
+    case IMPES_FIELD_SATURATION: RET_IF(copy_cells_local(h, hp, h->S[h->scur], cudaMemcpyHostToDevice)); h->coeff_valid = false; break;
+    case IMPES_FIELD_VELOCITY: RET_IF(copy_dvec_local(h, hp, nullptr, h->x, cudaMemcpyHostToDevice)); break;
+    case IMPES_FIELD_PRESSURE: RET_IF(copy_dvec_local(h, nullptr, hp, h->x, cudaMemcpyHostToDevice)); break;
+    case IMPES_FIELD_DARCY_X: RET_IF(copy_dvec_local(h, hp, hp + m.nx + m.ny + m.nz, h->x, cudaMemcpyHostToDevice)); break;
+    default: h->err = "unknown field"; return IMPES_ERR_BAD_ARG;
+  }
+  if (which != IMPES_FIELD_SATURATION) RET_IF(h->ord == 1 ? halo_darcy1(h, h->x) : halo_darcy(h, h->x));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+API int impes_get_field_local(impes_handle h, int which, double* host) {
+  RET_IF(check_handle(h));
+  if (!host) return IMPES_ERR_BAD_ARG;
+  const LocalMap m = local_map(h);
+  switch (which) {
+    case IMPES_FIELD_SATURATION: RET_IF(copy_cells_local(h, host, h->S[h->scur], cudaMemcpyDeviceToHost)); break;
+    case IMPES_FIELD_VELOCITY: RET_IF(copy_dvec_local(h, host, nullptr, h->x, cudaMemcpyDeviceToHost)); break;
+    case IMPES_FIELD_PRESSURE: RET_IF(copy_dvec_local(h, nullptr, host, h->x, cudaMemcpyDeviceToHost)); break;
+    case IMPES_FIELD_DARCY_X: RET_IF(copy_dvec_local(h, host, host + m.nx + m.ny + m.nz, h->x, cudaMemcpyDeviceToHost)); break;
+    default: h->err = "unknown field"; return IMPES_ERR_BAD_ARG;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 API int impes_guards(impes_handle h, int64_t* n_nonfinite, double* s_max) {
   RET_IF(check_handle(h));
   CK(cudaMemsetAsync(h->guard, 0, sizeof(unsigned long long) * 2, h->stream));
   {
-    Scope sc(h, KC_MISC, 1);
+    Scope sc(h, KI_MISC, 1);
     if (h->os == 1)
       k_guards_flat<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncl * h->nsl, h->S[h->scur] + (long)h->L.plane * h->nsl,
                                                         h->guard, h->guard + 1);
@@ -1725,7 +1927,7 @@ API int impes_prec_apply(impes_handle h, const double* r_host, double* y_host) {
   RET_IF(upload_dvec(h, r_host, r_host + h->g_nv, h->tmpv));
   CK(cudaMemsetAsync(h->q, 0, sizeof(double) * h->vec_n, h->stream));
   {
-    Scope sc(h, KC_PREC, 1);
+    Scope sc(h, KI_JACOBI_U, 1);
     k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_offp, h->tmpv, h->Md, h->q);
   }
   RET_IF(schur_prec(h, h->tmpv, h->q, nullptr));
@@ -1769,16 +1971,17 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
         RET_IF(launch_sat(h, false, h->S[h->scur], h->S[h->scur ^ 1], h->F[h->scur], h->F[h->scur ^ 1]));
         break;
       case IMPES_KERNEL_MINRES_UPDATE: {
-        Scope sc(h, KC_MINRES, 2);
+        { Scope sc(h, KI_MINRES_B, 1);
         k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
-                                                       h->st + 2);
+                                                       h->st + 2); }
+        Scope sc(h, KI_MINRES_C, 1);
         k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->w0, h->w1, h->u1, h->tmpv, h->v0, h->q, h->scal + 2,
                                                        h->scal + 3, h->st + 2, h->st + 3, 1 << 30);
         break;
       }
       case IMPES_KERNEL_PREC_APPLY: {
         {
-          Scope sc(h, KC_PREC, 1);
+          Scope sc(h, KI_JACOBI_U, 1);
           k_jacobi_u<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_offp, h->v1, h->Md, h->tmpv);
         }
         RET_IF(schur_prec(h, h->v1, h->tmpv, nullptr));
@@ -1827,6 +2030,8 @@ API int impes_profile_enable(impes_handle h, int on) {
   h->profiling = on != 0;
   memset(h->prof_ms, 0, sizeof h->prof_ms);
   memset(h->prof_n, 0, sizeof h->prof_n);
+  memset(h->ki_ms, 0, sizeof h->ki_ms);
+  memset(h->ki_n, 0, sizeof h->ki_n);
   return 0;
 }
 
@@ -1837,4 +2042,14 @@ API int impes_profile_read(impes_handle h, double* ms_by_kernel, int64_t* launch
     if (launches_by_kernel) launches_by_kernel[i] = h->prof_n[i];
   }
   return 0;
+}
+
+API int impes_profile_read_kernels(impes_handle h, int cap, const char** names, double* ms, int64_t* launches) {
+  if (!h) return -1;
+  for (int i = 0; i < KI_N && i < cap; ++i) {
+    if (names) names[i] = KI_NAME[i];
+    if (ms) ms[i] = h->ki_ms[i];
+    if (launches) launches[i] = h->ki_n[i];
+  }
+  return KI_N;
 }

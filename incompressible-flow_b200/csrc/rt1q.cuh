@@ -31,6 +31,8 @@ struct QTab {
   double dl[2];      // derivative of the open basis (constant): -sqrt 3, +sqrt 3
   double sn[2];      // the DG / L2 nodes 1/2 -+ 1/(2 sqrt 3)
   double wv;         // weight of a DG node in the collocated rule: (1/2)^dim
+  double OO[4][4][4];  // 3-D: O[qe][te] * O[qf][tf] at [qe][qf][te + 2 tf] (host-computed: the same IEEE products)
+  double OOF[3][3][4]; // 3-D: OF[qe][te] * OF[qf][tf] at [qe][qf][te + 2 tf]
 };
 
 template <bool HY>
@@ -186,29 +188,53 @@ __global__ void __launch_bounds__(BLK) k1_schur_diag(Lay1 L, Rt1Const C, const d
 }
 
 // ---------------------------------------------------------------------------------------
-// K1 (os = 1), pass A: one thread per owned cell applies its three dense element blocks
+// K1 (os = 1), pass A.  One thread per (owned cell, direction): a CTA covers K1Q_TC consecutive owned cells, its
+// warps are specialised by direction (x | y | z), so a thread applies ONE dense 12x12 element block
 //   y_loc = (geo_d / K_d) Phi^T diag(c_q) Phi x_loc          (c_q = w_q / lambda_q from k1q_rlam)
 // in sum-factorised form (per transverse point pair: collapse the open directions, run the 4-point line along d,
-// expand back), adds the line-structured B^T p terms, computes the pressure rows, and writes
+// expand back), adds the line-structured B^T p terms and writes
 //   interior-node rows: complete;  lower-face-node rows: own element + B^T (the lower cell's element part is added
 //   by pass B);  upper-face-node contributions: to yup[cell][dir][line] for the upper neighbour's pass B.
+// The c_q of the CTA's cells (one contiguous range of rlam) and their pressure dofs are staged through shared memory
+// with coalesced loads (odd row stride: conflict-free reads); the three direction threads of a cell meet in shared
+// memory for the pressure rows  yp = (yp_x + yp_y) + yp_z  and the cell's share of <x, y>
+//   acc = ((acc_x + acc_y) + acc_z) + sum_l pc_l yp_l,
+// which goes to accA[cell]; pass B reduces it together with its own share (fixed trees, no atomics on doubles).
 // Eliminated boundary nodes enter with x = 0 and keep identity rows [REF src/pressure_solver.cpp:56-61].
+// (Round 1's version ran one thread per cell through all three directions: 128 registers + 676 B of spills,
+// scattered 8-byte loads of the 64 c_q -- 9 % of the HBM roofline.)
 // ---------------------------------------------------------------------------------------
+constexpr int K1Q_TC = 64;  // cells per CTA
+
+template <bool HY>
+struct K1QS {
+  static constexpr int ND = HY ? 3 : 2;
+  static constexpr int RS = QD<HY>::NQP | 1;        // row stride of the staged c_q (odd)
+  static constexpr int PS = QD<HY>::NSL + 1;        // row stride of the staged pressure dofs / per-direction partials
+  static constexpr int THREADS = K1Q_TC * ND;
+  static constexpr int SMEM_DOUBLES = K1Q_TC * RS + K1Q_TC * PS + ND * K1Q_TC * PS;
+};
+
+// rl: the cell's c_q in shared memory; oo2: QTab::OO (products of the transverse open bases, host-computed doubles)
 template <bool HY, int D>
-__device__ __forceinline__ void elem_apply(const QTab& tb, const double* __restrict__ rl, const double (&xl)[12],
-                                           double (&yl)[12]) {
+__device__ __forceinline__ void elem_apply(const QTab& tb, const double* rl, const double (&xl)[12], double (&yl)[12]) {
   using R = QDir<HY, D>;
   constexpr int NOE = R::no(R::E), NOF = R::no(R::F);
 #pragma unroll
   for (int n = 0; n < 12; ++n) yl[n] = 0.0;
-  for (int qf = 0; qf < R::nq(R::F); ++qf)
+#pragma unroll
+  for (int qf = 0; qf < R::nq(R::F); ++qf) {
+    // keep the shared-memory loads of one qf slab together with their arithmetic: without this fence the
+    // scheduler hoists all 64 c_q loads to the top (158 registers; 3 CTAs per SM need <= 112)
+    asm volatile("" ::: "memory");
+#pragma unroll
     for (int qe = 0; qe < R::nq(R::E); ++qe) {
       double oo[NOE * NOF], v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int tf = 0; tf < NOF; ++tf)
 #pragma unroll
         for (int te = 0; te < NOE; ++te) {
-          const double o2 = ob<HY>(tb, R::E, qe, te) * ob<HY>(tb, R::F, qf, tf);
+          const double o2 = HY ? tb.OO[qe][qf][te + NOE * tf] : ob<HY>(tb, R::E, qe, te) * ob<HY>(tb, R::F, qf, tf);
           oo[te + NOE * tf] = o2;
 #pragma unroll
           for (int i = 0; i < 3; ++i) v[i] = __fma_rn(o2, xl[i + 3 * (te + NOE * tf)], v[i]);
@@ -227,20 +253,33 @@ __device__ __forceinline__ void elem_apply(const QTab& tb, const double* __restr
 #pragma unroll
         for (int i = 0; i < 3; ++i) yl[i + 3 * t] = __fma_rn(oo[t], r[i], yl[i + 3 * t]);
     }
+  }
 }
 
+// CTA-wide barrier that warps reach from different code paths (the three direction bodies below): a named
+// barrier is identified by its id, not by the program counter (PTX barrier.sync id, count).
+template <int NTHREADS>
+__device__ __forceinline__ void named_barrier_1() {
+  asm volatile("barrier.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+}
+
+// one (cell, direction) of pass A.  rl / pc: the cell's c_q and pressure dofs in shared memory (valid after the
+// barrier); ypd: this direction's partial pressure rows [NSL] followed by its share of the dot.  ok = false (ragged
+// last CTA): the lane shadows another cell and stores nothing.
 template <bool HY, int D, bool DOT>
-__device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, const Rt1Const& C, const QTab& tb,
-                                            const double* __restrict__ rlam, const double* __restrict__ K, double geo,
+__device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool ok, const Rt1Const& C, const QTab& tb,
+                                            const double* rl, const double* __restrict__ K, double geo,
                                             const double* __restrict__ x, double* __restrict__ y,
-                                            double* __restrict__ yup, const double (&pc)[QD<HY>::NSL],
-                                            double (&yp)[QD<HY>::NSL], double& acc) {
+                                            double* __restrict__ yup, const double* pc, double* ypd) {
   using R = QDir<HY, D>;
   using Q = QD<HY>;
-  constexpr int NOE = R::no(R::E), NOF = R::no(R::F);
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F), NT = NOE * NOF;
   constexpr int DI = HY ? D : (D == 0 ? 0 : 1);  // index of the direction among the present ones
-  double xl[12], yl[12], x0r[4], x2r[4];
+  constexpr int PS1 = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));  // stride between the two pressure dofs of a line
+  double xl[12], ttlo[NT];
   int cd = 0, nd = 1;
+  // ---- every global load of the thread, then the barrier that publishes the staged data
+  const double Kc = K[q.c];
 #pragma unroll
   for (int tf = 0; tf < NOF; ++tf)
 #pragma unroll
@@ -248,16 +287,41 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, const
       const Line1 l = line_of<HY, D>(L, q, te, tf);
       const int t = te + NOE * tf;
       cd = l.cd; nd = l.nd;
-      x0r[t] = x[l.base]; x2r[t] = x[l.base + 2 * l.sd];
-      xl[0 + 3 * t] = l.cd > 0 ? x0r[t] : 0.0;
+      xl[3 * t] = x[l.base];
       xl[1 + 3 * t] = x[l.base + l.sd];
-      xl[2 + 3 * t] = l.cd + 1 < l.nd ? x2r[t] : 0.0;
+      xl[2 + 3 * t] = x[l.base + 2 * l.sd];
+    }
+  const bool lo = cd > 0, hi = cd + 1 < nd;
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {  // lower neighbour's pressure dofs (clamped to the own cell where there is none)
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      const double* pL = x + (q.pb - (lo ? l.pdn : 0) + l.lp);
+      double tt = 0.0;
+      tt += C.Bv[0][2] * pL[0]; tt += C.Bv[1][2] * pL[l.ps];
+      ttlo[te + NOE * tf] = tt;
     }
 #pragma unroll
-  for (int n = 3 * NOE * NOF; n < 12; ++n) xl[n] = 0.0;
-  elem_apply<HY, D>(tb, rlam + (long)q.c * Q::NQP, xl, yl);
-  const double sc = geo / K[q.c];
-  const int pb = q.pb;  // owned_cell1: dvec1 index of the cell's first pressure dof
+  for (int n = 3 * NT; n < 12; ++n) xl[n] = 0.0;
+  cp_async_wait<0>();
+  named_barrier_1<K1QS<HY>::THREADS>();
+  const double sc = geo / Kc;
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const int t = te + NOE * tf;
+      const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
+      // B^T terms of the lower-face rows, completed before the element product
+      ttlo[t] += C.Bv[0][0] * pc[lp]; ttlo[t] += C.Bv[1][0] * pc[lp + PS1];
+      // eliminated boundary nodes enter the element product (and the pressure rows) with x = 0
+      xl[3 * t] = lo ? xl[3 * t] : 0.0;
+      xl[2 + 3 * t] = hi ? xl[2 + 3 * t] : 0.0;
+    }
+  double yl[12];
+  elem_apply<HY, D>(tb, rl, xl, yl);
+  double acc = 0.0;
 #pragma unroll
   for (int tf = 0; tf < NOF; ++tf)
 #pragma unroll
@@ -265,66 +329,119 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, const
       const Line1 l = line_of<HY, D>(L, q, te, tf);
       const int t = te + NOE * tf;
       const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
-      const int ps = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));
-      const double pc0 = pc[lp], pc1 = pc[lp + ps];
+      const double pc0 = pc[lp], pc1 = pc[lp + PS1];
       const double x0 = xl[3 * t], x1 = xl[1 + 3 * t], x2 = xl[2 + 3 * t];
       {  // interior node
         double tt = 0.0;
         tt += C.Bv[0][1] * pc0; tt += C.Bv[1][1] * pc1;
         const double y1 = sc * yl[1 + 3 * t] + tt;
-        y[l.base + l.sd] = y1;
+        if (ok) y[l.base + l.sd] = y1;
         if (DOT) acc += x1 * y1;
       }
-      if (cd > 0) {  // lower face node: own element part + B^T; completed by pass B
-        const double* pL = x + (pb - l.pdn + lp);
-        double tt = 0.0;
-        tt += C.Bv[0][2] * pL[0]; tt += C.Bv[1][2] * pL[ps]; tt += C.Bv[0][0] * pc0; tt += C.Bv[1][0] * pc1;
-        y[l.base] = sc * yl[3 * t] + tt;
+      if (lo) {  // lower face node: own element part + B^T; completed by pass B
+        if (ok) y[l.base] = sc * yl[3 * t] + ttlo[t];
+      } else {   // eliminated boundary node: identity row (its raw value is re-read: boundary cells only)
+        const double xr = x[l.base];
+        if (ok) y[l.base] = xr;
+        if (DOT) acc += xr * xr;
+      }
+      if (hi) {
+        if (ok) yup[(long)q.c * Q::NUP + DI * Q::NL + t] = sc * yl[2 + 3 * t];
       } else {
-        y[l.base] = x0r[t];
-        if (DOT) acc += x0r[t] * x0r[t];
+        const double xr = x[l.base + 2 * l.sd];
+        if (ok) y[l.base + 2 * l.sd] = xr;
+        if (DOT) acc += xr * xr;
       }
-      if (cd + 1 < nd) yup[(long)q.c * Q::NUP + DI * Q::NL + t] = sc * yl[2 + 3 * t];
-      else {
-        y[l.base + 2 * l.sd] = x2r[t];
-        if (DOT) acc += x2r[t] * x2r[t];
-      }
-      // pressure rows (eliminated columns carry x = 0)
-      yp[lp] += C.Bv[0][0] * x0; yp[lp] += C.Bv[0][1] * x1; yp[lp] += C.Bv[0][2] * x2;
-      yp[lp + ps] += C.Bv[1][0] * x0; yp[lp + ps] += C.Bv[1][1] * x1; yp[lp + ps] += C.Bv[1][2] * x2;
+      // this direction's part of the two pressure rows of the line
+      double a0 = 0.0, a1 = 0.0;
+      a0 += C.Bv[0][0] * x0; a0 += C.Bv[0][1] * x1; a0 += C.Bv[0][2] * x2;
+      a1 += C.Bv[1][0] * x0; a1 += C.Bv[1][1] * x1; a1 += C.Bv[1][2] * x2;
+      ypd[lp] = a0; ypd[lp + PS1] = a1;
     }
+  ypd[Q::NSL] = acc;
 }
 
 template <bool HY, bool DOT>
-__global__ void __launch_bounds__(BLK, 2) k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam,
-                                                   const double* __restrict__ Kx, const double* __restrict__ Ky,
-                                                   const double* __restrict__ Kz, double gx, double gy, double gz,
-                                                   const double* __restrict__ x, double* __restrict__ y,
-                                                   double* __restrict__ yup, double* partial, double* out,
-                                                   unsigned* ticket, const MinresState* st) {
+__global__ void __launch_bounds__(K1QS<HY>::THREADS, HY ? 3 : 4)
+k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam, const double* __restrict__ Kx,
+            const double* __restrict__ Ky, const double* __restrict__ Kz, double gx, double gy, double gz,
+            const double* __restrict__ x, double* __restrict__ y, double* __restrict__ yup,
+            double* __restrict__ accA, const MinresState* st) {
   using Q = QD<HY>;
+  using S = K1QS<HY>;
   if (st && st->done) return;
-  const Cell1 q = owned_cell1(L);
-  double acc = 0.0;
-  if (q.ok) {
-    double pc[Q::NSL], yp[Q::NSL];
-    const int pb = q.pb;
+  extern __shared__ double k1q_sm[];
+  double* s_rl = k1q_sm;                       // [TC][RS]
+  double* s_pc = s_rl + K1Q_TC * S::RS;        // [TC][PS]
+  double* s_yp = s_pc + K1Q_TC * S::PS;        // [ND][TC][PS]
+  const int tid = threadIdx.x;
+  const int ci = tid % K1Q_TC, dir = tid / K1Q_TC;   // dir is warp-uniform (K1Q_TC is a multiple of 32)
+  const unsigned t0 = blockIdx.x * (unsigned)K1Q_TC;  // first owned cell of the CTA
+  const unsigned nc = min((unsigned)K1Q_TC, (unsigned)L.ncl - t0);
+  {  // stage c_q and the pressure dofs of the CTA's cells: both are contiguous ranges (cell-major arrays).
+     // cp.async: every copy of the thread is in flight at once and lands in shared memory without a register
+     // round trip (the LDG -> STS loop it replaces paid one L2 latency per iteration: ncu long-scoreboard 4.5/issue)
+    const double* g_rl = rlam + ((long)t0 + L.plane) * Q::NQP;
+    constexpr int NRL = (K1Q_TC * Q::NQP + S::THREADS - 1) / S::THREADS;
 #pragma unroll
-    for (int l = 0; l < Q::NSL; ++l) { pc[l] = x[pb + l]; yp[l] = 0.0; }
-    q_apply_dir<HY, 0, DOT>(L, q, C, tb, rlam, Kx, gx, x, y, yup, pc, yp, acc);
-    if constexpr (HY) q_apply_dir<HY, 1, DOT>(L, q, C, tb, rlam, Ky, gy, x, y, yup, pc, yp, acc);
-    q_apply_dir<HY, 2, DOT>(L, q, C, tb, rlam, Kz, gz, x, y, yup, pc, yp, acc);
+    for (int it = 0; it < NRL; ++it) {
+      const unsigned e = tid + it * S::THREADS;
+      if (e < nc * Q::NQP) {
+        const unsigned c = e / Q::NQP, qq = e - c * Q::NQP;
+        cp_async8(s_rl + c * S::RS + qq, g_rl + e);
+      }
+    }
+    const double* g_pc = x + L.off_p + ((long)t0 + L.plane) * Q::NSL;
+    constexpr int NPC = (K1Q_TC * Q::NSL + S::THREADS - 1) / S::THREADS;
+#pragma unroll
+    for (int it = 0; it < NPC; ++it) {
+      const unsigned e = tid + it * S::THREADS;
+      if (e < nc * Q::NSL) {
+        const unsigned c = e / Q::NSL, l = e - c * Q::NSL;
+        cp_async8(s_pc + c * S::PS + l, g_pc + e);
+      }
+    }
+    cp_async_commit();
+  }
+  Cell1 q;
+  {
+    const unsigned t = t0 + ci;
+    q.ok = (unsigned)ci < nc;
+    const unsigned tt = q.ok ? t : t0;   // idle lanes (ragged last CTA) shadow the CTA's first cell and store nothing
+    const unsigned r = fastdiv(tt, L.fdx);
+    q.i = (int)(tt - r * (unsigned)L.NX);
+    q.kl = (int)fastdiv(r, L.fdy);
+    q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
+    q.k = q.kl + L.zlo;
+    q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+    q.pb = L.off_p + q.c * L.npl;
+  }
+  const int cs = q.ok ? ci : 0;
+  const double* rl = s_rl + cs * S::RS;
+  const double* pc = s_pc + cs * S::PS;
+  double* ypd = s_yp + (dir * K1Q_TC + ci) * S::PS;
+  // dir is warp-uniform: no divergence between the three bodies; each contains the named barrier once
+  if (dir == 0) q_apply_dir<HY, 0, DOT>(L, q, q.ok, C, tb, rl, Kx, gx, x, y, yup, pc, ypd);
+  else if (HY && dir == 1) q_apply_dir<HY, 1, DOT>(L, q, q.ok, C, tb, rl, Ky, gy, x, y, yup, pc, ypd);
+  else q_apply_dir<HY, 2, DOT>(L, q, q.ok, C, tb, rl, Kz, gz, x, y, yup, pc, ypd);
+  __syncthreads();
+  if (dir == 0 && q.ok) {  // pressure rows and the cell's share of <x, y>
+    const double* a = s_yp + ci * S::PS;
+    const double* b = s_yp + (K1Q_TC + ci) * S::PS;
+    const double* c2 = s_yp + (2 * K1Q_TC + ci) * S::PS;
+    double acc = HY ? (a[Q::NSL] + b[Q::NSL]) + c2[Q::NSL] : a[Q::NSL] + b[Q::NSL];
+    double ap = 0.0;
 #pragma unroll
     for (int l = 0; l < Q::NSL; ++l) {
-      y[pb + l] = yp[l];
-      if (DOT) acc += pc[l] * yp[l];
+      const double yp = HY ? (a[l] + b[l]) + c2[l] : a[l] + b[l];
+      y[q.pb + l] = yp;
+      if (DOT) ap += pc[l] * yp;
     }
+    if (DOT) accA[t0 + ci] = acc + ap;
   }
-  if (DOT) finish_dot(acc, partial, out, ticket);
 }
 
-// pass B: lower-face-node rows += the lower cell's element contribution; the dot gets their products and the
-// partial result of pass A
+// pass B: lower-face-node rows += the lower cell's element contribution; <x, y> = tree(accA) + tree(own share)
 template <bool HY, int D, bool DOT>
 __device__ __forceinline__ void q_face_dir(const Lay1& L, const Cell1& q, const double* __restrict__ x,
                                            double* __restrict__ y, const double* __restrict__ yup, double& acc) {
@@ -346,34 +463,41 @@ __device__ __forceinline__ void q_face_dir(const Lay1& L, const Cell1& q, const 
 }
 template <bool HY, bool DOT>
 __global__ void __launch_bounds__(BLK) k1q_apply_b(Lay1 L, const double* __restrict__ x, double* __restrict__ y,
-                                                   const double* __restrict__ yup, double* partial, double* out,
-                                                   const double* prev, unsigned* ticket, const MinresState* st) {
+                                                   const double* __restrict__ yup, const double* __restrict__ accA,
+                                                   double* partial, double* out, unsigned* ticket,
+                                                   const MinresState* st) {
   if (st && st->done) return;
   const Cell1 q = owned_cell1(L);
-  double acc = 0.0;
+  double acc = 0.0, accq = 0.0;
   if (q.ok) {
     q_face_dir<HY, 0, DOT>(L, q, x, y, yup, acc);
     if constexpr (HY) q_face_dir<HY, 1, DOT>(L, q, x, y, yup, acc);
     q_face_dir<HY, 2, DOT>(L, q, x, y, yup, acc);
+    if (DOT) accq = accA[blockIdx.x * (unsigned)BLK + threadIdx.x];
   }
   if (DOT) {
     __shared__ double sm[BLK / 32];
     __shared__ int is_last;
-    const double s = block_tree_256(acc, sm);
+    const double sa = block_tree_256(accq, sm);
+    __syncthreads();
+    const double sb = block_tree_256(acc, sm);
     if (threadIdx.x == 0) {
-      partial[blockIdx.x] = s;
+      partial[blockIdx.x] = sa;
+      partial[gridDim.x + blockIdx.x] = sb;
       __threadfence();
       is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (is_last) {
       __threadfence();
-      double a = 0.0;
-      for (unsigned j = threadIdx.x; j < gridDim.x; j += BLK) a += __ldcg(partial + j);
+      double a = 0.0, b = 0.0;
+      for (unsigned j = threadIdx.x; j < gridDim.x; j += BLK) { a += __ldcg(partial + j); b += __ldcg(partial + gridDim.x + j); }
       __syncthreads();
-      const double tot = block_tree_256(a, sm);
+      const double ta = block_tree_256(a, sm);
+      __syncthreads();
+      const double tb2 = block_tree_256(b, sm);
       if (threadIdx.x == 0) {
-        *out = *prev + tot;
+        *out = ta + tb2;
         *ticket = 0u;
       }
     }
@@ -397,16 +521,19 @@ __device__ __forceinline__ double sat_source_at(const SatParam& sp, double px, d
           py <= sp.inj_c1 + sp.inj_h) ? sp.src : 0.;
 }
 
+// One (cell, direction) of a stage: rd[m] = this direction's part of (Kt F)_m for the cell's NSL dofs.
+// g: the cell's own F (shared memory).  ok = false: the lane shadows another cell (ragged last CTA).
 template <bool HY, int D>
 __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const QTab& tb, const double* __restrict__ x,
-                                          const double* __restrict__ Fin, const double (&g)[QD<HY>::NSL],
-                                          double (&r)[QD<HY>::NSL]) {
+                                          const double* __restrict__ Fin, const double* g, double* rd) {
   using R = QDir<HY, D>;
   using Q = QD<HY>;
   constexpr int NOE = R::no(R::E), NOF = R::no(R::F), NT = NOE * NOF;
   constexpr int NFE = (R::E == 1 && !HY) ? 1 : Q::NF, NFF = (R::F == 1 && !HY) ? 1 : Q::NF;
-  double ulo[NT], uhi[NT], go0[NT], go1[NT], gn_lo[NT], gn_hi[NT];
-  int mlo[NT], ps = 1, cd = 0, nd = 1, cs = 1;
+  constexpr int PS1 = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));
+  double ulo[NT], uhi[NT], umid[NT], gnl0[NT], gnl1[NT], gnh0[NT], gnh1[NT];
+  int cd = 0, nd = 1;
+  // ---- global loads first: RT1 dofs of the cell's lines, F of the two line neighbours
 #pragma unroll
   for (int tf = 0; tf < NOF; ++tf)
 #pragma unroll
@@ -414,31 +541,44 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
       const Line1 l = line_of<HY, D>(L, q, te, tf);
       const int t = te + NOE * tf;
       const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
-      ps = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));
-      cd = l.cd; nd = l.nd; cs = l.cstride;
-      mlo[t] = lp;
-      const double u0 = x[l.base], u1 = x[l.base + l.sd], u2 = x[l.base + 2 * l.sd];
-      ulo[t] = u0; uhi[t] = u2;
-      const double g0 = g[lp], g1 = g[lp + ps];
+      cd = l.cd; nd = l.nd;
+      ulo[t] = x[l.base]; umid[t] = x[l.base + l.sd]; uhi[t] = x[l.base + 2 * l.sd];
+      const long nl = (long)(q.c - (l.cd > 0 ? l.cstride : 0)) * Q::NSL + lp;
+      const long nh = (long)(q.c + (l.cd + 1 < l.nd ? l.cstride : 0)) * Q::NSL + lp;
+      gnl0[t] = Fin[nl]; gnl1[t] = Fin[nl + PS1];
+      gnh0[t] = Fin[nh]; gnh1[t] = Fin[nh + PS1];
+    }
+  cp_async_wait<0>();
+  named_barrier_1<K1Q_TC * (HY ? 3 : 2)>();  // the staged F of the CTA's cells is in place
+  double go0[NT], go1[NT], gn_lo[NT], gn_hi[NT];
+#pragma unroll
+  for (int m = 0; m < Q::NSL; ++m) rd[m] = 0.0;
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const int t = te + NOE * tf;
+      const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
+      const double u0 = ulo[t], u1 = umid[t], u2 = uhi[t];
+      const double g0 = g[lp], g1 = g[lp + PS1];
       // volume term: sum over the two DG nodes of the line of  w g vhat dpsi_i/dxi_d
       const double vh0 = tb.LC[0][0] * u0 + tb.LC[0][1] * u1 + tb.LC[0][2] * u2;
       const double vh1 = tb.LC[1][0] * u0 + tb.LC[1][1] * u1 + tb.LC[1][2] * u2;
       const double vol = tb.wv * (g0 * vh0 + g1 * vh1);
-      r[lp] += tb.dl[0] * vol;
-      r[lp + ps] += tb.dl[1] * vol;
+      rd[lp] += tb.dl[0] * vol;
+      rd[lp + PS1] += tb.dl[1] * vol;
       // traces of g on the two faces: own side, and the neighbour's side
       go0[t] = tb.E0[0] * g0 + tb.E0[1] * g1;
       go1[t] = tb.E1[0] * g0 + tb.E1[1] * g1;
-      const long nl = (long)(q.c - (l.cd > 0 ? l.cstride : 0)) * Q::NSL + lp;
-      const long nh = (long)(q.c + (l.cd + 1 < l.nd ? l.cstride : 0)) * Q::NSL + lp;
-      gn_lo[t] = tb.E1[0] * Fin[nl] + tb.E1[1] * Fin[nl + ps];   // lower cell, its xi_d = 1 face
-      gn_hi[t] = tb.E0[0] * Fin[nh] + tb.E0[1] * Fin[nh + ps];   // upper cell, its xi_d = 0 face
+      gn_lo[t] = tb.E1[0] * gnl0[t] + tb.E1[1] * gnl1[t];   // lower cell, its xi_d = 1 face
+      gn_hi[t] = tb.E0[0] * gnh0[t] + tb.E0[1] * gnh1[t];   // upper cell, its xi_d = 0 face
     }
-  (void)cs;
   double cl[NT], ch[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) { cl[t] = 0.0; ch[t] = 0.0; }
+#pragma unroll
   for (int qf = 0; qf < NFF; ++qf)
+#pragma unroll
     for (int qe = 0; qe < NFE; ++qe) {
       double oo[NT];
       double unl = 0.0, unh = 0.0, g1l = 0.0, g2l = 0.0, g1h = 0.0, g2h = 0.0;
@@ -448,7 +588,7 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
         for (int te = 0; te < NOE; ++te) {
           const int t = te + NOE * tf;
           const double oe = (NFE == 1) ? 1.0 : tb.OF[qe][te], of = (NFF == 1) ? 1.0 : tb.OF[qf][tf];
-          oo[t] = oe * of;
+          oo[t] = (NFE == 1 || NFF == 1) ? oe * of : tb.OOF[qe][qf][t];
           unl += ulo[t] * oo[t]; unh += uhi[t] * oo[t];
           g1l += gn_lo[t] * oo[t]; g2l += go0[t] * oo[t];   // lower face: element 1 = lower cell, element 2 = this cell
           g1h += go1[t] * oo[t]; g2h += gn_hi[t] * oo[t];   // upper face: element 1 = this cell
@@ -468,49 +608,107 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
       }
     }
 #pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    if (cd > 0) {  // rows of element 2 of the lower face: + flux * psi_i(xi_d = 0)
-      r[mlo[t]] += tb.E0[0] * cl[t];
-      r[mlo[t] + ps] += tb.E0[1] * cl[t];
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const int t = te + NOE * tf;
+      const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
+      if (cd > 0) {  // rows of element 2 of the lower face: + flux * psi_i(xi_d = 0)
+        rd[lp] += tb.E0[0] * cl[t];
+        rd[lp + PS1] += tb.E0[1] * cl[t];
+      }
+      if (cd + 1 < nd) {  // rows of element 1 of the upper face: - flux * psi_i(xi_d = 1)
+        rd[lp] -= tb.E1[0] * ch[t];
+        rd[lp + PS1] -= tb.E1[1] * ch[t];
+      }
     }
-    if (cd + 1 < nd) {  // rows of element 1 of the upper face: - flux * psi_i(xi_d = 1)
-      r[mlo[t]] -= tb.E1[0] * ch[t];
-      r[mlo[t] + ps] -= tb.E1[1] * ch[t];
-    }
-  }
 }
 
+// One thread per (owned cell, direction) like K1 pass A: the CTA stages F of its K1Q_TC cells in shared memory, each
+// thread forms its direction's part of Kt F (volume term + both faces of the cell along that direction), the three
+// parts meet in shared memory as  r = (r_x + r_y) + r_z,  and the update runs one thread per DG dof (coalesced).
+// (Round 1's version: one thread per cell through all directions, 254 -> 128 registers with spills, 17 % of the HBM
+// roofline.)
 template <bool HY, bool RATE>
-__global__ void __launch_bounds__(BLK, 2) k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x,
-                                               const double* __restrict__ phi, const double* __restrict__ Sin,
-                                               const double* __restrict__ Fin, double* __restrict__ Sout,
-                                               double* __restrict__ Fout) {
+__global__ void __launch_bounds__(K1Q_TC * (HY ? 3 : 2), HY ? 3 : 4)
+k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x, const double* __restrict__ phi,
+        const double* __restrict__ Sin, const double* __restrict__ Fin, double* __restrict__ Sout,
+        double* __restrict__ Fout) {
   using Q = QD<HY>;
-  const Cell1 q = owned_cell1(L);
-  if (!q.ok) return;
-  double g[Q::NSL], r[Q::NSL];
-  const long sb = (long)q.c * Q::NSL;
+  constexpr int ND = HY ? 3 : 2, THREADS = K1Q_TC * ND, PS = Q::NSL + 1;
+  __shared__ double s_g[K1Q_TC * PS];        // F of the CTA's cells
+  __shared__ double s_r[ND * K1Q_TC * PS];   // per-direction parts of Kt F
+  const int tid = threadIdx.x;
+  const int ci = tid % K1Q_TC, dir = tid / K1Q_TC;
+  const unsigned t0 = blockIdx.x * (unsigned)K1Q_TC;
+  const unsigned nc = min((unsigned)K1Q_TC, (unsigned)L.ncl - t0);
+  const long sb0 = ((long)t0 + L.plane) * Q::NSL;   // first DG dof of the CTA's cells (cell-major, ghost plane below)
+  constexpr int NIT = (K1Q_TC * Q::NSL + THREADS - 1) / THREADS;
 #pragma unroll
-  for (int m = 0; m < Q::NSL; ++m) { g[m] = Fin[sb + m]; r[m] = 0.0; }
-  q_sat_dir<HY, 0>(L, q, tb, x, Fin, g, r);
-  if constexpr (HY) q_sat_dir<HY, 1>(L, q, tb, x, Fin, g, r);
-  q_sat_dir<HY, 2>(L, q, tb, x, Fin, g, r);
+  for (int it = 0; it < NIT; ++it) {
+    const unsigned e = tid + it * THREADS;
+    if (e < nc * Q::NSL) {
+      const unsigned c = e / Q::NSL, m = e - c * Q::NSL;
+      cp_async8(s_g + c * PS + m, Fin + sb0 + e);
+    }
+  }
+  cp_async_commit();
+  Cell1 q;
+  {
+    q.ok = (unsigned)ci < nc;
+    const unsigned tt = q.ok ? t0 + ci : t0;
+    const unsigned r = fastdiv(tt, L.fdx);
+    q.i = (int)(tt - r * (unsigned)L.NX);
+    q.kl = (int)fastdiv(r, L.fdy);
+    q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
+    q.k = q.kl + L.zlo;
+    q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+    q.pb = L.off_p + q.c * L.npl;
+  }
+  const double* g = s_g + (q.ok ? ci : 0) * PS;
+  double* rd = s_r + (dir * K1Q_TC + ci) * PS;
+  if (dir == 0) q_sat_dir<HY, 0>(L, q, tb, x, Fin, g, rd);
+  else if (HY && dir == 1) q_sat_dir<HY, 1>(L, q, tb, x, Fin, g, rd);
+  else q_sat_dir<HY, 2>(L, q, tb, x, Fin, g, rd);
+  // operands of the update pass (one DG dof per thread and pass), all in flight before the barrier
+  double phi_r[NIT], sin_r[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const unsigned e = tid + it * THREADS;
+    const bool in = e < nc * Q::NSL;
+    phi_r[it] = phi[(long)t0 + L.plane + (in ? e / Q::NSL : 0)];
+    sin_r[it] = RATE ? 0.0 : Sin[sb0 + (in ? e : 0)];
+  }
+  __syncthreads();
   const double wm = sp.vol * tb.wv;
-  const double mphi = phi[q.c] * wm;
 #pragma unroll
-  for (int m = 0; m < Q::NSL; ++m) {
+  for (int it = 0; it < NIT; ++it) {   // one DG dof per thread and pass
+    const unsigned e = tid + it * THREADS;
+    if (e >= nc * Q::NSL) break;
+    const unsigned c = e / Q::NSL, m = e - c * Q::NSL;
+    const unsigned tt = t0 + c;
+    const unsigned rr = fastdiv(tt, L.fdx);
+    const int i = (int)(tt - rr * (unsigned)L.NX);
+    const int kl = (int)fastdiv(rr, L.fdy);
+    const int j = (int)(rr - (unsigned)kl * (unsigned)L.NY);
+    const int k = kl + L.zlo;
+    const double ra = s_r[c * PS + m], rb = s_r[(K1Q_TC + c) * PS + m];
+    const double r = HY ? (ra + rb) + s_r[(2 * K1Q_TC + c) * PS + m] : ra + rb;
     const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
-    const double px = (q.i + tb.sn[m0]) * sp.hx, py = (q.j + tb.sn[m1]) * sp.hy, pz = (q.k + tb.sn[m2]) * sp.hz;
-    const double z = r[m] + sat_source_at(sp, px, py, pz) * wm;
+    // run-time node index: selects instead of indexing the kernel parameter (which would be copied to local memory)
+    const double px = (i + (m0 ? tb.sn[1] : tb.sn[0])) * sp.hx, py = (j + (m1 ? tb.sn[1] : tb.sn[0])) * sp.hy,
+                 pz = (k + (m2 ? tb.sn[1] : tb.sn[0])) * sp.hz;
+    const double z = r + sat_source_at(sp, px, py, pz) * wm;
+    const double mphi = phi_r[it] * wm;
     double yv = z / mphi;
     double so;
     if (RATE) so = yv;
     else {
       yv *= sp.dt;
-      so = Sin[sb + m] + yv;
+      so = sin_r[it] + yv;
     }
-    Sout[sb + m] = so;
-    if (!RATE) Fout[sb + m] = sp.two_phase ? frac_flow_of(ph, so) : so;
+    Sout[sb0 + e] = so;
+    if (!RATE) Fout[sb0 + e] = sp.two_phase ? frac_flow_of(ph, so) : so;
   }
 }
 

@@ -14,17 +14,42 @@ def slab_range(n_layers, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def slab_range_mg(n_layers, rank, world):
-    """Slabs of the multi-GPU multigrid mode (IMPES_SCHUR_MG, world > 1): cut in units of 2^m layers, m the
-    largest value (<= 6) with n_layers / 2^m >= world, so that the multigrid aggregates of the first m levels
-    never straddle two GPUs (csrc/api.cu create_impl).  256 layers on 8 GPUs -> m = 5, 32 layers each;
-    85 layers on 8 GPUs -> m = 3, units of 8 -> 16,16,16,8,8,8,8,5."""
+MG_REPL_CELLS = 1 << 19
+
+
+def mg_first_replicated_level(n_layers, world, plane_dims=None, repl=MG_REPL_CELLS):
+    """First multigrid level that runs replicated on every GPU (csrc/api.cu create_impl): the first level >= 1 with
+    at most `repl` cells, capped by the largest g whose 2^g-layer units still give every GPU a unit.
+    plane_dims: (nx,) in 2-D, (nx, ny) in 3-D; None: the cap itself (the round-1 rule)."""
+    gmax = 0
+    while gmax < 6 and (n_layers >> (gmax + 1)) >= world:
+        gmax += 1
+    if plane_dims is None or gmax < 1:
+        return gmax
+
+    def cells(l):
+        dims = list(plane_dims) + [n_layers]
+        for _ in range(l):
+            dims = [(v + 1) // 2 for v in dims]
+        out = 1
+        for v in dims:
+            out *= v
+        return out
+
+    g = 1
+    while g < gmax and cells(g) > repl:
+        g += 1
+    return g
+
+
+def slab_range_mg(n_layers, rank, world, plane_dims=None, repl=MG_REPL_CELLS):
+    """Slabs of the multi-GPU multigrid mode (IMPES_SCHUR_MG, world > 1): cut in units of 2^g layers, g the first
+    replicated level (mg_first_replicated_level), so that the aggregates of the distributed levels never straddle
+    two GPUs.  256^3 on 8 GPUs -> g = 2 (level 2 = 64^3 runs replicated), 32 layers each; the SPE10 shape
+    60x220x85 on 8 GPUs -> g = 1, units of 2 layers -> 12,12,12,10,10,10,10,9."""
     if world == 1:
         return 0, n_layers
-    m = 0
-    while m < 6 and (n_layers >> (m + 1)) >= world:
-        m += 1
-    unit = 1 << m
+    unit = 1 << mg_first_replicated_level(n_layers, world, plane_dims, repl)
     nu = (n_layers + unit - 1) // unit
     base, rem = divmod(nu, world)
     ulo = rank * base + min(rank, rem)

@@ -85,6 +85,7 @@ typedef struct orc {
   double *rlam;
   double q1_alpha;
   int threads;             /* >1: OpenMP in SpMV / vector ops (CPU baseline only) */
+  int det;                 /* threads > 1 with deterministic arithmetic: the canonical paths keep their bits */
   int mass_cg;             /* 1: invert M_phi with Jacobi-PCG like the reference */
   /* MG hierarchy for IMPES_SCHUR_MG (restated in orc_mg.inc) */
   void *mg;
@@ -250,6 +251,7 @@ static double canon_dot(const orc *o, const double *a, const double *b) {
   const long nvx = (long)(NX + 1) * NY * NZ, nvy = has_y ? (long)NX * (NY + 1) * NZ : 0;
   const long ncl = (long)NX * NY * NZ, nblk = (ncl + 255) / 256;
   double *partial = (double *)malloc(sizeof(double) * nblk);
+#pragma omp parallel for schedule(static) if (o->threads > 1)
   for (long blk = 0; blk < nblk; ++blk) {
     double v[256];
     for (int t = 0; t < 256; ++t) {
@@ -294,6 +296,7 @@ static double canon_dot_rt1(const orc *o, const double *a, const double *b) {
   const int dim = o->dim, npl = o->npl;
   const long nd = o->ncell * npl, nblk = (nd + 255) / 256;
   double *partial = (double *)malloc(sizeof(double) * nblk);
+#pragma omp parallel for schedule(static) if (o->threads > 1)
   for (long blk = 0; blk < nblk; ++blk) {
     double v[256];
     for (int t = 0; t < 256; ++t) {
@@ -334,8 +337,9 @@ static double canon_dot_rt1(const orc *o, const double *a, const double *b) {
 
 /* Vector::operator* : plain sequential sum [MFEM-recall] */
 static double vdot(const orc *o, const double *a, const double *b, long n) {
-  if (o->arith == 1 && o->threads <= 1 && n == o->nv + o->np && o->kv == 0 && o->kp == 0) return canon_dot(o, a, b);
-  if (o->arith == 1 && o->threads <= 1 && n == o->nv + o->np && o->kv == 1 && o->kp == 1) return canon_dot_rt1(o, a, b);
+  const int canon = o->arith == 1 && (o->threads <= 1 || o->det) && n == o->nv + o->np;
+  if (canon && o->kv == 0 && o->kp == 0) return canon_dot(o, a, b);
+  if (canon && o->kv == 1 && o->kp == 1) return canon_dot_rt1(o, a, b);
   if (o->threads > 1) {
     double s = 0.0;
 #pragma omp parallel for schedule(static) reduction(+ : s)
@@ -495,6 +499,12 @@ ORC_API void orc_set_threads(orc *o, int t) {
   omp_set_num_threads(o->threads);
 #endif
 }
+/* OpenMP threads for the canonical (arith == 1) paths as well: every loop that is threaded there runs over
+ * independent unknowns / reduction blocks, so the results are bit-identical to one thread. */
+ORC_API void orc_set_threads_det(orc *o, int t) {
+  orc_set_threads(o, t);
+  o->det = 1;
+}
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -651,7 +661,7 @@ static double sat_at(const orc *o, const double *S, long cell, const double *xi)
   return v;
 }
 
-static int q1_canonical(const orc *o) { return o->arith == 1 && o->kv == 1 && o->kp == 1 && o->ks == 1 && o->threads <= 1; }
+static int q1_canonical(const orc *o) { return o->arith == 1 && o->kv == 1 && o->kp == 1 && o->ks == 1 && (o->threads <= 1 || o->det); }
 static void q1_coefficients(orc *o, const double *S);
 static void q1_darcy_mult(orc *o, const double *x, double *y);
 static int q1_saturation_rate(const orc *o, const double *u, const double *S, const double *F, double *out, double dt, int rate);

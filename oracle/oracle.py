@@ -41,6 +41,7 @@ def lib():
         L.orc_last_error.restype = C.c_char_p
         L.orc_last_error.argtypes = [C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_threads_det.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_dot_mode.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_mass_cg.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_arith.argtypes = [C.c_void_p, C.c_int]
@@ -94,6 +95,10 @@ class Oracle:
 
     def set_threads(self, t):
         self.L.orc_set_threads(self.h, int(t))
+
+    def set_threads_det(self, t):
+        """OpenMP threads with deterministic arithmetic: every canonical (arith == 1) path keeps its bits"""
+        self.L.orc_set_threads_det(self.h, int(t))
 
     def set_dot_mode(self, m):
         self.L.orc_set_dot_mode(self.h, int(m))

@@ -29,7 +29,7 @@ def _worker(rank, world, port, dim, nx, ny, nz, order, mg, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n = nx * ny * (nz if dim == 3 else 1)
     nlay = nz if dim == 3 else ny
-    slab = pkg.partition.slab_range_mg(nlay, rank, world) if mg else None
+    slab = pkg.partition.slab_range_mg(nlay, rank, world, (nx, ny) if dim == 3 else (nx,)) if mg else None
     darcy, cells = pkg.partition.owned_ranges(dim, nx, ny, nz, rank, world, order=order, slab=slab)
     plane = n // nlay
     if order == 0:
@@ -85,11 +85,18 @@ def test_slab_ranges_balanced(pkg):
 
 
 def test_slab_ranges_multigrid_aligned(pkg):
-    """Multi-GPU multigrid mode: slabs in units of 2^m layers (aggregates never straddle GPUs)."""
-    r = [pkg.partition.slab_range_mg(256, k, 8) for k in range(8)]
+    """Multi-GPU multigrid mode: slabs in units of 2^g layers, g = the first replicated level (aggregates of the
+    distributed levels never straddle GPUs); small levels run replicated instead of exchanging halos."""
+    P = pkg.partition
+    assert P.mg_first_replicated_level(256, 8, (256, 256)) == 2          # 64^3 = 2^18 cells <= 2^19
+    r = [P.slab_range_mg(256, k, 8, (256, 256)) for k in range(8)]
     assert [hi - lo for lo, hi in r] == [32] * 8
-    r = [pkg.partition.slab_range_mg(85, k, 8) for k in range(8)]
-    assert [hi - lo for lo, hi in r] == [16, 16, 16, 8, 8, 8, 8, 5]
+    assert P.mg_first_replicated_level(85, 8, (60, 220)) == 1            # SPE10 shape: level 1 = 30x110x43
+    r = [P.slab_range_mg(85, k, 8, (60, 220)) for k in range(8)]
+    assert [hi - lo for lo, hi in r] == [12, 12, 12, 10, 10, 10, 10, 9]
     assert r[0][0] == 0 and r[-1][1] == 85 and all(r[i][1] == r[i + 1][0] for i in range(7))
-    assert all(lo % 8 == 0 for lo, _ in r)
-    assert pkg.partition.slab_range_mg(21, 0, 2) == (0, 16) and pkg.partition.slab_range_mg(21, 1, 2) == (16, 21)
+    assert all(lo % 2 == 0 for lo, _ in r)
+    # no plane dims: the alignment cap itself (as many distributed levels as the layer count allows)
+    r = [P.slab_range_mg(85, k, 8) for k in range(8)]
+    assert [hi - lo for lo, hi in r] == [16, 16, 16, 8, 8, 8, 8, 5]
+    assert P.slab_range_mg(21, 0, 2, (33,)) == (0, 12) and P.slab_range_mg(21, 1, 2, (33,)) == (12, 21)
