@@ -785,12 +785,23 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
     RET_IF(smooth(l, h->mg_nu, false));
   }
   if (q1) {
+    // prolongation fused into the first post-smoothing sweep (k1_mg_jacobi<.., PRO>): reads qb (before the
+    // correction) and the level-0 iterate, writes qa; the remaining sweeps alternate as before.  Needs the ghost
+    // planes of both: qb's are still valid from the exchange before the restriction, mg[0].yb's are fetched here.
+    if (multi) RET_IF(mg_halo(h, mg[0].yb, (size_t)L.plane, L.nzl));
     {
-      Scope sc(h, KI_MGQ_PROLONG, 1);
-      if (L.has_y) k1_mg_prolong<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
-      else k1_mg_prolong<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, mg[0].yb, qb, h->mg_cfac, st);
+      Scope sc(h, KI_MGQ_JACOBI, 1);
+      if (L.has_y) k1_mg_jacobi<true, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
+      else k1_mg_jacobi<false, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
     }
-    RET_IF(q1_smooth(h->mg_nu, false));
+    for (int s = 1; s < h->mg_nu; ++s) {
+      double* in = (s & 1) ? qa : qb;
+      double* out = (s & 1) ? qb : qa;
+      if (multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
+      Scope sc(h, KI_MGQ_JACOBI, 1);
+      if (L.has_y) k1_mg_jacobi<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+      else k1_mg_jacobi<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+    }
   }
   return 0;
 }
@@ -1392,6 +1403,14 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
       for (int qf = 0; qf < 3; ++qf)
         for (int tf = 0; tf < 2; ++tf)
           for (int te = 0; te < 2; ++te) t.OOF[qe][qf][te + 2 * tf] = t.OF[qe][te] * t.OF[qf][tf];
+    if (d.dim == 3) {  // the rolled 3-D quadrature loops read these from constant memory (same values for every handle)
+      double wf[3][3];
+      for (int qe = 0; qe < 3; ++qe)
+        for (int qf = 0; qf < 3; ++qf) wf[qe][qf] = t.fw[qe] * t.fw[qf];
+      CK(cudaMemcpyToSymbol(c_OO3, t.OO, sizeof t.OO));
+      CK(cudaMemcpyToSymbol(c_OOF3, t.OOF, sizeof t.OOF));
+      CK(cudaMemcpyToSymbol(c_WF3, wf, sizeof wf));
+    }
     h->nqp = d.dim == 3 ? 64 : 9;
     h->nup = d.dim == 3 ? 12 : 4;
   }

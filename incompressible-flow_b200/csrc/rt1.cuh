@@ -518,22 +518,28 @@ __global__ void __launch_bounds__(BLK) k1_face_flux(Lay1 L1, Lay L0, Rt1Const C,
 // 18 % DRAM, because each lane walked its own 64-byte block with 8-byte loads).
 // Branch-free neighbour terms for the per-dof kernels: T is stored as 0 on eliminated boundary nodes, so a
 // missing neighbour contributes y * (b (b' 0)) = +-0 with y loaded from a clamped (own-cell) address.
+// e: cfac * (coarse correction of the neighbour cell) when the prolongation is fused into the sweep (PRO), else unused
+template <bool PRO>
 __device__ __forceinline__ void nb_lower(const Rt1Const& C, const Line1& l, int a, double T0, const double* y, int pb,
-                                         double& sum) {
+                                         double e, double& sum) {
   const double* yl = y + (pb - (l.cd > 0 ? l.pdn : 0) + l.lp);
-  sum += yl[0] * (BV(a, 0) * (C.Bv[0][2] * T0));
-  sum += yl[l.ps] * (BV(a, 0) * (C.Bv[1][2] * T0));
+  sum += (PRO ? yl[0] + e : yl[0]) * (BV(a, 0) * (C.Bv[0][2] * T0));
+  sum += (PRO ? yl[l.ps] + e : yl[l.ps]) * (BV(a, 0) * (C.Bv[1][2] * T0));
 }
+template <bool PRO>
 __device__ __forceinline__ void nb_upper(const Rt1Const& C, const Line1& l, int a, double T2, const double* y, int pb,
-                                         double& sum) {
+                                         double e, double& sum) {
   const double* yu = y + (pb + (l.cd + 1 < l.nd ? l.pdn : 0) + l.lp);
-  sum += yu[0] * (BV(a, 2) * (C.Bv[0][0] * T2));
-  sum += yu[l.ps] * (BV(a, 2) * (C.Bv[1][0] * T2));
+  sum += (PRO ? yu[0] + e : yu[0]) * (BV(a, 2) * (C.Bv[0][0] * T2));
+  sum += (PRO ? yu[l.ps] + e : yu[l.ps]) * (BV(a, 2) * (C.Bv[1][0] * T2));
 }
-// off-diagonal part of row l (all columns); ys = y of this dof; all 32 lanes must call
-template <bool HY>
+// off-diagonal part of row l (all columns); ys = y of this dof; all 32 lanes must call.
+// PRO: y is the iterate BEFORE the prolongation y += cfac * ec(cell) (k1_mg_prolong); the correction is added on the
+// fly to every neighbour value (same expression, same bits), ec = cell-level iterate with one ghost plane below.
+template <bool HY, bool PRO = false>
 __device__ __forceinline__ double q1_row_sum_dof(const Lay1& L, const Rt1Const& C, const Dof1& d,
-                                                 const double* __restrict__ T, const double* __restrict__ y, double ys) {
+                                                 const double* __restrict__ T, const double* __restrict__ y, double ys,
+                                                 const double* __restrict__ ec = nullptr, double cfac = 0.0) {
   const Cell1& q = d.q;
   const int l = d.l;
   const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
@@ -549,11 +555,18 @@ __device__ __forceinline__ double q1_row_sum_dof(const Lay1& L, const Rt1Const& 
   const double Tz0 = T[lz.base], Tz1 = T[lz.base + lz.sd], Tz2 = T[lz.base + 2 * lz.sd];
   const double Sx = s_in(C, a0, Tx0, Tx1, Tx2), Sz = s_in(C, a2, Tz0, Tz1, Tz2);
   const double Sy = HY ? s_in(C, a1, Ty0, Ty1, Ty2) : 0.0;
+  double ezl = 0.0, eyl = 0.0, exl = 0.0, exu = 0.0, eyu = 0.0, ezu = 0.0;
+  if constexpr (PRO) {  // coarse corrections of the six line-neighbour cells (clamped like the y loads)
+    const int cc = q.i + L.NX * (q.j + L.NY * q.kl);   // cell index in the level-0 arrays (ghost plane at -plane)
+    ezl = cfac * ec[cc - (lz.cd > 0 ? L.plane : 0)]; ezu = cfac * ec[cc + (lz.cd + 1 < lz.nd ? L.plane : 0)];
+    if constexpr (HY) { eyl = cfac * ec[cc - (ly.cd > 0 ? L.NX : 0)]; eyu = cfac * ec[cc + (ly.cd + 1 < ly.nd ? L.NX : 0)]; }
+    exl = cfac * ec[cc - (lx.cd > 0 ? 1 : 0)]; exu = cfac * ec[cc + (lx.cd + 1 < lx.nd ? 1 : 0)];
+  }
   double sum = 0.0;
   // lower cells, ascending cell index: z-, y-, x-
-  nb_lower(C, lz, a2, Tz0, y, q.pb, sum);
-  if constexpr (HY) nb_lower(C, ly, a1, Ty0, y, q.pb, sum);
-  nb_lower(C, lx, a0, Tx0, y, q.pb, sum);
+  nb_lower<PRO>(C, lz, a2, Tz0, y, q.pb, ezl, sum);
+  if constexpr (HY) nb_lower<PRO>(C, ly, a1, Ty0, y, q.pb, eyl, sum);
+  nb_lower<PRO>(C, lx, a0, Tx0, y, q.pb, exl, sum);
   // in-cell partners: smaller local index (flip a2, a1, a0 from 1 to 0), then larger (flip a0, a1, a2 from 0 to 1)
   sum += a2 ? yz * Sz : 0.0;
   if constexpr (HY) sum += a1 ? yy * Sy : 0.0;
@@ -562,17 +575,21 @@ __device__ __forceinline__ double q1_row_sum_dof(const Lay1& L, const Rt1Const& 
   if constexpr (HY) sum += a1 ? 0.0 : yy * Sy;
   sum += a2 ? 0.0 : yz * Sz;
   // upper cells: x+, y+, z+
-  nb_upper(C, lx, a0, Tx2, y, q.pb, sum);
-  if constexpr (HY) nb_upper(C, ly, a1, Ty2, y, q.pb, sum);
-  nb_upper(C, lz, a2, Tz2, y, q.pb, sum);
+  nb_upper<PRO>(C, lx, a0, Tx2, y, q.pb, exu, sum);
+  if constexpr (HY) nb_upper<PRO>(C, ly, a1, Ty2, y, q.pb, eyu, sum);
+  nb_upper<PRO>(C, lz, a2, Tz2, y, q.pb, ezu, sum);
   return sum;
 }
 
-template <bool HY>
+// PRO: the first post-smoothing sweep with the prolongation fused in: yin is the iterate before
+// y += cfac * ec(cell) (what k1_mg_prolong would have written, one whole pass over the level saved); a missing
+// neighbour contributes (y + e) * (b (b' 0)) = +-0 as before.
+template <bool HY, bool PRO = false>
 __global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
                                                     const double* __restrict__ Dp, const double* __restrict__ rp,
                                                     const double* __restrict__ yin, double* __restrict__ yout,
-                                                    double omega, int first, const MinresState* st) {
+                                                    double omega, int first, const MinresState* st,
+                                                    const double* __restrict__ ec = nullptr, double cfac = 0.0) {
   if (st && st->done) return;
   const Dof1 d = owned_dof1<HY>(L);
   const int p = d.q.pb + d.l;
@@ -580,8 +597,9 @@ __global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const do
     if (d.q.ok) yout[p] = omega * (rp[p] / Dp[p]);
     return;
   }
-  const double ys = yin[p];
-  const double sum = q1_row_sum_dof<HY>(L, C, d, T, yin, ys);
+  double ys = yin[p];
+  if constexpr (PRO) ys = ys + cfac * ec[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)];
+  const double sum = q1_row_sum_dof<HY, PRO>(L, C, d, T, yin, ys, ec, cfac);
   const double dd = Dp[p];
   const double sy = dd * ys + sum;
   if (d.q.ok) yout[p] = ys + omega * ((rp[p] - sy) / dd);
@@ -606,18 +624,6 @@ __global__ void __launch_bounds__(BLK) k1_mg_restrict(Lay1 L, Rt1Const C, const 
 #pragma unroll
   for (int l = 0; l < NPL; ++l) acc += __shfl_sync(0xffffffffu, res, lane0 + l);
   if (d.q.ok && d.l == 0) rc[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)] = acc;
-}
-
-template <bool HY>
-__global__ void __launch_bounds__(BLK) k1_mg_prolong(Lay1 L, const double* __restrict__ ec, double* __restrict__ y,
-                                                     double cfac, const MinresState* st) {
-  constexpr int NPL = HY ? 8 : 4;
-  if (st && st->done) return;
-  const Cell1 q = owned_cell1(L);
-  if (!q.ok) return;
-  const double e = cfac * ec[q.i + L.NX * (q.j + L.NY * q.kl)];
-#pragma unroll
-  for (int l = 0; l < NPL; ++l) y[q.c * NPL + l] = y[q.c * NPL + l] + e;
 }
 
 // cell-level transmissibilities below the Q1 level: Galerkin with cell-wise constant prolongation.  The two L2

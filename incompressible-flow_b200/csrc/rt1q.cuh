@@ -35,6 +35,12 @@ struct QTab {
   double OOF[3][3][4]; // 3-D: OF[qe][te] * OF[qf][tf] at [qe][qf][te + 2 tf]
 };
 
+// 3-D products of the transverse open bases (QTab::OO / QTab::OOF) in constant memory: the rolled quadrature loops
+// index them with a run-time point index (a dynamically indexed kernel parameter would be copied to local memory)
+__constant__ double c_OO3[4][4][4];
+__constant__ double c_OOF3[3][3][4];
+__constant__ double c_WF3[3][3];   // fw[qe] * fw[qf] of the 3-D face rule
+
 template <bool HY>
 struct QD {
   static constexpr int NQ = HY ? 4 : 3;     // mass-rule points per direction
@@ -204,7 +210,8 @@ __global__ void __launch_bounds__(BLK) k1_schur_diag(Lay1 L, Rt1Const C, const d
 // (Round 1's version ran one thread per cell through all three directions: 128 registers + 676 B of spills,
 // scattered 8-byte loads of the 64 c_q -- 9 % of the HBM roofline.)
 // ---------------------------------------------------------------------------------------
-constexpr int K1Q_TC = 64;  // cells per CTA
+constexpr int K1Q_TC = 32;  // cells per CTA: one warp per direction (registers are split per SM sub-partition:
+                            // 3-warp CTAs at <= 96 registers keep 18 warps per SM resident, 6-warp CTAs at 112 only 12)
 
 template <bool HY>
 struct K1QS {
@@ -215,44 +222,71 @@ struct K1QS {
   static constexpr int SMEM_DOUBLES = K1Q_TC * RS + K1Q_TC * PS + ND * K1Q_TC * PS;
 };
 
-// rl: the cell's c_q in shared memory; oo2: QTab::OO (products of the transverse open bases, host-computed doubles)
+// rl: the cell's c_q in shared memory.  3-D: the 16 transverse point pairs run as a ROLLED loop (a fully unrolled
+// body is 1600 instructions per direction, executed once per thread: ncu showed the warps starving on instruction
+// fetch, stall_no_instruction 4.6 per issue); 2-D (9 points) stays unrolled.
 template <bool HY, int D>
 __device__ __forceinline__ void elem_apply(const QTab& tb, const double* rl, const double (&xl)[12], double (&yl)[12]) {
   using R = QDir<HY, D>;
   constexpr int NOE = R::no(R::E), NOF = R::no(R::F);
 #pragma unroll
   for (int n = 0; n < 12; ++n) yl[n] = 0.0;
+  if constexpr (HY) {
+#pragma unroll 1
+    for (int p = 0; p < 16; ++p) {
+      const int qe = p & 3, qf = p >> 2;
+      const double* oo = c_OO3[qe][qf];
+      const double o0 = oo[0], o1 = oo[1], o2 = oo[2], o3 = oo[3];
+      double v[3];
 #pragma unroll
-  for (int qf = 0; qf < R::nq(R::F); ++qf) {
-    // keep the shared-memory loads of one qf slab together with their arithmetic: without this fence the
-    // scheduler hoists all 64 c_q loads to the top (158 registers; 3 CTAs per SM need <= 112)
-    asm volatile("" ::: "memory");
-#pragma unroll
-    for (int qe = 0; qe < R::nq(R::E); ++qe) {
-      double oo[NOE * NOF], v[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int tf = 0; tf < NOF; ++tf)
-#pragma unroll
-        for (int te = 0; te < NOE; ++te) {
-          const double o2 = HY ? tb.OO[qe][qf][te + NOE * tf] : ob<HY>(tb, R::E, qe, te) * ob<HY>(tb, R::F, qf, tf);
-          oo[te + NOE * tf] = o2;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) v[i] = __fma_rn(o2, xl[i + 3 * (te + NOE * tf)], v[i]);
-        }
+      for (int i = 0; i < 3; ++i)
+        v[i] = __fma_rn(o3, xl[i + 9], __fma_rn(o2, xl[i + 6], __fma_rn(o1, xl[i + 3], __fma_rn(o0, xl[i], 0.0))));
       double r[3] = {0.0, 0.0, 0.0};
       const double* rq = rl + qe * R::sq(R::E) + qf * R::sq(R::F);
 #pragma unroll
-      for (int qd = 0; qd < QD<HY>::NQ; ++qd) {
+      for (int qd = 0; qd < 4; ++qd) {
         const double u = __fma_rn(tb.C[qd][2], v[2], __fma_rn(tb.C[qd][1], v[1], tb.C[qd][0] * v[0]));
         const double cu = rq[qd * R::sq(D)] * u;
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] = __fma_rn(tb.C[qd][i], cu, r[i]);
       }
 #pragma unroll
-      for (int t = 0; t < NOE * NOF; ++t)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) yl[i + 3 * t] = __fma_rn(oo[t], r[i], yl[i + 3 * t]);
+      for (int i = 0; i < 3; ++i) {
+        yl[i] = __fma_rn(o0, r[i], yl[i]);
+        yl[i + 3] = __fma_rn(o1, r[i], yl[i + 3]);
+        yl[i + 6] = __fma_rn(o2, r[i], yl[i + 6]);
+        yl[i + 9] = __fma_rn(o3, r[i], yl[i + 9]);
+      }
     }
+  } else {
+#pragma unroll
+    for (int qf = 0; qf < R::nq(R::F); ++qf)
+#pragma unroll
+      for (int qe = 0; qe < R::nq(R::E); ++qe) {
+        double oo[NOE * NOF], v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+          for (int te = 0; te < NOE; ++te) {
+            const double o2 = ob<HY>(tb, R::E, qe, te) * ob<HY>(tb, R::F, qf, tf);
+            oo[te + NOE * tf] = o2;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[i] = __fma_rn(o2, xl[i + 3 * (te + NOE * tf)], v[i]);
+          }
+        double r[3] = {0.0, 0.0, 0.0};
+        const double* rq = rl + qe * R::sq(R::E) + qf * R::sq(R::F);
+#pragma unroll
+        for (int qd = 0; qd < QD<HY>::NQ; ++qd) {
+          const double u = __fma_rn(tb.C[qd][2], v[2], __fma_rn(tb.C[qd][1], v[1], tb.C[qd][0] * v[0]));
+          const double cu = rq[qd * R::sq(D)] * u;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) r[i] = __fma_rn(tb.C[qd][i], cu, r[i]);
+        }
+#pragma unroll
+        for (int t = 0; t < NOE * NOF; ++t)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) yl[i + 3 * t] = __fma_rn(oo[t], r[i], yl[i + 3 * t]);
+      }
   }
 }
 
@@ -362,7 +396,7 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool 
 }
 
 template <bool HY, bool DOT>
-__global__ void __launch_bounds__(K1QS<HY>::THREADS, HY ? 3 : 4)
+__global__ void __launch_bounds__(K1QS<HY>::THREADS) __maxnreg__(HY ? 96 : 80)
 k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam, const double* __restrict__ Kx,
             const double* __restrict__ Ky, const double* __restrict__ Kz, double gx, double gy, double gz,
             const double* __restrict__ x, double* __restrict__ y, double* __restrict__ yup,
@@ -576,37 +610,53 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
   double cl[NT], ch[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) { cl[t] = 0.0; ch[t] = 0.0; }
+  // face quadrature: traces at the point (fma chains over the face's NT nodes), upwind flux, back to the nodes.
+  // 3-D: 9 points as a rolled loop (instruction-fetch friendly, like elem_apply); 2-D: 2 points, unrolled.
+  auto face_point = [&](const double (&oo)[NT], double w) {
+    double unl = 0.0, unh = 0.0, g1l = 0.0, g2l = 0.0, g1h = 0.0, g2h = 0.0;
 #pragma unroll
-  for (int qf = 0; qf < NFF; ++qf)
-#pragma unroll
-    for (int qe = 0; qe < NFE; ++qe) {
-      double oo[NT];
-      double unl = 0.0, unh = 0.0, g1l = 0.0, g2l = 0.0, g1h = 0.0, g2h = 0.0;
-#pragma unroll
-      for (int tf = 0; tf < NOF; ++tf)
-#pragma unroll
-        for (int te = 0; te < NOE; ++te) {
-          const int t = te + NOE * tf;
-          const double oe = (NFE == 1) ? 1.0 : tb.OF[qe][te], of = (NFF == 1) ? 1.0 : tb.OF[qf][tf];
-          oo[t] = (NFE == 1 || NFF == 1) ? oe * of : tb.OOF[qe][qf][t];
-          unl += ulo[t] * oo[t]; unh += uhi[t] * oo[t];
-          g1l += gn_lo[t] * oo[t]; g2l += go0[t] * oo[t];   // lower face: element 1 = lower cell, element 2 = this cell
-          g1h += go1[t] * oo[t]; g2h += gn_hi[t] * oo[t];   // upper face: element 1 = this cell
-        }
-      const double w = ((NFE == 1) ? 1.0 : tb.fw[qe]) * ((NFF == 1) ? 1.0 : tb.fw[qf]);
-      {
-        const double a = 0.5 * unl, b = 0.5 * fabs(unl);
-        const double fl = (w * (a + b)) * g1l - (w * (b - a)) * g2l;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) cl[t] += fl * oo[t];
-      }
-      {
-        const double a = 0.5 * unh, b = 0.5 * fabs(unh);
-        const double fh = (w * (a + b)) * g1h - (w * (b - a)) * g2h;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) ch[t] += fh * oo[t];
-      }
+    for (int t = 0; t < NT; ++t) {
+      unl = __fma_rn(ulo[t], oo[t], unl); unh = __fma_rn(uhi[t], oo[t], unh);
+      g1l = __fma_rn(gn_lo[t], oo[t], g1l); g2l = __fma_rn(go0[t], oo[t], g2l);   // lower face: element 1 = lower cell, 2 = this cell
+      g1h = __fma_rn(go1[t], oo[t], g1h); g2h = __fma_rn(gn_hi[t], oo[t], g2h);   // upper face: element 1 = this cell
     }
+    {
+      const double a = 0.5 * unl, b = 0.5 * fabs(unl);
+      const double fl = (w * (a + b)) * g1l - (w * (b - a)) * g2l;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) cl[t] = __fma_rn(fl, oo[t], cl[t]);
+    }
+    {
+      const double a = 0.5 * unh, b = 0.5 * fabs(unh);
+      const double fh = (w * (a + b)) * g1h - (w * (b - a)) * g2h;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ch[t] = __fma_rn(fh, oo[t], ch[t]);
+    }
+  };
+  if constexpr (HY) {
+#pragma unroll 1
+    for (int p = 0; p < 9; ++p) {
+      const int qf = p / 3, qe = p - 3 * qf;
+      const double* o = c_OOF3[qe][qf];
+      const double oo[NT] = {o[0], o[1], o[2], o[3]};
+      face_point(oo, c_WF3[qe][qf]);
+    }
+  } else {
+#pragma unroll
+    for (int qf = 0; qf < NFF; ++qf)
+#pragma unroll
+      for (int qe = 0; qe < NFE; ++qe) {
+        double oo[NT];
+#pragma unroll
+        for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+          for (int te = 0; te < NOE; ++te) {
+            const double oe = (NFE == 1) ? 1.0 : tb.OF[qe][te], of = (NFF == 1) ? 1.0 : tb.OF[qf][tf];
+            oo[te + NOE * tf] = oe * of;
+          }
+        face_point(oo, ((NFE == 1) ? 1.0 : tb.fw[qe]) * ((NFF == 1) ? 1.0 : tb.fw[qf]));
+      }
+  }
 #pragma unroll
   for (int tf = 0; tf < NOF; ++tf)
 #pragma unroll
@@ -630,7 +680,7 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
 // (Round 1's version: one thread per cell through all directions, 254 -> 128 registers with spills, 17 % of the HBM
 // roofline.)
 template <bool HY, bool RATE>
-__global__ void __launch_bounds__(K1Q_TC * (HY ? 3 : 2), HY ? 3 : 4)
+__global__ void __launch_bounds__(K1Q_TC * (HY ? 3 : 2)) __maxnreg__(HY ? 96 : 80)
 k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x, const double* __restrict__ phi,
         const double* __restrict__ Sin, const double* __restrict__ Fin, double* __restrict__ Sout,
         double* __restrict__ Fout) {

@@ -6,6 +6,7 @@
 #include <iostream>
 #include <vector>
 
+#include "dofmap.hpp"
 #include "param.hpp"
 #include "utilities.hpp"
 
@@ -79,6 +80,37 @@ int main(int argc, char** argv) {
     p.init_arrays();
     CHECK(p.K_array_x[11] == 2.5 && p.K_array_y[0] == 1.0 && p.K_array_z == nullptr && p.phi_array[5] == 1e-3);
     std::cout << "ok init_arrays" << std::endl;
+  }
+  {  // MFEM numbering <-> native layout, identified geometrically from the element interface (dofmap.hpp): the shim
+     // space is scrambled (random permutation, random orientation of the RT dofs, outward-pointing lower-face bases)
+     // and the map has to undo exactly that
+    for (int dim = 2; dim <= 3; ++dim)
+      for (int order = 0; order <= 1; ++order)
+        for (int rt = 0; rt <= 1; ++rt) {
+          const int n[3] = {5, 4, dim == 3 ? 3 : 1};
+          const double size[3] = {10.0, 6.0, 4.5};
+          mfem::Mesh* mesh = dim == 2 ? new mfem::Mesh(n[0], n[1], mfem::Element::QUADRILATERAL, 1, size[0], size[1])
+                                      : new mfem::Mesh(n[0], n[1], n[2], mfem::Element::HEXAHEDRON, 1, size[0], size[1], size[2]);
+          mfem::FiniteElementCollection* fec = rt ? (mfem::FiniteElementCollection*)new mfem::RT_FECollection(order, dim)
+                                                   : (mfem::FiniteElementCollection*)new mfem::L2_FECollection(order, dim);
+          mfem::FiniteElementSpace fes(mesh, fec);
+          const DofMap id = build_dofmap(fes, rt, order, dim, n, size);
+          CHECK(id.identity);  // unscrambled shim space = native layout
+          fes.SetScramble(17 + dim + 2 * order + rt);
+          const DofMap m = build_dofmap(fes, rt, order, dim, n, size);
+          CHECK(!m.identity);
+          const int nd = fes.GetVSize();
+          std::vector<double> nat(nd), own(nd), back(nd), again(nd);
+          for (int i = 0; i < nd; ++i) nat[i] = std::sin(0.37 * i) + 2.0;
+          fes.FromNative(nat.data(), own.data());   // the same field in the scrambled numbering
+          m.to_native(own.data(), back.data());
+          for (int i = 0; i < nd; ++i) CHECK(back[i] == nat[i]);
+          m.from_native(nat.data(), again.data());
+          for (int i = 0; i < nd; ++i) CHECK(again[i] == own[i]);
+          delete fec;
+          delete mesh;
+        }
+    std::cout << "ok dofmap" << std::endl;
   }
   return 0;
 }

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "config.hpp"
+#include "dofmap.hpp"
 #include "param.hpp"
 #include "pressure_solver.hpp"
 #include "saturation_solver.hpp"
@@ -28,18 +29,26 @@ double seconds_since(const chrono::steady_clock::time_point& t0) {
 // [REF src/run_serial.cpp:123-127] [REF src/param.hpp:413-442]: every nodal evaluation of an element overwrites
 // the cell's entry, so the value that survives is the one of the element's LAST local dof [MFEM-recall:
 // NodalFiniteElement::Project loops over the dofs in order].  DG_0: the cell value; DG-Q1: local dof 2^dim - 1.
-void output_saturation_cells(const Param& p, const Vector& S, int ti) {
+void output_saturation_cells(const Param& p, const Vector& S_own, const DofMap& map, int ti) {
   const string phase = p.two_phase_flow ? "2phase" : "1phase";
   const string fname = string(p.outdir) + "/saturation_" + p.extra + "_" + d2s(p.spacedim) + "D_" + phase + "_" +
                        d2s(ti, 0, 0, 0, 6) + ".bin";
   const int n = p.get_n_cells();
-  const int nsl = S.Size() / n;
+  const int nsl = S_own.Size() / n;
+  // cell-major view of the dofs (the space's own numbering need not be: dofmap.hpp)
+  std::vector<double> nat;
+  const double* S = S_own.GetData();
+  if (!map.identity) {
+    nat.resize(S_own.Size());
+    map.to_native(S_own.GetData(), nat.data());
+    S = nat.data();
+  }
   if (nsl == 1) {
-    write_binary(fname.c_str(), n, S.GetData());
+    write_binary(fname.c_str(), n, S);
     return;
   }
   std::vector<double> in_cells(n);
-  for (int c = 0; c < n; ++c) in_cells[c] = S.GetData()[(long)c * nsl + nsl - 1];
+  for (int c = 0; c < n; ++c) in_cells[c] = S[(long)c * nsl + nsl - 1];
   write_binary(fname.c_str(), n, in_cells.data());
 }
 }  // namespace
@@ -102,7 +111,10 @@ void run_serial(int argc, char** argv) {
   GridFunctionCoefficient saturation(&S);
   VectorGridFunctionCoefficient velocity(&V);
 
-  if (p.saturation_steps > 0) output_saturation_cells(p, S, 0);
+  const int ncell_dir[3] = {p.nx, p.ny, p.nz};
+  const double size_dir[3] = {p.sx, p.sy, p.sz};
+  const DofMap s_map = build_dofmap(S_space, false, p.order_s, dim, ncell_dir, size_dir);
+  if (p.saturation_steps > 0) output_saturation_cells(p, S, s_map, 0);
 
   const auto global_time_loop = chrono::steady_clock::now();
   const int nt = (int)ceil(p.t_final / p.dt_global);
@@ -111,7 +123,7 @@ void run_serial(int argc, char** argv) {
     PressureSolver(block_offsets, *mesh, p, V_space, P_space, saturation, x);
     SaturationSolver(p, S, velocity, ti, p.dt_global);
 
-    if (p.saturation_steps > 0 && ti % p.saturation_steps == 0) output_saturation_cells(p, S, ti);
+    if (p.saturation_steps > 0 && ti % p.saturation_steps == 0) output_saturation_cells(p, S, s_map, ti);
     cout << "time step " << ti << " is done" << endl;
 
     if (S.CheckFinite() > 0) {

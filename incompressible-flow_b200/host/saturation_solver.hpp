@@ -1,5 +1,5 @@
-// saturation_solver.hpp -- SaturationSolver with the reference's signature
-// [REF src/saturation_solver.hpp:9-11], executed by the B200 library through the C ABI.
+// saturation_solver.hpp -- SaturationSolver / ParSaturationSolver with the reference's signatures
+// [REF src/saturation_solver.hpp:9-11,14-16], executed by the B200 library through the C ABI.
 #pragma once
 #include "config.hpp"
 
@@ -7,3 +7,6 @@ struct Param;
 
 void SaturationSolver(const Param& param, mfem::GridFunction& S, mfem::VectorCoefficient& velocity, int global_ti,
                       double global_dt);
+
+void ParSaturationSolver(const Param& param, mfem::ParGridFunction& S, mfem::VectorCoefficient& velocity, int global_ti,
+                         double global_dt, mfem::VisItDataCollection& visit);

@@ -21,7 +21,7 @@ def host_bins(native_lib):
 def test_host_selftest(host_bins, tmp_path):
     out = subprocess.run([host_bins[1], str(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    for name in ("defaults", "options", "binary_io", "init_arrays"):
+    for name in ("defaults", "options", "binary_io", "init_arrays", "dofmap"):
         assert f"ok {name}" in out.stdout
 
 
@@ -145,3 +145,29 @@ def test_driver_run_dgq1(pkg, orc, host_bins, tmp_path, dim):
         dump = np.fromfile(out / f"saturation_q_{dim}D_2phase_{ti:06d}.bin", dtype=np.float32)
         want = S.reshape(n, nsl)[:, nsl - 1]
         assert dump.shape == (n,) and np.allclose(dump, want, rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spaces", ["0 0 0", "1 1 0", "1 1 1"])
+def test_driver_with_foreign_dof_numbering(host_bins, tmp_path, spaces):
+    """The reference hands the solvers vectors in MFEM's numbering (RT dofs by mesh entity, face dofs oriented by the
+    face's first element).  IMPES_COMPAT_SCRAMBLE makes the MFEM shim number its spaces with a random permutation and
+    random RT orientations; the adapter's dof maps (host/dofmap.cpp: identified from GetElementDofs / GetNodes /
+    CalcVShape, i.e. MFEM's public element interface) must make the run indistinguishable: same iteration counts,
+    bit-identical dumps."""
+    ov, op, os_ = spaces.split()
+    runs = []
+    for seed in ("0", "5"):
+        out = tmp_path / f"o{seed}"
+        args = [host_bins[0], "-d", "3", "-nx", "6", "-ny", "5", "-nz", "6", "-sx", "6", "-sy", "5", "-sz", "6", "-ov", ov, "-op", op,
+                "-os", os_, "-two-phase", "-tf", "1.0", "-dtg", "0.5", "-dtl", "0.05", "-vsg", "0", "-outdir", str(out), "-extra", "s",
+                "-inj-xcen", "0", "-inj-zcen", "0", "-inj-ycen", "0", "-inj-h", "5", "-inj-r", "1", "-pro-xcen", "6", "-pro-zcen", "6",
+                "-pro-ycen", "0", "-pro-h", "5", "-pro-r", "1", "-sat-source", "0.5", "-darcy-maxiter", "5000"]
+        o = subprocess.run(args, capture_output=True, text=True, timeout=300, env=dict(os.environ, IMPES_COMPAT_SCRAMBLE=seed))
+        assert o.returncode == 0, o.stdout + o.stderr
+        its = re.findall(r"Darcy solver converged\. Iter = (\d+)\. Final norm = (\S+)\.", o.stdout)
+        dumps = [np.fromfile(out / f"saturation_s_3D_2phase_{ti:06d}.bin", dtype=np.float32) for ti in (1, 2)]
+        runs.append((its, dumps))
+    assert len(runs[0][0]) == 2 and runs[0][0] == runs[1][0]
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert a.size == 180 and np.array_equal(a, b)
