@@ -432,12 +432,14 @@ def main():
     ncl = (ld.n_s // (2 ** d.dim)) if d.order_s == 1 else ld.n_s
     rl = rooflines_from_profile(kern, d.dim, ncl, ld.n_v + ld.n_p, peak, traffic_table())
     iso = None
-    if rank == 0 and not args.no_extras:
-        # cross-check: the same kernels alone, L2 flushed before every launch
+    if not args.no_extras:
+        # cross-check: the same kernels alone, L2 flushed before every launch.  EVERY rank takes part: K1 carries the
+        # halo exchange and the all-reduce of its fused dot (a rank-0-only call would wait for its neighbours forever)
         iso = {}
         for kid, nm in ((abi.KERNEL_DARCY_APPLY, "K1"), (abi.KERNEL_MINRES_UPDATE, "K2"), (abi.KERNEL_SAT_SUBSTEP, "K6")):
             a, m = s.time_kernel(kid, 5, True)
-            iso[nm] = rnd(a * 1e3, 4)
+            iso[nm] = rnd(max_over_ranks(a) * 1e3, 4)
+    barrier()
     s.close()
     roofline = None
     for r in rl:

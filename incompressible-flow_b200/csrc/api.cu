@@ -87,6 +87,11 @@ struct impes_ctx {
   double *x = nullptr, *v0 = nullptr, *v1 = nullptr, *w0 = nullptr, *w1 = nullptr, *q = nullptr, *u1 = nullptr;
   double* tmpv = nullptr;  // scratch dvec for operator-level entry points
   double* partial = nullptr;
+  double* partial_u = nullptr;  // per-chunk velocity part of <v0, P v0> (k_minres_b_dot), n_u_chunks entries
+  int n_u_chunks = 0;       // chunks that hold velocity entries
+  int n_u_chunks_all = 0;   // chunks of the whole vector (grid of k_minres_b_dot)
+  bool lazy_u = false;          // DG-Q1 path: u = P v stays unscaled in memory (MinresState::mu)
+  bool fold_dot = false;        // RT1/Q1 + multigrid: beta^2 is folded into k_minres_b and the last V-cycle sweep
   double* scal = nullptr;  // [0] alpha, [1] beta^2
   unsigned* ticket = nullptr;
   MinresState* st = nullptr;  // [2]
@@ -160,6 +165,16 @@ namespace {
       return IMPES_ERR_NCCL;                                                      \
     }                                                                             \
   } while (0)
+
+// ncclGroupStart ... ncclGroupEnd that cannot be left open by an early error return (a dangling group would make the
+// next collective hang): the guard closes the group when it goes out of scope.
+struct NcclGroup {
+  NcclShim& n;
+  bool open;
+  explicit NcclGroup(NcclShim& n_) : n(n_), open(n_.GroupStart() == 0) {}
+  int end() { open = false; return n.GroupEnd(); }
+  ~NcclGroup() { if (open) n.GroupEnd(); }
+};
 
 #define RET_IF(x)            \
   do {                       \
@@ -361,7 +376,8 @@ int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool sen
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   const size_t pl = (size_t)L.plane * mult;
   Scope sc(h, KI_COMM, 1);
-  NK(h->nccl.GroupStart());
+  NcclGroup grp(h->nccl);
+  if (!grp.open) { h->err = "ncclGroupStart failed"; return IMPES_ERR_NCCL; }
   if (send_up_top_owned) {
     if (up >= 0) NK(h->nccl.Send(base + pl * L.nzl, pl, ncclFloat64, up, h->comm, h->stream));
     if (dn >= 0) NK(h->nccl.Recv(base, pl, ncclFloat64, dn, h->comm, h->stream));
@@ -370,7 +386,7 @@ int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool sen
     if (dn >= 0) NK(h->nccl.Send(base + pl, pl, ncclFloat64, dn, h->comm, h->stream));
     if (up >= 0) NK(h->nccl.Recv(base + pl * (L.nzl + 1), pl, ncclFloat64, up, h->comm, h->stream));
   }
-  NK(h->nccl.GroupEnd());
+  NK(grp.end());
   return 0;
 }
 // halo of a Darcy vector before K1: p ghost-below, uz ghost-below (from the lower rank's top owned
@@ -380,7 +396,8 @@ int halo_darcy(impes_ctx* h, double* v) {
   const Lay& L = h->L;
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   Scope sc(h, KI_COMM, 1);
-  NK(h->nccl.GroupStart());
+  NcclGroup grp(h->nccl);
+  if (!grp.open) { h->err = "ncclGroupStart failed"; return IMPES_ERR_NCCL; }
   if (up >= 0) {
     NK(h->nccl.Send(v + L.off_p + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
     NK(h->nccl.Send(v + L.off_z + L.plane * L.nzl, (size_t)L.plane, ncclFloat64, up, h->comm, h->stream));
@@ -391,7 +408,7 @@ int halo_darcy(impes_ctx* h, double* v) {
     NK(h->nccl.Recv(v + L.off_z, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
     NK(h->nccl.Send(v + L.off_z + L.plane, (size_t)L.plane, ncclFloat64, dn, h->comm, h->stream));
   }
-  NK(h->nccl.GroupEnd());
+  NK(grp.end());
   return 0;
 }
 // dvec1 halo before K1 (rt1.cuh): p ghost-below cell plane; uz ghost node planes below (2: the lower cell's
@@ -402,7 +419,8 @@ int halo_darcy1(impes_ctx* h, double* v) {
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   const size_t pz = (size_t)L.gz0 * L.gz1, pp = (size_t)L.plane * L.npl;
   Scope sc(h, KI_COMM, 1);
-  NK(h->nccl.GroupStart());
+  NcclGroup grp(h->nccl);
+  if (!grp.open) { h->err = "ncclGroupStart failed"; return IMPES_ERR_NCCL; }
   if (up >= 0) {
     NK(h->nccl.Send(v + L.off_p + pp * L.nzl, pp, ncclFloat64, up, h->comm, h->stream));
     NK(h->nccl.Send(v + L.off_z + pz * (2 * L.nzl), 2 * pz, ncclFloat64, up, h->comm, h->stream));
@@ -413,7 +431,7 @@ int halo_darcy1(impes_ctx* h, double* v) {
     NK(h->nccl.Recv(v + L.off_z, 2 * pz, ncclFloat64, dn, h->comm, h->stream));
     NK(h->nccl.Send(v + L.off_z + pz * 2, pz, ncclFloat64, dn, h->comm, h->stream));
   }
-  NK(h->nccl.GroupEnd());
+  NK(grp.end());
   return 0;
 }
 int allreduce_scalar(impes_ctx* h, double* p) {
@@ -570,8 +588,7 @@ int launch_skew_sweep(impes_ctx* h, double* y, int fwd, int bwd, const MinresSta
 
 template <int NPS, bool HY>
 void launch_sgs_tma_t(impes_ctx* h, double* y, int fwd, int bwd, const MinresState* st) {
-  k_sgs_tma<NPS, HY><<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(h->L, h->pack, h->T, y, getenv("IMPES_SGS_NOSTORE") ? -h->sgs_ns : h->sgs_ns, getenv("IMPES_SGS_NOTMA") ? -h->sgs_yp : h->sgs_yp, fwd,
-                                                                    bwd, st);
+  k_sgs_tma<NPS, HY><<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(h->L, h->pack, h->T, y, h->sgs_ns, h->sgs_yp, fwd, bwd, st);
 }
 void launch_sgs_tma(impes_ctx* h, double* y, int fwd, int bwd, const MinresState* st) {
   const bool hy = h->L.has_y != 0;
@@ -660,7 +677,8 @@ int mg_halo(impes_ctx* h, double* buf, size_t pe, int nz) {
   if (L.nranks == 1) return 0;
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   Scope sc(h, KI_COMM, 1);
-  NK(h->nccl.GroupStart());
+  NcclGroup grp(h->nccl);
+  if (!grp.open) { h->err = "ncclGroupStart failed"; return IMPES_ERR_NCCL; }
   if (up >= 0) {
     NK(h->nccl.Send(buf + pe * (size_t)(nz - 1), pe, ncclFloat64, up, h->comm, h->stream));
     NK(h->nccl.Recv(buf + pe * (size_t)nz, pe, ncclFloat64, up, h->comm, h->stream));
@@ -669,7 +687,7 @@ int mg_halo(impes_ctx* h, double* buf, size_t pe, int nz) {
     NK(h->nccl.Send(buf, pe, ncclFloat64, dn, h->comm, h->stream));
     NK(h->nccl.Recv(buf - pe, pe, ncclFloat64, dn, h->comm, h->stream));
   }
-  NK(h->nccl.GroupEnd());
+  NK(grp.end());
   return 0;
 }
 // every rank contributes planes [off[r], off[r]+cnt[r]) of `full` (pe doubles per plane); afterwards all
@@ -678,13 +696,14 @@ int mg_gather(impes_ctx* h, double* full, size_t pe) {
   const Lay& L = h->L;
   if (L.nranks == 1) return 0;
   Scope sc(h, KI_COMM, 1);
-  NK(h->nccl.GroupStart());
+  NcclGroup grp(h->nccl);
+  if (!grp.open) { h->err = "ncclGroupStart failed"; return IMPES_ERR_NCCL; }
   for (int r = 0; r < L.nranks; ++r) {
     if (r == L.rank) continue;
     NK(h->nccl.Send(full + pe * (size_t)h->mg_goff[L.rank], pe * (size_t)h->mg_gcnt[L.rank], ncclFloat64, r, h->comm, h->stream));
     NK(h->nccl.Recv(full + pe * (size_t)h->mg_goff[r], pe * (size_t)h->mg_gcnt[r], ncclFloat64, r, h->comm, h->stream));
   }
-  NK(h->nccl.GroupEnd());
+  NK(grp.end());
   return 0;
 }
 // this rank's part of the first replicated level, addressed like a distributed level
@@ -709,7 +728,7 @@ MgLevel mg_view(const impes_ctx* h, const MgLevel& v) {
 // Multi-GPU: levels < mg_g live on slabs (ghost planes refreshed before every sweep that reads neighbours),
 // level mg_g is assembled on every rank by a gather and the levels below it run replicated -- the same
 // arithmetic as on one GPU, so the result does not depend on the number of GPUs.
-int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
+int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, bool dot = false) {
   const Lay& L = h->L;
   std::vector<MgLevel>& mg = h->mg;
   const int nl = (int)mg.size();
@@ -799,8 +818,13 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
       double* out = (s & 1) ? qb : qa;
       if (multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
       Scope sc(h, KI_MGQ_JACOBI, 1);
-      if (L.has_y) k1_mg_jacobi<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
-      else k1_mg_jacobi<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+      if (dot && s + 1 == h->mg_nu) {  // last sweep: finishes beta^2 = <v0, P v0> (see k1_mg_jacobi<.., DOT>)
+        if (L.has_y) k1_mg_jacobi<true, false, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+        else k1_mg_jacobi<false, false, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+      } else {
+        if (L.has_y) k1_mg_jacobi<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+        else k1_mg_jacobi<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+      }
     }
   }
   return 0;
@@ -808,9 +832,9 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st) {
 
 // y_p = SchurPrec(r_p).  Parity mode: lexicographic symmetric GS; across slabs the sweep is pipelined
 // rank by rank (exact global ordering, so results do not depend on the number of GPUs).
-int schur_prec(impes_ctx* h, const double* r, double* y, const MinresState* st) {
+int schur_prec(impes_ctx* h, const double* r, double* y, const MinresState* st, bool dot = false) {
   const Lay& L = h->L;
-  if (h->d.schur_prec == IMPES_SCHUR_MG) return mg_vcycle(h, r, y, st);
+  if (h->d.schur_prec == IMPES_SCHUR_MG) return mg_vcycle(h, r, y, st, dot);
   if (L.nranks == 1) return launch_sgs(h, r, y, 1, 1, st);
   const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
   double* yp = y + h->vec_offp;
@@ -842,16 +866,35 @@ int dot_owned(impes_ctx* h, const double* a, const double* b, double* out, const
 int minres_iteration(impes_ctx* h, double* u1, double* q, double* v0, double* v1, double* w0, double* w1,
                      const MinresState* st_cur, MinresState* st_next) {
   RET_IF(darcy_apply(h, u1, q, true, st_cur));
-  {
-    Scope sc(h, KI_MINRES_B, 1);
-    k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, q, v0, v1, h->Md, q, h->scal + 0, st_cur);
+  if (h->fold_dot) {
+    // beta^2 = <v0, P v0> without a dot kernel: velocity part inside pass B, pressure part + final sum inside the last
+    // smoothing sweep of the V-cycle
+    {
+      Scope sc(h, KI_MINRES_B, 1);
+      const Lay1& Q = h->L1;
+      const long pz = (long)Q.gz0 * Q.gz1;
+      const long own_z0 = Q.off_z + 2 * pz, own_z1 = own_z0 + pz * (2 * Q.nzl + (Q.zhi == Q.NZ ? 1 : 0));
+      k_minres_b_dot<<<h->n_u_chunks_all, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, q, v0, v1, h->Md, q, h->scal + 0, st_cur,
+                                                               (long)Q.off_z, own_z0, own_z1, (long)Q.off_p, h->partial_u);
+    }
+    RET_IF(schur_prec(h, v0, q, st_cur, true));
+    RET_IF(allreduce_scalar(h, h->scal + 1));
+  } else {
+    {
+      Scope sc(h, KI_MINRES_B, 1);
+      k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, q, v0, v1, h->Md, q, h->scal + 0, st_cur);
+    }
+    RET_IF(schur_prec(h, v0, q, st_cur));
+    RET_IF(dot_owned(h, v0, q, h->scal + 1, st_cur));
   }
-  RET_IF(schur_prec(h, v0, q, st_cur));
-  RET_IF(dot_owned(h, v0, q, h->scal + 1, st_cur));
   {
     Scope sc(h, KI_MINRES_C, 1);
-    k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, w0, w1, u1, h->x, v0, q, h->scal + 0, h->scal + 1, st_cur,
-                                                   st_next, h->d.darcy_maxiter);
+    if (h->lazy_u)
+      k_minres_c<true><<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, w0, w1, u1, h->x, v0, q, h->scal + 0, h->scal + 1, st_cur,
+                                                           st_next, h->d.darcy_maxiter);
+    else
+      k_minres_c<false><<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, w0, w1, u1, h->x, v0, q, h->scal + 0, h->scal + 1, st_cur,
+                                                            st_next, h->d.darcy_maxiter);
   }
   return 0;
 }
@@ -905,9 +948,13 @@ int build_minres_graph(impes_ctx* h) {
 
 int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
   auto t0 = std::chrono::steady_clock::now();
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
+  struct EventPair {  // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  CK(cudaEventCreate(&ev.a));
+  CK(cudaEventCreate(&ev.b));
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   CK(cudaEventRecord(e0, h->stream));
   RET_IF(update_coeff(h));
   const size_t nb = sizeof(double) * (size_t)h->vec_n;
@@ -927,7 +974,7 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
   {
     Scope sc(h, KI_MINRES_INIT, 1);
     k_minres_init<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->v1, h->u1, h->scal + 1, h->st + 0, h->d.darcy_rtol,
-                                                      h->d.darcy_atol);
+                                                      h->d.darcy_atol, h->lazy_u ? 1 : 0);
   }
   CK(cudaGetLastError());
   RET_IF(build_minres_graph(h));
@@ -936,8 +983,21 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
     CK(cudaMemcpyAsync(&hs, h->st + 0, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (hs.done) break;
-    if (h->d.darcy_print_level == 1 && h->L.rank == 0)
-      printf("MINRES: iteration %3d: ||r||_B = %g\n", hs.it, fabs(hs.eta));
+    if (h->d.darcy_print_level == 1) {
+      // MFEM prints the residual of EVERY iteration [MFEM-recall: MINRESSolver::Mult, print_level 1]: no batching --
+      // one pair of iterations per host check, both states read back
+      if (h->L.rank == 0 && hs.it == 0) printf("MINRES: iteration %3d: ||r||_B = %g\n", 0, fabs(hs.eta));
+      RET_IF(minres_pair(h));
+      MinresState h1;
+      CK(cudaMemcpyAsync(&h1, h->st + 1, sizeof h1, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(&hs, h->st + 0, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->L.rank == 0) {
+        printf("MINRES: iteration %3d: ||r||_B = %g\n", h1.it, fabs(h1.eta));
+        if (hs.it > h1.it) printf("MINRES: iteration %3d: ||r||_B = %g\n", hs.it, fabs(hs.eta));
+      }
+      continue;
+    }
     if (h->minres_exec && !h->profiling) {
       CK(cudaGraphLaunch(h->minres_exec, h->stream));
       h->launches += h->graph_launches;
@@ -953,8 +1013,6 @@ int pressure_solve_device(impes_ctx* h, impes_solve_stats* stats) {
   CK(cudaEventSynchronize(e1));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (stats) {
     stats->iterations = hs.it;
     stats->converged = hs.done == 1;
@@ -1203,7 +1261,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup, h->accA};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup, h->accA, h->partial_u};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   for (double* b : h->mg_bufs)
@@ -1589,6 +1647,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     CK(cudaFuncSetAttribute(k1q_apply_a<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
     CK(cudaFuncSetAttribute(k1q_apply_a<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
     h->sat_mode = 0;  // the DG-Q1 kernel always carries f(S)
+    h->lazy_u = !getenv("IMPES_NO_LAZY_U");
   }
   double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
   for (double** v : vecs) RET_IF(dev_alloc(h, v, h->vec_n));
@@ -1642,6 +1701,12 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   }
   RET_IF(dev_alloc(h, &h->partial, std::max(2 * L.nblk, h->grid_dofs1) + 8));
   RET_IF(dev_alloc(h, &h->scal, 8));
+  if (h->ord == 1 && d.schur_prec == IMPES_SCHUR_MG && !getenv("IMPES_NO_FOLD_DOT")) {
+    h->fold_dot = true;
+    h->n_u_chunks_all = (int)(((long)h->vec_n + DOT_CHUNK - 1) / DOT_CHUNK);
+    h->n_u_chunks = (int)(((long)h->vec_offp + DOT_CHUNK - 1) / DOT_CHUNK);
+    RET_IF(dev_alloc(h, &h->partial_u, h->n_u_chunks_all + 8));
+  }
   CK(cudaMalloc((void**)&h->ticket, sizeof(unsigned) * 4));
   CK(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned) * 4, h->stream));
   CK(cudaMalloc((void**)&h->st, sizeof(MinresState) * 4));  // [0,1] solver, [2] timing state, [3] sink
@@ -1649,7 +1714,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   {
     MinresState bs;
     memset(&bs, 0, sizeof bs);
-    bs.beta = 1.0; bs.eta = 1.0; bs.gamma0 = bs.gamma1 = 1.0; bs.m0 = bs.m1 = 1.0;
+    bs.beta = 1.0; bs.eta = 1.0; bs.gamma0 = bs.gamma1 = 1.0; bs.m0 = bs.m1 = 1.0; bs.mu = 1.0;
     const double sc[4] = {0.0, 0.0, 0.5, 1.0};
     CK(cudaMemcpyAsync(h->st + 2, &bs, sizeof bs, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->scal, sc, sizeof sc, cudaMemcpyHostToDevice, h->stream));
@@ -1971,12 +2036,14 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
     h->flush_n = (long)(256u << 20) / 8;  // 256 MiB > 126 MB L2
     CK(cudaMalloc((void**)&h->flushbuf, sizeof(double) * h->flush_n));
   }
-  const Lay& L = h->L;
   double sum = 0, mn = 1e300;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  const bool prof = h->profiling;
+  struct Guard {  // events destroyed and the profiling flag restored on every return path
+    impes_ctx* h; bool prof; cudaEvent_t a = nullptr, b = nullptr;
+    ~Guard() { h->profiling = prof; if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } guard{h, h->profiling};
+  CK(cudaEventCreate(&guard.a));
+  CK(cudaEventCreate(&guard.b));
+  cudaEvent_t e0 = guard.a, e1 = guard.b;
   h->profiling = false;
   if (kernel == IMPES_KERNEL_SAT_SUBSTEP && h->sat_mode == 0)  // f(S) is carried between sub-steps
     RET_IF(launch_frac(h, h->S[h->scur], h->F[h->scur]));
@@ -1991,11 +2058,19 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
         break;
       case IMPES_KERNEL_MINRES_UPDATE: {
         { Scope sc(h, KI_MINRES_B, 1);
+        if (h->fold_dot)
+          k_minres_b_dot<<<h->n_u_chunks_all, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
+                                                                   h->st + 2, 0L, 0L, 0L, 0L, h->partial_u);
+        else
         k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
                                                        h->st + 2); }
         Scope sc(h, KI_MINRES_C, 1);
-        k_minres_c<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->w0, h->w1, h->u1, h->tmpv, h->v0, h->q, h->scal + 2,
-                                                       h->scal + 3, h->st + 2, h->st + 3, 1 << 30);
+        if (h->lazy_u)
+          k_minres_c<true><<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->w0, h->w1, h->u1, h->tmpv, h->v0, h->q, h->scal + 2,
+                                                               h->scal + 3, h->st + 2, h->st + 3, 1 << 30);
+        else
+          k_minres_c<false><<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->w0, h->w1, h->u1, h->tmpv, h->v0, h->q, h->scal + 2,
+                                                                h->scal + 3, h->st + 2, h->st + 3, 1 << 30);
         break;
       }
       case IMPES_KERNEL_PREC_APPLY: {
@@ -2015,9 +2090,6 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (r >= 0) { sum += ms; mn = std::min<double>(mn, ms); }
   }
-  h->profiling = prof;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   CK(cudaGetLastError());
   if (ms_avg) *ms_avg = sum / reps;
   if (ms_min) *ms_min = mn;

@@ -41,6 +41,22 @@ __device__ __forceinline__ double block_tree_256(double v, double* sm) {
   return s;
 }
 
+// Ordered sum of entries t, t + 256, ... of p[0, n) by thread t: the loads of 8 terms are issued together (the tail of
+// a dot over 65k+ block partials was a chain of dependent L2 round trips), the additions stay sequential.
+__device__ __forceinline__ double ordered_partial_sum(const double* p, unsigned n) {
+  double acc = 0.0;
+  unsigned j = threadIdx.x;
+  for (; j + 7 * 256 < n; j += 8 * 256) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + j + u * 256);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  for (; j < n; j += 256) acc += __ldcg(p + j);
+  return acc;
+}
+
 // Block partial -> partial[blockIdx.x]; the last block to arrive adds all partials in index
 // order (thread t takes t, t+256, ...; then the same tree) and writes *out.  Deterministic:
 // which block is last does not matter.
@@ -57,8 +73,7 @@ __device__ __forceinline__ void finish_dot(double v, double* partial, double* ou
   __syncthreads();
   if (is_last) {
     __threadfence();
-    double a = 0.0;
-    for (unsigned j = threadIdx.x; j < gridDim.x; j += BLK) a += __ldcg(partial + j);
+    const double a = ordered_partial_sum(partial, gridDim.x);
     __syncthreads();
     const double tot = block_tree_256(a, sm);
     if (threadIdx.x == 0) {
@@ -343,10 +358,48 @@ __global__ void __launch_bounds__(BLK) k_minres_b(long n, long n_u, const double
   }
 }
 
+// The same pass with the velocity part of beta^2 = <v0, P v0> folded in (P_u = diag(M)^-1 is applied right here, so
+// v0_u and q_u never have to be read again by a dot kernel: 3/4 of that kernel's traffic).  One CTA per chunk of
+// DOT_CHUNK consecutive entries of the vector (a mapping that does not depend on the SM count, so the CPU checker can
+// follow it): thread t adds v0 q of entries t, t + 256, ... of its chunk in order, the CTA reduces with the canonical
+// tree and stores partial_u[chunk]; the pressure part and the final sum come from the last smoothing sweep of the
+// Schur preconditioner (k1_mg_jacobi<.., DOT>).  Entries in [x0, x1) u [x2, x3) are ghost layers (stale on several
+// GPUs) and padding; they are updated like everything else but left out of the sum.
+constexpr int DOT_CHUNK = 16384;
+__global__ void __launch_bounds__(BLK) k_minres_b_dot(long n, long n_u, const double* q_in,
+                                                      double* __restrict__ v0, const double* __restrict__ v1,
+                                                      const double* __restrict__ Md, double* q_out,
+                                                      const double* alpha_p, const MinresState* st,
+                                                      long x0, long x1, long x2, long x3, double* __restrict__ partial_u) {
+  if (st->done) return;
+  const double alpha = *alpha_p, beta = st->beta, m0 = st->m0, m1 = st->m1;
+  const long base = (long)blockIdx.x * DOT_CHUNK;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < DOT_CHUNK / BLK; ++k) {
+    const long i = base + threadIdx.x + k * BLK;
+    if (i < n) {
+      const double t = q_in[i] + (-beta) * (v0[i] * m0);
+      const double v = t + (-alpha) * (v1[i] * m1);
+      v0[i] = v;
+      if (i < n_u) {
+        const double qv = v / Md[i];
+        q_out[i] = qv;
+        const bool ghost = (i >= x0 && i < x1) || (i >= x2 && i < x3);
+        acc += ghost ? 0.0 : v * qv;
+      }
+    }
+  }
+  __shared__ double sm[BLK / 32];
+  const double s = block_tree_256(acc, sm);
+  if (threadIdx.x == 0) partial_u[blockIdx.x] = s;
+}
+
 // pass C: scalar recurrence + w/x update + scaling of the next Lanczos pair.
 //   w0 <- (-rho3/rho1) w0 + (-rho2/rho1) w1 + (1/rho1) u1 ; x += gamma1 eta w0 ;
 //   q *= 1/beta_new (becomes u1 of the next iteration: K1 and the halo exchange read it as is);
 //   the scaling v0 *= 1/beta_new (becomes v1) is lazy: only the factor is recorded (MinresState::m1)
+template <bool LAZYU>
 __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w0, const double* __restrict__ w1,
                                                   const double* __restrict__ u1, double* __restrict__ x,
                                                   double* __restrict__ v0, double* __restrict__ q,
@@ -369,12 +422,13 @@ __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w
   const double sigma1n = beta / rho1;
   const double etan = -sigma1n * eta;
   const double m = 1.0 / beta;
+  const double mu = st->mu;
   for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
     const double t = a * w0[i] + c * w1[i];
-    const double w = t + e * u1[i];
+    const double w = t + e * (LAZYU ? u1[i] * mu : u1[i]);
     w0[i] = w;
     x[i] += xf * w;
-    q[i] *= m;
+    if (!LAZYU) q[i] *= m;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     MinresState s = *st;
@@ -382,6 +436,7 @@ __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w
     s.gamma0 = gamma1; s.gamma1 = gamma1n;
     s.sigma0 = sigma1; s.sigma1 = sigma1n;
     s.m0 = st->m1; s.m1 = m;
+    s.mu = LAZYU ? m : 1.0;
     s.it = st->it + 1;
     s.done = (fabs(etan) <= s.norm_goal) ? 1 : (s.it >= maxiter ? 2 : 0);
     *st_next = s;
@@ -390,11 +445,12 @@ __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w
 
 // start of a solve: eta = beta = sqrt(<u1, v1>), goal = max(rtol*eta, atol); v1 /= beta, u1 /= beta.
 __global__ void __launch_bounds__(BLK) k_minres_init(long n, double* __restrict__ v1, double* __restrict__ u1,
-                                                     const double* bb_p, MinresState* st0, double rtol, double atol) {
+                                                     const double* bb_p, MinresState* st0, double rtol, double atol,
+                                                     int lazy_u) {
   const double beta = sqrt(*bb_p);
   const double goal = fmax(rtol * beta, atol);
   const bool done = beta <= goal;
-  if (!done) {  // u1 /= beta; v1 /= beta lazily through m1
+  if (!done && !lazy_u) {  // u1 /= beta (or lazily through mu); v1 /= beta lazily through m1
     const double m = 1.0 / beta;
     for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) u1[i] *= m;
   }
@@ -404,6 +460,7 @@ __global__ void __launch_bounds__(BLK) k_minres_init(long n, double* __restrict_
     s.gamma0 = 1.; s.gamma1 = 1.; s.sigma0 = 0.; s.sigma1 = 0.;
     s.norm_goal = goal;
     s.m0 = 1.0; s.m1 = done ? 1.0 : 1.0 / beta;
+    s.mu = (lazy_u && !done) ? 1.0 / beta : 1.0;
     s.it = 0;
     s.done = done ? 1 : 0;
     *st0 = s;

@@ -88,6 +88,10 @@ IMPES_HD int ix_c(const Lay& L, int i, int j, int kk) { return i + L.NX * (j + L
 struct MinresState {
   double beta, eta, gamma0, gamma1, sigma0, sigma1, norm_goal, eta0;
   double m0, m1;
+  double mu;  // lazy scaling of u = P v as well (DG-Q1 path only, 1 otherwise): K1 and pass C multiply the stored,
+              // UNscaled vector by mu on load -- the same rounded products the explicit scaling stored; pass C then
+              // neither reads nor writes q (a quarter of its traffic).  Round 1 rejected this for the RT0 K1 (its 13
+              // loads per cell became 30 % slower); the DG-Q1 K1 does ~1000 fp64 operations per thread and does not notice.
   int it;     // iterations completed
   int done;   // 0 running, 1 converged, 2 hit maxiter
 };

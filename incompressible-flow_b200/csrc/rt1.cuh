@@ -584,12 +584,19 @@ __device__ __forceinline__ double q1_row_sum_dof(const Lay1& L, const Rt1Const& 
 // PRO: the first post-smoothing sweep with the prolongation fused in: yin is the iterate before
 // y += cfac * ec(cell) (what k1_mg_prolong would have written, one whole pass over the level saved); a missing
 // neighbour contributes (y + e) * (b (b' 0)) = +-0 as before.
-template <bool HY, bool PRO = false>
+// DOT: the last sweep of a V-cycle inside MINRES also finishes beta^2 = <v0, P v0>: its right-hand side rp IS the
+// pressure part of v0 and its result the pressure part of P v0, so the products are formed here (canonical tree over
+// the CTA's 256 dofs -> partial_p[cta]); the last CTA adds tree(partial_u) (velocity part, from k_minres_b_dot) and
+// tree(partial_p) and writes the scalar.
+template <bool HY, bool PRO = false, bool DOT = false>
 __global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
                                                     const double* __restrict__ Dp, const double* __restrict__ rp,
                                                     const double* __restrict__ yin, double* __restrict__ yout,
                                                     double omega, int first, const MinresState* st,
-                                                    const double* __restrict__ ec = nullptr, double cfac = 0.0) {
+                                                    const double* __restrict__ ec = nullptr, double cfac = 0.0,
+                                                    double* partial_p = nullptr, const double* partial_u = nullptr,
+                                                    unsigned n_u_chunks = 0, double* out = nullptr,
+                                                    unsigned* ticket = nullptr) {
   if (st && st->done) return;
   const Dof1 d = owned_dof1<HY>(L);
   const int p = d.q.pb + d.l;
@@ -602,7 +609,32 @@ __global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const do
   const double sum = q1_row_sum_dof<HY, PRO>(L, C, d, T, yin, ys, ec, cfac);
   const double dd = Dp[p];
   const double sy = dd * ys + sum;
-  if (d.q.ok) yout[p] = ys + omega * ((rp[p] - sy) / dd);
+  const double rv = rp[p];
+  const double yn = ys + omega * ((rv - sy) / dd);
+  if (d.q.ok) yout[p] = yn;
+  if constexpr (DOT) {
+    __shared__ double sm[BLK / 32];
+    __shared__ int is_last;
+    const double s = block_tree_256(d.q.ok ? rv * yn : 0.0, sm);
+    if (threadIdx.x == 0) {
+      partial_p[blockIdx.x] = s;
+      __threadfence();
+      is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const double a = ordered_partial_sum(partial_u, n_u_chunks), b = ordered_partial_sum(partial_p, gridDim.x);
+      __syncthreads();
+      const double ta = block_tree_256(a, sm);
+      __syncthreads();
+      const double tb = block_tree_256(b, sm);
+      if (threadIdx.x == 0) {
+        *out = ta + tb;
+        *ticket = 0u;
+      }
+    }
+  }
 }
 
 // cell rhs = sum over the cell's dofs (local order) of the residual r - S y

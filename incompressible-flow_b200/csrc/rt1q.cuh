@@ -303,13 +303,15 @@ __device__ __forceinline__ void named_barrier_1() {
 template <bool HY, int D, bool DOT>
 __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool ok, const Rt1Const& C, const QTab& tb,
                                             const double* rl, const double* __restrict__ K, double geo,
-                                            const double* __restrict__ x, double* __restrict__ y,
+                                            const double* __restrict__ x, double mu, double* __restrict__ y,
                                             double* __restrict__ yup, const double* pc, double* ypd) {
   using R = QDir<HY, D>;
   using Q = QD<HY>;
   constexpr int NOE = R::no(R::E), NOF = R::no(R::F), NT = NOE * NOF;
   constexpr int DI = HY ? D : (D == 0 ? 0 : 1);  // index of the direction among the present ones
   constexpr int PS1 = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));  // stride between the two pressure dofs of a line
+  // mu: lazy MINRES scaling of the input vector (MinresState::mu; 1 outside MINRES): every entry is multiplied once,
+  // right after its load, so all arithmetic below sees the doubles an explicitly scaled vector would hold
   double xl[12], ttlo[NT];
   int cd = 0, nd = 1;
   // ---- every global load of the thread, then the barrier that publishes the staged data
@@ -321,9 +323,9 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool 
       const Line1 l = line_of<HY, D>(L, q, te, tf);
       const int t = te + NOE * tf;
       cd = l.cd; nd = l.nd;
-      xl[3 * t] = x[l.base];
-      xl[1 + 3 * t] = x[l.base + l.sd];
-      xl[2 + 3 * t] = x[l.base + 2 * l.sd];
+      xl[3 * t] = x[l.base] * mu;
+      xl[1 + 3 * t] = x[l.base + l.sd] * mu;
+      xl[2 + 3 * t] = x[l.base + 2 * l.sd] * mu;
     }
   const bool lo = cd > 0, hi = cd + 1 < nd;
 #pragma unroll
@@ -333,7 +335,7 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool 
       const Line1 l = line_of<HY, D>(L, q, te, tf);
       const double* pL = x + (q.pb - (lo ? l.pdn : 0) + l.lp);
       double tt = 0.0;
-      tt += C.Bv[0][2] * pL[0]; tt += C.Bv[1][2] * pL[l.ps];
+      tt += C.Bv[0][2] * (pL[0] * mu); tt += C.Bv[1][2] * (pL[l.ps] * mu);
       ttlo[te + NOE * tf] = tt;
     }
 #pragma unroll
@@ -348,7 +350,7 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool 
       const int t = te + NOE * tf;
       const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
       // B^T terms of the lower-face rows, completed before the element product
-      ttlo[t] += C.Bv[0][0] * pc[lp]; ttlo[t] += C.Bv[1][0] * pc[lp + PS1];
+      ttlo[t] += C.Bv[0][0] * (pc[lp] * mu); ttlo[t] += C.Bv[1][0] * (pc[lp + PS1] * mu);
       // eliminated boundary nodes enter the element product (and the pressure rows) with x = 0
       xl[3 * t] = lo ? xl[3 * t] : 0.0;
       xl[2 + 3 * t] = hi ? xl[2 + 3 * t] : 0.0;
@@ -363,7 +365,7 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool 
       const Line1 l = line_of<HY, D>(L, q, te, tf);
       const int t = te + NOE * tf;
       const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
-      const double pc0 = pc[lp], pc1 = pc[lp + PS1];
+      const double pc0 = pc[lp] * mu, pc1 = pc[lp + PS1] * mu;
       const double x0 = xl[3 * t], x1 = xl[1 + 3 * t], x2 = xl[2 + 3 * t];
       {  // interior node
         double tt = 0.0;
@@ -375,14 +377,14 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool 
       if (lo) {  // lower face node: own element part + B^T; completed by pass B
         if (ok) y[l.base] = sc * yl[3 * t] + ttlo[t];
       } else {   // eliminated boundary node: identity row (its raw value is re-read: boundary cells only)
-        const double xr = x[l.base];
+        const double xr = x[l.base] * mu;
         if (ok) y[l.base] = xr;
         if (DOT) acc += xr * xr;
       }
       if (hi) {
         if (ok) yup[(long)q.c * Q::NUP + DI * Q::NL + t] = sc * yl[2 + 3 * t];
       } else {
-        const double xr = x[l.base + 2 * l.sd];
+        const double xr = x[l.base + 2 * l.sd] * mu;
         if (ok) y[l.base + 2 * l.sd] = xr;
         if (DOT) acc += xr * xr;
       }
@@ -455,9 +457,10 @@ k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam, const 
   const double* pc = s_pc + cs * S::PS;
   double* ypd = s_yp + (dir * K1Q_TC + ci) * S::PS;
   // dir is warp-uniform: no divergence between the three bodies; each contains the named barrier once
-  if (dir == 0) q_apply_dir<HY, 0, DOT>(L, q, q.ok, C, tb, rl, Kx, gx, x, y, yup, pc, ypd);
-  else if (HY && dir == 1) q_apply_dir<HY, 1, DOT>(L, q, q.ok, C, tb, rl, Ky, gy, x, y, yup, pc, ypd);
-  else q_apply_dir<HY, 2, DOT>(L, q, q.ok, C, tb, rl, Kz, gz, x, y, yup, pc, ypd);
+  const double mu = st ? st->mu : 1.0;
+  if (dir == 0) q_apply_dir<HY, 0, DOT>(L, q, q.ok, C, tb, rl, Kx, gx, x, mu, y, yup, pc, ypd);
+  else if (HY && dir == 1) q_apply_dir<HY, 1, DOT>(L, q, q.ok, C, tb, rl, Ky, gy, x, mu, y, yup, pc, ypd);
+  else q_apply_dir<HY, 2, DOT>(L, q, q.ok, C, tb, rl, Kz, gz, x, mu, y, yup, pc, ypd);
   __syncthreads();
   if (dir == 0 && q.ok) {  // pressure rows and the cell's share of <x, y>
     const double* a = s_yp + ci * S::PS;
@@ -469,7 +472,7 @@ k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam, const 
     for (int l = 0; l < Q::NSL; ++l) {
       const double yp = HY ? (a[l] + b[l]) + c2[l] : a[l] + b[l];
       y[q.pb + l] = yp;
-      if (DOT) ap += pc[l] * yp;
+      if (DOT) ap += (pc[l] * mu) * yp;
     }
     if (DOT) accA[t0 + ci] = acc + ap;
   }
@@ -477,7 +480,7 @@ k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam, const 
 
 // pass B: lower-face-node rows += the lower cell's element contribution; <x, y> = tree(accA) + tree(own share)
 template <bool HY, int D, bool DOT>
-__device__ __forceinline__ void q_face_dir(const Lay1& L, const Cell1& q, const double* __restrict__ x,
+__device__ __forceinline__ void q_face_dir(const Lay1& L, const Cell1& q, const double* __restrict__ x, double mu,
                                            double* __restrict__ y, const double* __restrict__ yup, double& acc) {
   using R = QDir<HY, D>;
   using Q = QD<HY>;
@@ -491,7 +494,7 @@ __device__ __forceinline__ void q_face_dir(const Lay1& L, const Cell1& q, const 
       if (l.cd > 0) {
         const double yv = y[l.base] + yup[(long)(q.c - l.cstride) * Q::NUP + DI * Q::NL + te + NOE * tf];
         y[l.base] = yv;
-        if (DOT) acc += x[l.base] * yv;
+        if (DOT) acc += (x[l.base] * mu) * yv;
       }
     }
 }
@@ -504,9 +507,10 @@ __global__ void __launch_bounds__(BLK) k1q_apply_b(Lay1 L, const double* __restr
   const Cell1 q = owned_cell1(L);
   double acc = 0.0, accq = 0.0;
   if (q.ok) {
-    q_face_dir<HY, 0, DOT>(L, q, x, y, yup, acc);
-    if constexpr (HY) q_face_dir<HY, 1, DOT>(L, q, x, y, yup, acc);
-    q_face_dir<HY, 2, DOT>(L, q, x, y, yup, acc);
+    const double mu = st ? st->mu : 1.0;
+    q_face_dir<HY, 0, DOT>(L, q, x, mu, y, yup, acc);
+    if constexpr (HY) q_face_dir<HY, 1, DOT>(L, q, x, mu, y, yup, acc);
+    q_face_dir<HY, 2, DOT>(L, q, x, mu, y, yup, acc);
     if (DOT) accq = accA[blockIdx.x * (unsigned)BLK + threadIdx.x];
   }
   if (DOT) {
@@ -524,8 +528,7 @@ __global__ void __launch_bounds__(BLK) k1q_apply_b(Lay1 L, const double* __restr
     __syncthreads();
     if (is_last) {
       __threadfence();
-      double a = 0.0, b = 0.0;
-      for (unsigned j = threadIdx.x; j < gridDim.x; j += BLK) { a += __ldcg(partial + j); b += __ldcg(partial + gridDim.x + j); }
+      const double a = ordered_partial_sum(partial, gridDim.x), b = ordered_partial_sum(partial + gridDim.x, gridDim.x);
       __syncthreads();
       const double ta = block_tree_256(a, sm);
       __syncthreads();

@@ -208,7 +208,8 @@ class FiniteElementSpace {
     else { long tot = 0; for (int d = 0; d < dim; ++d) { long s = 1; for (int e = 0; e < dim; ++e) s *= (e == d) ? n[e] * (k + 1) + 1 : n[e] * (k + 1); tot += s; } size_ = (int)tot; }
     if (const char* e = std::getenv("IMPES_COMPAT_SCRAMBLE")) SetScramble((unsigned)std::atoi(e));
   }
-  int GetVSize() const { return size_; }
+  virtual ~FiniteElementSpace() {}
+  virtual int GetVSize() const { return size_; }
   int GetNE() const { return mesh_->GetNE(); }
   Mesh* GetMesh() const { return mesh_; }
   const FiniteElementCollection* FEColl() const { return fec_; }
@@ -310,13 +311,24 @@ class VectorGridFunctionCoefficient : public VectorCoefficient {
 // multi-GPU decomposition lives inside the library: impes_*_local, host/run_parallel.cpp).
 class ParMesh : public Mesh {
  public:
-  explicit ParMesh(const Mesh& m) : Mesh(m) {}
+  explicit ParMesh(const Mesh& m, int rank = 0, int nranks = 1) : Mesh(m), rank_(rank), nranks_(nranks) {}
+  int GetMyRank() const { return rank_; }
+  int GetNRanks() const { return nranks_; }
+ private:
+  int rank_, nranks_;
 };
 class ParFiniteElementSpace : public FiniteElementSpace {
  public:
-  ParFiniteElementSpace(ParMesh* m, const FiniteElementCollection* fec) : FiniteElementSpace(m, fec) {}
+  ParFiniteElementSpace(ParMesh* m, const FiniteElementCollection* fec) : FiniteElementSpace(m, fec), pmesh_(m), local_(-1) {}
+  // shim-only: the dofs this rank holds (its slab, impes_get_local_dims) when the mesh is split over several ranks
+  ParFiniteElementSpace(ParMesh* m, const FiniteElementCollection* fec, int local_size) : FiniteElementSpace(m, fec), pmesh_(m), local_(local_size) {}
+  int GetVSize() const override { return local_ >= 0 ? local_ : FiniteElementSpace::GetVSize(); }
   int GetTrueVSize() const { return GetVSize(); }
   int TrueVSize() const { return GetVSize(); }
+  ParMesh* GetParMesh() const { return pmesh_; }
+ private:
+  ParMesh* pmesh_;
+  int local_;
 };
 class ParGridFunction : public GridFunction {
  public:

@@ -71,9 +71,36 @@ void PressureSolver(const Array<int>& block_offsets, const Mesh& mesh, const Par
 void ParPressureSolver(const Array<int>& block_offsets, const Array<int>& block_trueOffsets, const ParMesh& mesh,
                        const Param& param, ParFiniteElementSpace& V_space, ParFiniteElementSpace& P_space,
                        GridFunctionCoefficient& saturation, BlockVector& x, BlockVector& trueX) {
-  (void)mesh;
-  MFEM_VERIFY(block_trueOffsets.Last() == block_offsets.Last(), "ParPressureSolver: one rank owns every dof in this build");
-  impes_handle h = impes_host_context(param, IMPES_SUBSTEPS_PARALLEL);
-  pressure_solve(h, param, V_space, P_space, saturation, block_offsets, x, true);
-  for (int i = 0; i < x.Size(); ++i) trueX(i) = x(i);
+  const int rank = mesh.GetMyRank(), world = mesh.GetNRanks();
+  impes_handle h = impes_host_context(param, IMPES_SUBSTEPS_PARALLEL, rank, world);
+  if (world == 1) {
+    MFEM_VERIFY(block_trueOffsets.Last() == block_offsets.Last(), "ParPressureSolver: one rank owns every dof");
+    pressure_solve(h, param, V_space, P_space, saturation, block_offsets, x, true);
+    for (int i = 0; i < x.Size(); ++i) trueX(i) = x(i);
+    return;
+  }
+  // one process per GPU: every rank holds the dofs of its slab (native local layout, impes_get_local_dims) -- the
+  // local / true dofs of the reference's ParGridFunctions [REF src/run_parallel.cpp:118-125]; ghost layers stay on
+  // the GPUs.  Rank 0 prints, like the reference [REF src/par_pressure_solver.cpp:111-127].
+  impes_host_comm_bootstrap(param, rank, world);
+  impes_local_dims ld;
+  impes_get_local_dims(h, &ld);
+  MFEM_VERIFY(V_space.GetVSize() == ld.n_v && P_space.GetVSize() == ld.n_p, "ParPressureSolver: local space sizes mismatch");
+  const GridFunction* S = saturation.GetGridFunction();
+  MFEM_VERIFY(S && S->Size() == ld.n_s, "ParPressureSolver: local saturation size mismatch");
+  impes_solve_stats st;
+  const int rc = impes_pressure_solve_local(h, S->GetData(), trueX.GetData(), &st);
+  for (int i = 0; i < x.Size(); ++i) x(i) = trueX(i);
+  if (rc == IMPES_OK) {
+    if (rank == 0)
+      cout << "Darcy solver converged. Iter = " << st.iterations << ". Final norm = " << st.final_norm
+           << ". Time = " << st.seconds << " sec" << endl;
+  } else if (rc == IMPES_ERR_NOT_CONVERGED) {
+    if (rank == 0)
+      cerr << "Darcy solver DIDN'T converge. Iter = " << st.iterations << ". Final norm = " << st.final_norm
+           << ". Time = " << st.seconds << " sec" << endl;
+    MFEM_ABORT("The solver didn't converge => terminating");
+  } else {
+    MFEM_ABORT("impes_pressure_solve_local failed: " + string(impes_last_error(h)));
+  }
 }

@@ -51,5 +51,21 @@ void SaturationSolver(const Param& param, GridFunction& S, VectorCoefficient& ve
 void ParSaturationSolver(const Param& param, ParGridFunction& S, VectorCoefficient& velocity, int global_ti,
                          double global_dt, VisItDataCollection& visit) {
   (void)visit;
-  saturation_advance(impes_host_context(param, IMPES_SUBSTEPS_PARALLEL), param, S, velocity, global_ti, global_dt);
+  ParFiniteElementSpace* pfes = dynamic_cast<ParFiniteElementSpace*>(S.FESpace());
+  const int rank = pfes ? pfes->GetParMesh()->GetMyRank() : 0, world = pfes ? pfes->GetParMesh()->GetNRanks() : 1;
+  impes_handle h = impes_host_context(param, IMPES_SUBSTEPS_PARALLEL, rank, world);
+  if (world == 1) {
+    saturation_advance(h, param, S, velocity, global_ti, global_dt);
+    return;
+  }
+  impes_host_comm_bootstrap(param, rank, world);
+  VectorGridFunctionCoefficient* vgf = dynamic_cast<VectorGridFunctionCoefficient*>(&velocity);
+  MFEM_VERIFY(vgf && vgf->GetGridFunction(), "ParSaturationSolver: velocity must wrap a GridFunction");
+  impes_local_dims ld;
+  impes_get_local_dims(h, &ld);
+  MFEM_VERIFY(S.Size() == ld.n_s && vgf->GetGridFunction()->Size() == ld.n_v, "ParSaturationSolver: local sizes mismatch");
+  const int rc = impes_saturation_advance_local(h, vgf->GetGridFunction()->GetData(), S.GetData(), global_ti, global_dt,
+                                                param.dt_local, nullptr);
+  if (rc == IMPES_ERR_UNSUPPORTED) throw runtime_error(impes_last_error(h));
+  if (rc != IMPES_OK) MFEM_ABORT("impes_saturation_advance_local failed: " + string(impes_last_error(h)));
 }

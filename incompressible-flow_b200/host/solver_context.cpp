@@ -1,8 +1,12 @@
 #include "solver_context.hpp"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 
 #include "param.hpp"
 
@@ -12,6 +16,7 @@ struct Entry {
   impes_desc d;
   const double *kx = nullptr, *ky = nullptr, *kz = nullptr, *phi = nullptr;
   double probe[8] = {0};  // a few values of the K / phi arrays: catches a reload into the same buffers
+  bool comm_ready = false;
   std::map<const mfem::FiniteElementSpace*, DofMap> maps;
 };
 struct Registry {
@@ -81,4 +86,36 @@ const DofMap& impes_host_dofmap(const Param& param, mfem::FiniteElementSpace& fe
   const double size[3] = {param.sx, param.sy, param.sz};
   maps[&fes] = build_dofmap(fes, rt, order, param.spacedim, n, size);
   return maps[&fes];
+}
+
+void impes_host_comm_bootstrap(const Param& param, int rank, int world_size) {
+  if (world_size <= 1) return;
+  Registry& r = registry();
+  auto it = r.handles.find(&param);
+  MFEM_VERIFY(it != r.handles.end(), "impes_host_comm_bootstrap: no context for this Param");
+  Entry& e = it->second;
+  if (e.comm_ready) return;
+  const char* path = std::getenv("IMPES_NCCL_ID_FILE");
+  MFEM_VERIFY(path, "multi-process run: set IMPES_NCCL_ID_FILE to a path all ranks can read");
+  unsigned char id[128];
+  if (rank == 0) {
+    MFEM_VERIFY(impes_comm_unique_id(id) == IMPES_OK, "impes_comm_unique_id failed");
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    MFEM_VERIFY(f && std::fwrite(id, 1, 128, f) == 128, "cannot write the NCCL id file");
+    std::fclose(f);
+    MFEM_VERIFY(std::rename(tmp.c_str(), path) == 0, "cannot publish the NCCL id file");
+  } else {
+    size_t got = 0;
+    for (int tries = 0; tries < 6000 && got != 128; ++tries) {  // up to 10 minutes
+      if (FILE* f = std::fopen(path, "rb")) {
+        got = std::fread(id, 1, 128, f);
+        std::fclose(f);
+      }
+      if (got != 128) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    }
+    MFEM_VERIFY(got == 128, "timed out waiting for the NCCL id file");
+  }
+  if (impes_comm_init(e.h, id) != IMPES_OK) MFEM_ABORT("impes_comm_init failed: " + std::string(impes_last_error(e.h)));
+  e.comm_ready = true;
 }

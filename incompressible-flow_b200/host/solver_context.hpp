@@ -15,6 +15,10 @@ struct Param;
 impes_handle impes_host_context(const Param& param, int substep_rule = IMPES_SUBSTEPS_SERIAL, int rank = 0,
                                 int world_size = 1);
 void impes_host_release(const Param& param);
+// NCCL bootstrap of a multi-process run (one process per GPU): rank 0 creates the unique id, the others receive it.
+// Transport: the file named by IMPES_NCCL_ID_FILE (written atomically by rank 0, polled by the others) -- with real
+// MFEM + MPI an MPI_Bcast does the same [REF src/par_pressure_solver.cpp:99 uses MPI_COMM_WORLD].  Idempotent.
+void impes_host_comm_bootstrap(const Param& param, int rank, int world_size);
 
 // MFEM numbering <-> native layout of a space, built on first use (see dofmap.hpp)
 const DofMap& impes_host_dofmap(const Param& param, mfem::FiniteElementSpace& fes, bool rt, int order);

@@ -335,6 +335,69 @@ static double canon_dot_rt1(const orc *o, const double *a, const double *b) {
   return tree256(v);
 }
 
+/* beta^2 = <v0, P v0> of the RT1/Q1 + multigrid path, where the GPU folds the dot into other kernels
+ * (csrc/kernels.cuh k_minres_b_dot, csrc/rt1.cuh k1_mg_jacobi<.., DOT>):
+ *   velocity part: the device vector [ux | pad | uy | pad | ghost, uz, ghost | pad] is cut into chunks of 16384 entries;
+ *     "thread" t of a chunk adds a b of entries t, t + 256, ... in order, tree256 per chunk, then the ordered sum of the
+ *     chunk partials (padding and ghost entries contribute nothing);
+ *   pressure part: blocks of 256 consecutive L2 dofs, tree256 per block, ordered sum of the block partials;
+ *   result = velocity part + pressure part. */
+static double strided_tree(const double *partial, long n) {
+  double v[256];
+  for (int t = 0; t < 256; ++t) {
+    double acc = 0.0;
+    for (long j = t; j < n; j += 256) acc += partial[j];
+    v[t] = acc;
+  }
+  return tree256(v);
+}
+static double canon_dot_fold(const orc *o, const double *a, const double *b) {
+  const int HY = o->dim == 3;
+  const long NX = o->n[0], NY = HY ? o->n[1] : 1, NZ = HY ? o->n[2] : o->n[1], oy = HY ? 2 : 1;
+  const long nx_ = (2 * NX + 1) * (oy * NY) * 2 * NZ, ny_ = HY ? 2 * NX * (2 * NY + 1) * 2 * NZ : 0;
+  const long pz = 2 * NX * oy * NY, nz_ = pz * (2 * NZ + 3);
+#define PAD32(v) (((v) + 31) / 32 * 32)
+  const long off_y = PAD32(nx_), off_z = PAD32(off_y + ny_), off_p = PAD32(off_z + nz_);
+#undef PAD32
+  const long own_z0 = off_z + 2 * pz, own_z1 = own_z0 + pz * (2 * NZ + 1);
+  const long nvx = nx_, nvy = ny_;
+  const long nch = (off_p + 16383) / 16384;
+  double *partial = (double *)malloc(sizeof(double) * (nch > 0 ? nch : 1));
+#pragma omp parallel for schedule(static) if (o->threads > 1)
+  for (long c = 0; c < nch; ++c) {
+    double v[256];
+    for (int t = 0; t < 256; ++t) {
+      double acc = 0.0;
+      for (int k = 0; k < 64; ++k) {
+        const long i = c * 16384 + t + 256L * k;
+        long f = -1;
+        if (i < nx_) f = i;
+        else if (i >= off_y && i < off_y + ny_) f = nvx + (i - off_y);
+        else if (i >= own_z0 && i < own_z1) f = nvx + nvy + (i - own_z0);
+        if (i < off_p) acc += f >= 0 ? a[f] * b[f] : 0.0;
+      }
+      v[t] = acc;
+    }
+    partial[c] = tree256(v);
+  }
+  const double tu = strided_tree(partial, nch);
+  free(partial);
+  const long nb = (o->np + 255) / 256;
+  partial = (double *)malloc(sizeof(double) * (nb > 0 ? nb : 1));
+#pragma omp parallel for schedule(static) if (o->threads > 1)
+  for (long blk = 0; blk < nb; ++blk) {
+    double v[256];
+    for (int t = 0; t < 256; ++t) {
+      const long p = blk * 256 + t;
+      v[t] = p < o->np ? a[o->nv + p] * b[o->nv + p] : 0.0;
+    }
+    partial[blk] = tree256(v);
+  }
+  const double tp = strided_tree(partial, nb);
+  free(partial);
+  return tu + tp;
+}
+
 /* Vector::operator* : plain sequential sum [MFEM-recall] */
 static double vdot(const orc *o, const double *a, const double *b, long n) {
   const int canon = o->arith == 1 && (o->threads <= 1 || o->det) && n == o->nv + o->np;
@@ -919,7 +982,10 @@ static void minres(orc *o, const double *b, double *x, impes_solve_stats *st) {
     rho3 = sigma0 * beta;
     rho2 = sigma1 * alpha + gamma0 * gamma1 * beta;
     prec_mult(o, v0, q);
-    beta = sqrt(vdot(o, v0, q, n));
+    {
+      const int fold = o->arith == 1 && (o->threads <= 1 || o->det) && o->kv == 1 && o->kp == 1 && o->d.schur_prec == IMPES_SCHUR_MG;
+      beta = sqrt(fold ? canon_dot_fold(o, v0, q) : vdot(o, v0, q, n));
+    }
     rho1 = o->arith == 1 ? sqrt(delta * delta + beta * beta) : hypot(delta, beta);
     if (it == 1) {
       const double a = 1. / rho1;

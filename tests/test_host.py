@@ -171,3 +171,63 @@ def test_driver_with_foreign_dof_numbering(host_bins, tmp_path, spaces):
     assert len(runs[0][0]) == 2 and runs[0][0] == runs[1][0]
     for a, b in zip(runs[0][1], runs[1][1]):
         assert a.size == 180 and np.array_equal(a, b)
+
+
+def _run_parallel_driver(host_bins, out, world, extra_args, env_extra=None):
+    """Launch impes_run_parallel as `world` processes (one per GPU) the way a job script would: rank / world size from
+    the environment, NCCL id through a file."""
+    exe = os.path.join(os.path.dirname(host_bins[0]), "impes_run_parallel")
+    idf = str(out) + ".ncclid"
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, IMPES_RANK=str(r), IMPES_WORLD_SIZE=str(world), IMPES_NCCL_ID_FILE=idf)
+        env.update(env_extra or {})
+        procs.append(subprocess.Popen([exe] + extra_args + ["-outdir", str(out)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True, env=env))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, so[-2000:] + se[-2000:]
+    return outs[0][0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("spaces", ["0 0 0", "1 1 1"])
+def test_parallel_driver_matches_oracle(pkg, orc, host_bins, tmp_path, world, spaces):
+    """The run_parallel-compatible driver [REF src/run_parallel.cpp:118-230]: ParPressureSolver -> V.Distribute ->
+    ParSaturationSolver with the MPI path's sub-step rule and -ode, rank-0 log lines, pressure and saturation per-cell
+    dumps; on 2 GPUs every process holds only its slab.  Iteration counts and dumps as the oracle's loop."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from incompressible_flow_b200 import abi, workloads
+    ov, op, os_ = (int(v) for v in spaces.split())
+    nx, ny, nz, dtg, dtl = 8, 6, 8, 0.6, 0.05
+    args = ["-d", "3", "-nx", str(nx), "-ny", str(ny), "-nz", str(nz), "-sx", "8", "-sy", "6", "-sz", "8", "-ov", str(ov), "-op", str(op),
+            "-os", str(os_), "-two-phase", "-tf", str(2 * dtg), "-dtg", str(dtg), "-dtl", str(dtl), "-vsg", "1", "-ode", "3",
+            "-extra", "p", "-schur-prec", "1", "-sat-source", "0.5", "-darcy-maxiter", "5000",
+            "-inj-xcen", "0", "-inj-zcen", "0", "-inj-ycen", "0", "-inj-h", "6", "-inj-r", "1",
+            "-pro-xcen", "8", "-pro-zcen", "8", "-pro-ycen", "0", "-pro-h", "6", "-pro-r", "1"]
+    so = _run_parallel_driver(host_bins, tmp_path / "o", world, args)
+    its = [int(m) for m in re.findall(r"Darcy solver converged\. Iter = (\d+)", so)]
+    assert "Number of global time steps: 2" in so and so.count("is done") == 2 and "Kx: min 1 max 1" in so
+    d = workloads.make_desc(3, nx, ny, nz, sx=8, sy=6, sz=8, maxiter=5000, order=ov, order_s=os_, schur_prec=abi.SCHUR_MG,
+                            substep_rule=abi.SUBSTEPS_PARALLEL, ode_solver_type=3, saturation_source=0.5)
+    for w, c in ((d.injection, (0, 0, 0)), (d.production, (8, 0, 8))):
+        w.center[0], w.center[1], w.center[2] = c
+        w.radius, w.height = 1.0, 6.0
+    n = nx * ny * nz
+    oc = orc.Oracle(d, np.ones(n), np.ones(n), np.ones(n), np.ones(n))
+    oc.set_arith(1)
+    S, nsl, npl = np.zeros(oc.ns), oc.ns // n, oc.np_ // n
+    for ti in (1, 2):
+        x, st, rc = oc.pressure_solve(S)
+        S, nsub = oc.saturation_advance(x[:oc.nv], S, dtg, dtl)
+        assert nsub == 12 and abs(its[ti - 1] - st.iterations) <= (0 if world == 1 else 2)
+        sat = np.fromfile(tmp_path / "o" / f"saturation_p_3D_2phase_{ti:06d}.bin", dtype=np.float32)
+        prs = np.fromfile(tmp_path / "o" / f"pressure_p_3D_2phase_{ti:06d}.bin", dtype=np.float32)
+        want_s = S.reshape(n, nsl)[:, nsl - 1]
+        want_p = x[oc.nv:].reshape(n, npl)[:, npl - 1]
+        assert sat.shape == (n,) and np.allclose(sat, want_s, rtol=2e-5, atol=1e-6)
+        # the pressure is determined up to a constant (all-Neumann problem)
+        assert np.allclose(prs - prs.mean(), want_p - want_p.mean(), rtol=1e-4, atol=1e-4 * np.abs(want_p).max())
