@@ -255,7 +255,7 @@ def run_reference(args, wname, cfg, dtg, dtl):
 
 
 # algorithmic bytes per launch (fp64, every unique dof / coefficient once per pass)
-def kernel_bytes(name, dim, ncl, ndof):
+def kernel_bytes(name, dim, ncl, ndof, lazy_u=False):
     d3 = dim == 3
     per_cell = {
         "k_darcy_apply": 88 if d3 else 64,
@@ -269,7 +269,9 @@ def kernel_bytes(name, dim, ncl, ndof):
         "k1q_sat": 328 if d3 else 136,                 # 8 + 24 + 1 + 8 doubles per 3-D cell
         "k_sgs": 100,
     }
-    per_dof = {"k_minres_b+c": 104, "k_dot_owned": 16, "k_jacobi_u": 24}
+    # K2: pass B reads q, v0, v1 (+ diag(M) on the velocity part, 3/4 of the dofs) and writes v0 (+ q_u); pass C reads
+    # w0, w1, u, x and writes w0, x (+ reads and writes q unless u is scaled lazily: the DG-Q1 path)
+    per_dof = {"k_minres_b+c": 92 if lazy_u else 108, "k_dot_owned": 16, "k_jacobi_u": 24}
     if name in per_cell:
         return per_cell[name] * ncl
     if name in per_dof:
@@ -277,7 +279,7 @@ def kernel_bytes(name, dim, ncl, ndof):
     return None
 
 
-def rooflines_from_profile(kern, dim, ncl, ndof, peak, traffic):
+def rooflines_from_profile(kern, dim, ncl, ndof, peak, traffic, lazy_u=False):
     """kern: {kernel: (ms, launches)} of one profiled step -> list of per-kernel records sorted by share of the step."""
     tot = sum(ms for ms, _ in kern.values()) or 1.0
     merged = {}
@@ -291,7 +293,7 @@ def rooflines_from_profile(kern, dim, ncl, ndof, peak, traffic):
             del merged[a], merged[b]
     out = []
     for name, (ms, n) in merged.items():
-        b = kernel_bytes(name, dim, ncl, ndof)
+        b = kernel_bytes(name, dim, ncl, ndof, lazy_u)
         us = 1e3 * ms / max(n, 1)
         rec = {"k": name, "share": rnd(ms / tot, 3), "n": n, "us": rnd(us, 4)}
         if b:
@@ -430,7 +432,7 @@ def main():
     kern = s.profile_read_kernels()
     s.profile_enable(False)
     ncl = (ld.n_s // (2 ** d.dim)) if d.order_s == 1 else ld.n_s
-    rl = rooflines_from_profile(kern, d.dim, ncl, ld.n_v + ld.n_p, peak, traffic_table())
+    rl = rooflines_from_profile(kern, d.dim, ncl, ld.n_v + ld.n_p, peak, traffic_table(), lazy_u=d.order_s == 1)
     iso = None
     if not args.no_extras:
         # cross-check: the same kernels alone, L2 flushed before every launch.  EVERY rank takes part: K1 carries the

@@ -748,8 +748,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
       const int first = from_zero && s == 0;
       if (!first && multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
       Scope sc(h, first ? KI_MGQ_FIRST : KI_MGQ_JACOBI, 1);
-      if (L.has_y) k1_mg_jacobi<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
-      else k1_mg_jacobi<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
+      if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
+      else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
     }
     return 0;
   };
@@ -776,8 +776,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
     RET_IF(q1_smooth(h->mg_nu, true));
     if (multi) RET_IF(mg_halo(h, qb + qpe, qpe, L.nzl));
     Scope sc(h, KI_MGQ_RESTRICT, 1);
-    if (L.has_y) k1_mg_restrict<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
-    else k1_mg_restrict<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
+    if (L.has_y) k1_mg_restrict<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
+    else k1_mg_restrict<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, mg[0].r, st);
   }
   for (int l = 0; l + 1 < nl; ++l) {
     RET_IF(smooth(l, h->mg_nu, true));
@@ -810,8 +810,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
     if (multi) RET_IF(mg_halo(h, mg[0].yb, (size_t)L.plane, L.nzl));
     {
       Scope sc(h, KI_MGQ_JACOBI, 1);
-      if (L.has_y) k1_mg_jacobi<true, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
-      else k1_mg_jacobi<false, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
+      if (L.has_y) k1_mg_jacobi<true, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
+      else k1_mg_jacobi<false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
     }
     for (int s = 1; s < h->mg_nu; ++s) {
       double* in = (s & 1) ? qa : qb;
@@ -819,11 +819,11 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
       if (multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
       Scope sc(h, KI_MGQ_JACOBI, 1);
       if (dot && s + 1 == h->mg_nu) {  // last sweep: finishes beta^2 = <v0, P v0> (see k1_mg_jacobi<.., DOT>)
-        if (L.has_y) k1_mg_jacobi<true, false, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
-        else k1_mg_jacobi<false, false, true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+        if (L.has_y) k1_mg_jacobi<true, false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+        else k1_mg_jacobi<false, false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
       } else {
-        if (L.has_y) k1_mg_jacobi<true><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
-        else k1_mg_jacobi<false><<<gq, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+        if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+        else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
       }
     }
   }

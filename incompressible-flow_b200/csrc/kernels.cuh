@@ -57,6 +57,38 @@ __device__ __forceinline__ double ordered_partial_sum(const double* p, unsigned 
   return acc;
 }
 
+// The same for an explicit slot t of the canonical 256-thread reduction block (CTAs of another size)
+__device__ __forceinline__ double ordered_partial_sum_at(const double* p, unsigned n, unsigned t) {
+  double acc = 0.0;
+  unsigned j = t;
+  for (; j + 7 * 256 < n; j += 8 * 256) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + j + u * 256);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  for (; j < n; j += 256) acc += __ldcg(p + j);
+  return acc;
+}
+// block_tree_256 over 256 values held by a 128-thread CTA as slots t (x0) and t + 128 (x1): warp w of the canonical
+// block = slots 32w .. 32w+31 = threads 32 (w & 3) .. +31 with x0 (w < 4) or x1 (w >= 4).  Result valid in thread 0.
+__device__ __forceinline__ double block_tree_256_split(double x0, double x1, double* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+    x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = x0; sm[4 + (threadIdx.x >> 5)] = x1; }
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[w];
+  }
+  return s;
+}
+
 // Block partial -> partial[blockIdx.x]; the last block to arrive adds all partials in index
 // order (thread t takes t, t+256, ...; then the same tree) and writes *out.  Deterministic:
 // which block is last does not matter.

@@ -516,106 +516,197 @@ __global__ void __launch_bounds__(BLK) k1_face_flux(Lay1 L1, Lay L0, Rt1Const C,
 // other dofs come through warp shuffles.  Same terms in the same order as q1_row_sum<HY, true>, so the result
 // is bit-identical to the one-thread-per-cell form (ncu: that form was L1/LSU bound, 95 % l1tex throughput at
 // 18 % DRAM, because each lane walked its own 64-byte block with 8-byte loads).
-// Branch-free neighbour terms for the per-dof kernels: T is stored as 0 on eliminated boundary nodes, so a
-// missing neighbour contributes y * (b (b' 0)) = +-0 with y loaded from a clamped (own-cell) address.
-// e: cfac * (coarse correction of the neighbour cell) when the prolongation is fused into the sweep (PRO), else unused
-template <bool PRO>
-__device__ __forceinline__ void nb_lower(const Rt1Const& C, const Line1& l, int a, double T0, const double* y, int pb,
-                                         double e, double& sum) {
-  const double* yl = y + (pb - (l.cd > 0 ? l.pdn : 0) + l.lp);
-  sum += (PRO ? yl[0] + e : yl[0]) * (BV(a, 0) * (C.Bv[0][2] * T0));
-  sum += (PRO ? yl[l.ps] + e : yl[l.ps]) * (BV(a, 0) * (C.Bv[1][2] * T0));
+// Branch-free neighbour terms: T is stored as 0 on eliminated boundary nodes, so a missing neighbour contributes
+// y * (b (b' 0)) = +-0 with y loaded from a clamped (own-cell) address.
+//
+// One thread per PAIR of L2 dofs (a0 = 0, 1 with the same (a1, a2): consecutive in memory): the two rows share the
+// cell's index arithmetic, the x-line and every 16-byte load (their y / T operands are neighbours in memory), and are
+// each other's x-partner, so the instruction count per row drops by ~40 % against the one-thread-per-dof form of round
+// 1 (456 instructions per row, issue bound at 45 % of the HBM roofline).  Every row still adds the same terms in the
+// same order (the ascending-column order of the assembled S): z-, y-, x- neighbour cells, in-cell partners with a
+// smaller, then larger index, x+, y+, z+ neighbour cells.
+constexpr int MGQ_T = 128;  // threads per CTA = 256 dofs (the canonical reduction block)
+
+struct double2v { double v0, v1; };
+__device__ __forceinline__ double2v ld2(const double* p) {
+  const double2 t = *reinterpret_cast<const double2*>(p);
+  return {t.x, t.y};
 }
-template <bool PRO>
-__device__ __forceinline__ void nb_upper(const Rt1Const& C, const Line1& l, int a, double T2, const double* y, int pb,
-                                         double e, double& sum) {
-  const double* yu = y + (pb + (l.cd + 1 < l.nd ? l.pdn : 0) + l.lp);
-  sum += (PRO ? yu[0] + e : yu[0]) * (BV(a, 2) * (C.Bv[0][0] * T2));
-  sum += (PRO ? yu[l.ps] + e : yu[l.ps]) * (BV(a, 2) * (C.Bv[1][0] * T2));
+
+struct Pair1 {
+  Cell1 q;       // q.pb: index of the cell's first dof RELATIVE to the p-part
+  int a1, a2, l0;  // transverse indices of the pair and local index of its first dof
+};
+template <bool HY>
+__device__ __forceinline__ Pair1 owned_pair1(const Lay1& L) {
+  constexpr int NG = HY ? 4 : 2, NPL = HY ? 8 : 4;
+  Pair1 d;
+  const unsigned t = blockIdx.x * (unsigned)MGQ_T + threadIdx.x;
+  const unsigned cell = t / NG, g = t % NG;
+  d.a1 = HY ? (int)(g & 1) : 0;
+  d.a2 = HY ? (int)(g >> 1) : (int)g;
+  d.l0 = HY ? 2 * d.a1 + 4 * d.a2 : 2 * d.a2;
+  Cell1& q = d.q;
+  q.ok = cell < (unsigned)L.ncl;
+  const unsigned tt = q.ok ? cell : 0u;
+  const unsigned r = fastdiv(tt, L.fdx);
+  q.i = (int)(tt - r * (unsigned)L.NX);
+  q.kl = (int)fastdiv(r, L.fdy);
+  q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
+  q.k = q.kl + L.zlo;
+  q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+  q.pb = q.c * NPL;
+  return d;
 }
-// off-diagonal part of row l (all columns); ys = y of this dof; all 32 lanes must call.
-// PRO: y is the iterate BEFORE the prolongation y += cfac * ec(cell) (k1_mg_prolong); the correction is added on the
-// fly to every neighbour value (same expression, same bits), ec = cell-level iterate with one ghost plane below.
-template <bool HY, bool PRO = false>
-__device__ __forceinline__ double q1_row_sum_dof(const Lay1& L, const Rt1Const& C, const Dof1& d,
-                                                 const double* __restrict__ T, const double* __restrict__ y, double ys,
-                                                 const double* __restrict__ ec = nullptr, double cfac = 0.0) {
+
+// two-dof contribution of one neighbour cell on a line: row a adds  yA * (ba (b0 T)) + yB * (ba (b1 T))
+__device__ __forceinline__ void nb_term(double yA, double yB, double ba, double b0, double b1, double T, double& sum) {
+  sum += yA * (ba * (b0 * T));
+  sum += yB * (ba * (b1 * T));
+}
+
+// off-diagonal parts of the pair's two rows; ys0 / ys1 = y of the two dofs (after the fused prolongation if PRO);
+// all 32 lanes must call.  PRO: see k1_mg_jacobi.
+template <bool HY, bool PRO>
+__device__ __forceinline__ void q1_rows_pair(const Lay1& L, const Rt1Const& C, const Pair1& d, const double* __restrict__ T,
+                                             const double* __restrict__ y, double ys0, double ys1,
+                                             const double* __restrict__ ec, double cfac, double& sum0, double& sum1) {
+  constexpr int NPL = HY ? 8 : 4;
   const Cell1& q = d.q;
-  const int l = d.l;
-  const int a0 = l & 1, a1 = HY ? (l >> 1) & 1 : 0, a2 = l >> (HY ? 2 : 1);
-  const double yx = __shfl_xor_sync(0xffffffffu, ys, 1);
-  const double yy = HY ? __shfl_xor_sync(0xffffffffu, ys, 2) : 0.0;
-  const double yz = __shfl_xor_sync(0xffffffffu, ys, HY ? 4 : 2);
+  const int a1 = d.a1, a2 = d.a2;
+  const bool xlo = q.i > 0, xhi = q.i + 1 < L.NX, ylo = HY && q.j > 0, yhi = HY && q.j + 1 < L.NY;
+  const bool zlo = q.k > 0, zhi = q.k + 1 < L.NZ;
+  // ---- loads: T on the x-line (shared by both rows) and on the two y- / z-lines (one 16-byte load per node)
   const Line1 lx = line_x<HY>(L, q, a1, a2);
-  const Line1 lz = line_z<HY>(L, q, a0, a1);
-  Line1 ly = lx;
-  if constexpr (HY) ly = line_y(L, q, a0, a2);
-  const double Tx0 = T[lx.base], Tx1 = T[lx.base + lx.sd], Tx2 = T[lx.base + 2 * lx.sd];
-  const double Ty0 = HY ? T[ly.base] : 0.0, Ty1 = HY ? T[ly.base + ly.sd] : 0.0, Ty2 = HY ? T[ly.base + 2 * ly.sd] : 0.0;
-  const double Tz0 = T[lz.base], Tz1 = T[lz.base + lz.sd], Tz2 = T[lz.base + 2 * lz.sd];
-  const double Sx = s_in(C, a0, Tx0, Tx1, Tx2), Sz = s_in(C, a2, Tz0, Tz1, Tz2);
-  const double Sy = HY ? s_in(C, a1, Ty0, Ty1, Ty2) : 0.0;
+  const Line1 lz = line_z<HY>(L, q, 0, a1);
+  const double Tx0 = T[lx.base], Tx1 = T[lx.base + 1], Tx2 = T[lx.base + 2];
+  const double2v Tz0 = ld2(T + lz.base), Tz1 = ld2(T + lz.base + lz.sd), Tz2 = ld2(T + lz.base + 2 * lz.sd);
+  double2v Ty0 = {0.0, 0.0}, Ty1 = {0.0, 0.0}, Ty2 = {0.0, 0.0};
+  int pdn_y = 0;
+  if constexpr (HY) {
+    const Line1 ly = line_y(L, q, 0, a2);
+    Ty0 = ld2(T + ly.base); Ty1 = ld2(T + ly.base + ly.sd); Ty2 = ld2(T + ly.base + 2 * ly.sd);
+    pdn_y = ly.pdn;
+  }
+  // neighbour cells' dofs on the pair's lines (clamped to the own cell where there is no neighbour)
+  const int pb = q.pb;
+  const double2v xl = ld2(y + (pb - (xlo ? NPL : 0) + d.l0)), xu = ld2(y + (pb + (xhi ? NPL : 0) + d.l0));
+  const int oz = HY ? 2 * a1 : 0, sz = HY ? 4 : 2;   // z-line dofs: local (a0 + oz) and (a0 + oz + sz)
+  const double2v zlA = ld2(y + (pb - (zlo ? lz.pdn : 0) + oz)), zlB = ld2(y + (pb - (zlo ? lz.pdn : 0) + oz + sz));
+  const double2v zuA = ld2(y + (pb + (zhi ? lz.pdn : 0) + oz)), zuB = ld2(y + (pb + (zhi ? lz.pdn : 0) + oz + sz));
+  double2v ylA = {0.0, 0.0}, ylB = {0.0, 0.0}, yuA = {0.0, 0.0}, yuB = {0.0, 0.0};
+  if constexpr (HY) {   // y-line dofs: local (a0 + 4 a2) and (a0 + 4 a2 + 2)
+    ylA = ld2(y + (pb - (ylo ? pdn_y : 0) + 4 * a2)); ylB = ld2(y + (pb - (ylo ? pdn_y : 0) + 4 * a2 + 2));
+    yuA = ld2(y + (pb + (yhi ? pdn_y : 0) + 4 * a2)); yuB = ld2(y + (pb + (yhi ? pdn_y : 0) + 4 * a2 + 2));
+  }
   double ezl = 0.0, eyl = 0.0, exl = 0.0, exu = 0.0, eyu = 0.0, ezu = 0.0;
   if constexpr (PRO) {  // coarse corrections of the six line-neighbour cells (clamped like the y loads)
     const int cc = q.i + L.NX * (q.j + L.NY * q.kl);   // cell index in the level-0 arrays (ghost plane at -plane)
-    ezl = cfac * ec[cc - (lz.cd > 0 ? L.plane : 0)]; ezu = cfac * ec[cc + (lz.cd + 1 < lz.nd ? L.plane : 0)];
-    if constexpr (HY) { eyl = cfac * ec[cc - (ly.cd > 0 ? L.NX : 0)]; eyu = cfac * ec[cc + (ly.cd + 1 < ly.nd ? L.NX : 0)]; }
-    exl = cfac * ec[cc - (lx.cd > 0 ? 1 : 0)]; exu = cfac * ec[cc + (lx.cd + 1 < lx.nd ? 1 : 0)];
+    ezl = cfac * ec[cc - (zlo ? L.plane : 0)]; ezu = cfac * ec[cc + (zhi ? L.plane : 0)];
+    if constexpr (HY) { eyl = cfac * ec[cc - (ylo ? L.NX : 0)]; eyu = cfac * ec[cc + (yhi ? L.NX : 0)]; }
+    exl = cfac * ec[cc - (xlo ? 1 : 0)]; exu = cfac * ec[cc + (xhi ? 1 : 0)];
   }
-  double sum = 0.0;
-  // lower cells, ascending cell index: z-, y-, x-
-  nb_lower<PRO>(C, lz, a2, Tz0, y, q.pb, ezl, sum);
-  if constexpr (HY) nb_lower<PRO>(C, ly, a1, Ty0, y, q.pb, eyl, sum);
-  nb_lower<PRO>(C, lx, a0, Tx0, y, q.pb, exl, sum);
-  // in-cell partners: smaller local index (flip a2, a1, a0 from 1 to 0), then larger (flip a0, a1, a2 from 0 to 1)
-  sum += a2 ? yz * Sz : 0.0;
-  if constexpr (HY) sum += a1 ? yy * Sy : 0.0;
-  sum += a0 ? yx * Sx : 0.0;
-  sum += a0 ? 0.0 : yx * Sx;
-  if constexpr (HY) sum += a1 ? 0.0 : yy * Sy;
-  sum += a2 ? 0.0 : yz * Sz;
-  // upper cells: x+, y+, z+
-  nb_upper<PRO>(C, lx, a0, Tx2, y, q.pb, exu, sum);
-  if constexpr (HY) nb_upper<PRO>(C, ly, a1, Ty2, y, q.pb, eyu, sum);
-  nb_upper<PRO>(C, lz, a2, Tz2, y, q.pb, ezu, sum);
-  return sum;
+  // in-cell partners of the other lanes of the cell (same a0): a1 flipped = lane ^ 1, a2 flipped = lane ^ (HY ? 2 : 1)
+  const double yy0 = HY ? __shfl_xor_sync(0xffffffffu, ys0, 1) : 0.0, yy1 = HY ? __shfl_xor_sync(0xffffffffu, ys1, 1) : 0.0;
+  const double yz0 = __shfl_xor_sync(0xffffffffu, ys0, HY ? 2 : 1), yz1 = __shfl_xor_sync(0xffffffffu, ys1, HY ? 2 : 1);
+  // ---- the two rows.  PRO adds the neighbour cell's correction to its dofs on the fly (same expression as the prolongation)
+  const double b10 = BV(a1, 0), b12 = BV(a1, 2), b20 = BV(a2, 0), b22 = BV(a2, 2);
+#define IMPES_Q1_ROW(A0, YS_OTHER, TZ0, TZ1, TZ2, TY0, TY1, TY2, ZLA, ZLB, YLA, YLB, XUA_, YUA, YUB, ZUA, ZUB, YY, YZ, SUM) \
+  {                                                                                                                        \
+    double sum = 0.0;                                                                                                      \
+    /* lower cells, ascending cell index: z-, y-, x- */                                                                    \
+    nb_term(PRO ? ZLA + ezl : ZLA, PRO ? ZLB + ezl : ZLB, b20, C.Bv[0][2], C.Bv[1][2], TZ0, sum);                          \
+    if constexpr (HY) nb_term(PRO ? YLA + eyl : YLA, PRO ? YLB + eyl : YLB, b10, C.Bv[0][2], C.Bv[1][2], TY0, sum);        \
+    nb_term(PRO ? xl.v0 + exl : xl.v0, PRO ? xl.v1 + exl : xl.v1, C.Bv[A0][0], C.Bv[0][2], C.Bv[1][2], Tx0, sum);          \
+    /* in-cell partners: smaller local index first (a2, a1, a0 flipped from 1 to 0), then larger (a0, a1, a2 from 0 to 1) */ \
+    const double Sz = s_in(C, a2, TZ0, TZ1, TZ2), Sx = s_in(C, A0, Tx0, Tx1, Tx2);                                         \
+    const double Sy = HY ? s_in(C, a1, TY0, TY1, TY2) : 0.0;                                                               \
+    if (a2) sum += YZ * Sz;                                                                                                \
+    if constexpr (HY) { if (a1) sum += YY * Sy; }                                                                          \
+    if (A0) sum += YS_OTHER * Sx;                                                                                          \
+    if (!A0) sum += YS_OTHER * Sx;                                                                                         \
+    if constexpr (HY) { if (!a1) sum += YY * Sy; }                                                                         \
+    if (!a2) sum += YZ * Sz;                                                                                               \
+    /* upper cells: x+, y+, z+ */                                                                                          \
+    nb_term(PRO ? xu.v0 + exu : xu.v0, PRO ? xu.v1 + exu : xu.v1, C.Bv[A0][2], C.Bv[0][0], C.Bv[1][0], Tx2, sum);          \
+    if constexpr (HY) nb_term(PRO ? YUA + eyu : YUA, PRO ? YUB + eyu : YUB, b12, C.Bv[0][0], C.Bv[1][0], TY2, sum);        \
+    nb_term(PRO ? ZUA + ezu : ZUA, PRO ? ZUB + ezu : ZUB, b22, C.Bv[0][0], C.Bv[1][0], TZ2, sum);                          \
+    SUM = sum;                                                                                                             \
+  }
+  IMPES_Q1_ROW(0, ys1, Tz0.v0, Tz1.v0, Tz2.v0, Ty0.v0, Ty1.v0, Ty2.v0, zlA.v0, zlB.v0, ylA.v0, ylB.v0, 0, yuA.v0, yuB.v0, zuA.v0, zuB.v0, yy0, yz0, sum0)
+  IMPES_Q1_ROW(1, ys0, Tz0.v1, Tz1.v1, Tz2.v1, Ty0.v1, Ty1.v1, Ty2.v1, zlA.v1, zlB.v1, ylA.v1, ylB.v1, 0, yuA.v1, yuB.v1, zuA.v1, zuB.v1, yy1, yz1, sum1)
+#undef IMPES_Q1_ROW
 }
 
+// block_tree_256 over 256 values held two per thread by a 128-thread CTA (value 2t, 2t+1 in thread t): the same
+// butterfly (xor 16, 8, 4, 2, 1 over the VALUE index inside groups of 32) and the same ordered sum of the 8 group
+// results, hence the same bits.  Result valid in thread 0.  sm: 8 doubles.
+__device__ __forceinline__ double block_tree_256_pairs(double x0, double x1, double* sm) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {   // value-index xor 16, 8, 4, 2 = lane xor 8, 4, 2, 1
+    x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+    x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+  }
+  const double v = x0 + x1;           // value-index xor 1
+  if ((threadIdx.x & 15) == 0) sm[threadIdx.x >> 4] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[w];
+  }
+  return s;
+}
+
+// One damped-Jacobi sweep on the Q1 level: first = 1: y_out = omega (r / D) (zero initial guess), else
+// y_out = y_in + omega ((r - S y_in) / D).
 // PRO: the first post-smoothing sweep with the prolongation fused in: yin is the iterate before
-// y += cfac * ec(cell) (what k1_mg_prolong would have written, one whole pass over the level saved); a missing
-// neighbour contributes (y + e) * (b (b' 0)) = +-0 as before.
+// y += cfac * ec(cell) (one whole pass over the level saved); a missing neighbour contributes
+// (y + e) * (b (b' 0)) = +-0 as before.
 // DOT: the last sweep of a V-cycle inside MINRES also finishes beta^2 = <v0, P v0>: its right-hand side rp IS the
 // pressure part of v0 and its result the pressure part of P v0, so the products are formed here (canonical tree over
 // the CTA's 256 dofs -> partial_p[cta]); the last CTA adds tree(partial_u) (velocity part, from k_minres_b_dot) and
 // tree(partial_p) and writes the scalar.
 template <bool HY, bool PRO = false, bool DOT = false>
-__global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
-                                                    const double* __restrict__ Dp, const double* __restrict__ rp,
-                                                    const double* __restrict__ yin, double* __restrict__ yout,
-                                                    double omega, int first, const MinresState* st,
-                                                    const double* __restrict__ ec = nullptr, double cfac = 0.0,
-                                                    double* partial_p = nullptr, const double* partial_u = nullptr,
-                                                    unsigned n_u_chunks = 0, double* out = nullptr,
-                                                    unsigned* ticket = nullptr) {
+__global__ void __launch_bounds__(MGQ_T, (PRO || DOT) ? 6 : 8) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
+                                                      const double* __restrict__ Dp, const double* __restrict__ rp,
+                                                      const double* __restrict__ yin, double* __restrict__ yout,
+                                                      double omega, int first, const MinresState* st,
+                                                      const double* __restrict__ ec = nullptr, double cfac = 0.0,
+                                                      double* partial_p = nullptr, const double* partial_u = nullptr,
+                                                      unsigned n_u_chunks = 0, double* out = nullptr,
+                                                      unsigned* ticket = nullptr) {
   if (st && st->done) return;
-  const Dof1 d = owned_dof1<HY>(L);
-  const int p = d.q.pb + d.l;
+  const Pair1 d = owned_pair1<HY>(L);
+  const int p = d.q.pb + d.l0;
+  const double2v rv = ld2(rp + p), dd = ld2(Dp + p);
   if (first) {
-    if (d.q.ok) yout[p] = omega * (rp[p] / Dp[p]);
+    if (d.q.ok) {
+      double2 o;
+      o.x = omega * div_rcp(rv.v0, dd.v0);   // same bits as `/`, half the instructions
+      o.y = omega * div_rcp(rv.v1, dd.v1);
+      *reinterpret_cast<double2*>(yout + p) = o;
+    }
     return;
   }
-  double ys = yin[p];
-  if constexpr (PRO) ys = ys + cfac * ec[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)];
-  const double sum = q1_row_sum_dof<HY, PRO>(L, C, d, T, yin, ys, ec, cfac);
-  const double dd = Dp[p];
-  const double sy = dd * ys + sum;
-  const double rv = rp[p];
-  const double yn = ys + omega * ((rv - sy) / dd);
-  if (d.q.ok) yout[p] = yn;
+  double2v ys = ld2(yin + p);
+  if constexpr (PRO) {
+    const double e = cfac * ec[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)];
+    ys.v0 = ys.v0 + e; ys.v1 = ys.v1 + e;
+  }
+  double sum0, sum1;
+  q1_rows_pair<HY, PRO>(L, C, d, T, yin, ys.v0, ys.v1, ec, cfac, sum0, sum1);
+  const double sy0 = dd.v0 * ys.v0 + sum0, sy1 = dd.v1 * ys.v1 + sum1;
+  const double yn0 = ys.v0 + omega * div_rcp(rv.v0 - sy0, dd.v0), yn1 = ys.v1 + omega * div_rcp(rv.v1 - sy1, dd.v1);
+  if (d.q.ok) {
+    double2 o;
+    o.x = yn0; o.y = yn1;
+    *reinterpret_cast<double2*>(yout + p) = o;
+  }
   if constexpr (DOT) {
-    __shared__ double sm[BLK / 32];
+    __shared__ double sm[8];
     __shared__ int is_last;
-    const double s = block_tree_256(d.q.ok ? rv * yn : 0.0, sm);
+    const double s = block_tree_256_pairs(d.q.ok ? rv.v0 * yn0 : 0.0, d.q.ok ? rv.v1 * yn1 : 0.0, sm);
     if (threadIdx.x == 0) {
       partial_p[blockIdx.x] = s;
       __threadfence();
@@ -624,11 +715,14 @@ __global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const do
     __syncthreads();
     if (is_last) {
       __threadfence();
-      const double a = ordered_partial_sum(partial_u, n_u_chunks), b = ordered_partial_sum(partial_p, gridDim.x);
+      // thread t of the canonical 256-thread reduction block = value slots t (x0) and t + 128 (x1) here:
+      // ordered sums of entries t, t + 256, ... like ordered_partial_sum, two slots per thread
+      const double a0 = ordered_partial_sum_at(partial_u, n_u_chunks, threadIdx.x), a1 = ordered_partial_sum_at(partial_u, n_u_chunks, threadIdx.x + 128);
+      const double b0 = ordered_partial_sum_at(partial_p, gridDim.x, threadIdx.x), b1 = ordered_partial_sum_at(partial_p, gridDim.x, threadIdx.x + 128);
       __syncthreads();
-      const double ta = block_tree_256(a, sm);
+      const double ta = block_tree_256_split(a0, a1, sm);
       __syncthreads();
-      const double tb = block_tree_256(b, sm);
+      const double tb = block_tree_256_split(b0, b1, sm);
       if (threadIdx.x == 0) {
         *out = ta + tb;
         *ticket = 0u;
@@ -639,23 +733,27 @@ __global__ void __launch_bounds__(BLK) k1_mg_jacobi(Lay1 L, Rt1Const C, const do
 
 // cell rhs = sum over the cell's dofs (local order) of the residual r - S y
 template <bool HY>
-__global__ void __launch_bounds__(BLK) k1_mg_restrict(Lay1 L, Rt1Const C, const double* __restrict__ T,
-                                                      const double* __restrict__ Dp, const double* __restrict__ rp,
-                                                      const double* __restrict__ y, double* __restrict__ rc,
-                                                      const MinresState* st) {
-  constexpr int NPL = HY ? 8 : 4;
+__global__ void __launch_bounds__(MGQ_T, 6) k1_mg_restrict(Lay1 L, Rt1Const C, const double* __restrict__ T,
+                                                        const double* __restrict__ Dp, const double* __restrict__ rp,
+                                                        const double* __restrict__ y, double* __restrict__ rc,
+                                                        const MinresState* st) {
+  constexpr int NG = HY ? 4 : 2;
   if (st && st->done) return;
-  const Dof1 d = owned_dof1<HY>(L);
-  const int p = d.q.pb + d.l;
-  const double ys = y[p];
-  const double sum = q1_row_sum_dof<HY>(L, C, d, T, y, ys);
-  const double res = rp[p] - (Dp[p] * ys + sum);
-  // ordered sum over the cell's lanes: ((0 + res_0) + res_1) + ...
-  const int lane0 = (threadIdx.x & 31) & ~(NPL - 1);
+  const Pair1 d = owned_pair1<HY>(L);
+  const int p = d.q.pb + d.l0;
+  const double2v ys = ld2(y + p), rv = ld2(rp + p), dd = ld2(Dp + p);
+  double sum0, sum1;
+  q1_rows_pair<HY, false>(L, C, d, T, y, ys.v0, ys.v1, nullptr, 0.0, sum0, sum1);
+  const double res0 = rv.v0 - (dd.v0 * ys.v0 + sum0), res1 = rv.v1 - (dd.v1 * ys.v1 + sum1);
+  // ordered sum over the cell's dofs: ((0 + res_0) + res_1) + ...   (dof 2g, 2g+1 in lane g of the cell's group)
+  const int lane0 = (threadIdx.x & 31) & ~(NG - 1);
   double acc = 0.0;
 #pragma unroll
-  for (int l = 0; l < NPL; ++l) acc += __shfl_sync(0xffffffffu, res, lane0 + l);
-  if (d.q.ok && d.l == 0) rc[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)] = acc;
+  for (int g = 0; g < NG; ++g) {
+    acc += __shfl_sync(0xffffffffu, res0, lane0 + g);
+    acc += __shfl_sync(0xffffffffu, res1, lane0 + g);
+  }
+  if (d.q.ok && (threadIdx.x & (NG - 1)) == 0) rc[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)] = acc;
 }
 
 // cell-level transmissibilities below the Q1 level: Galerkin with cell-wise constant prolongation.  The two L2

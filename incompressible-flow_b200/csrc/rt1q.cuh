@@ -753,7 +753,7 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x, con
                  pz = (k + (m2 ? tb.sn[1] : tb.sn[0])) * sp.hz;
     const double z = r + sat_source_at(sp, px, py, pz) * wm;
     const double mphi = phi_r[it] * wm;
-    double yv = z / mphi;
+    double yv = div_rcp(z, mphi);   // same bits as `/` (kernels.cuh), without the call into the division subroutine
     double so;
     if (RATE) so = yv;
     else {
@@ -761,7 +761,15 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x, con
       so = sin_r[it] + yv;
     }
     Sout[sb0 + e] = so;
-    if (!RATE) Fout[sb0 + e] = sp.two_phase ? frac_flow_of(ph, so) : so;
+    if (!RATE) {
+      double fo = so;
+      if (sp.two_phase) {
+        double mw, mo;
+        mobilities(ph, so, mw, mo);
+        fo = div_rcp(mw, mw + mo);   // FS [REF src/saturation_solver.cpp:8-17]
+      }
+      Fout[sb0 + e] = fo;
+    }
   }
 }
 
