@@ -29,7 +29,8 @@ EXPORTS = [
 
 
 def library_path():
-    return os.path.join(_HERE, "libimpes_b200.so")
+    # IMPES_B200_LIB: development override (A/B builds of the same CUDA library with other tuning macros)
+    return os.environ.get("IMPES_B200_LIB") or os.path.join(_HERE, "libimpes_b200.so")
 
 
 def build_native(force=False, verbose=False):

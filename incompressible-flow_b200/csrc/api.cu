@@ -60,6 +60,8 @@ struct impes_ctx {
   int grid_dofs1 = 0;    // blocks of 256 L2 dofs (ord == 1: K1, dot, Q1 multigrid level run one thread per dof)
   int vec_n = 0, vec_offp = 0;  // length and p-offset of a Darcy-sized device vector in the active layout
   double* flux0 = nullptr;      // ord == 1: face fluxes of x in the RT0 dvec layout (input of K6)
+  double* vhq = nullptr;        // os == 1: per-step velocity records of the DG-Q1 stage kernel (k1q_sat_pre)
+  double* fnq = nullptr;
   double* mg1_ya = nullptr;     // ord == 1: second iterate buffer of the Q1 multigrid level (p-part)
   int os = 0, nsl = 1;          // saturation order (DG_os) and dofs per cell; os == 1 needs ord == 1 (rt1q.cuh)
   QTab qt;
@@ -385,6 +387,29 @@ int exchange_planes(impes_ctx* h, double* base, bool send_up_top_owned, bool sen
   if (send_down_bottom_owned) {
     if (dn >= 0) NK(h->nccl.Send(base + pl, pl, ncclFloat64, dn, h->comm, h->stream));
     if (up >= 0) NK(h->nccl.Recv(base + pl * (L.nzl + 1), pl, ncclFloat64, up, h->comm, h->stream));
+  }
+  NK(grp.end());
+  return 0;
+}
+// both ghost planes of a dof-major cell array a[m ncv + c] (f(S) of the DG-Q1 stage kernel): nsl planes per side
+int exchange_planes_dofmajor(impes_ctx* h, double* base, int nsl) {
+  if (h->L.nranks == 1) return 0;
+  const Lay& L = h->L;
+  const int up = L.rank + 1 < L.nranks ? L.rank + 1 : -1, dn = L.rank > 0 ? L.rank - 1 : -1;
+  const size_t pl = (size_t)L.plane;
+  Scope sc(h, KI_COMM, 1);
+  NcclGroup grp(h->nccl);
+  if (!grp.open) { h->err = "ncclGroupStart failed"; return IMPES_ERR_NCCL; }
+  for (int m = 0; m < nsl; ++m) {
+    double* b = base + (size_t)m * L.ncv;
+    if (up >= 0) {
+      NK(h->nccl.Send(b + pl * L.nzl, pl, ncclFloat64, up, h->comm, h->stream));
+      NK(h->nccl.Recv(b + pl * (L.nzl + 1), pl, ncclFloat64, up, h->comm, h->stream));
+    }
+    if (dn >= 0) {
+      NK(h->nccl.Recv(b, pl, ncclFloat64, dn, h->comm, h->stream));
+      NK(h->nccl.Send(b + pl, pl, ncclFloat64, dn, h->comm, h->stream));
+    }
   }
   NK(grp.end());
   return 0;
@@ -1045,11 +1070,20 @@ int n_substeps(const impes_ctx* h, double global_dt, double dt) {
 int launch_frac(impes_ctx* h, const double* S, double* F) {
   Scope sc(h, KI_SAT_AUX, 1);
   if (h->os == 1) {
-    k_frac_flat<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv * h->nsl, h->ph, h->sp.two_phase, S, F);
+    k_frac_flat<<<h->grid_vec, BLK, 0, h->stream>>>((long)h->L.ncv, h->nsl, h->ph, h->sp.two_phase, S, F);
     return 0;
   }
   const int g = (int)((h->L.ncv + BLK - 1) / BLK);
   k_frac_flow<<<g, BLK, 0, h->stream>>>(h->L, h->ph, h->sp.two_phase, S, F);
+  return 0;
+}
+
+// os == 1: velocity records of the stage kernel from the RT1 dofs in h->x (once per step: the velocity is frozen)
+int launch_sat_pre(impes_ctx* h) {
+  Scope sc(h, KI_SAT_AUX, 1);
+  const int g = (h->L.ncl + K1Q_TC - 1) / K1Q_TC;
+  if (h->L.has_y) k1q_sat_pre<true><<<g, SatQ<true>::THREADS, 0, h->stream>>>(h->L1, h->qt, h->x, (long)h->L.ncv, h->vhq, h->fnq);
+  else k1q_sat_pre<false><<<g, SatQ<false>::THREADS, 0, h->stream>>>(h->L1, h->qt, h->x, (long)h->L.ncv, h->vhq, h->fnq);
   return 0;
 }
 
@@ -1063,11 +1097,11 @@ int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout, const d
   if (h->os == 1) {  // DG-Q1: volume + face terms straight from the RT1 dofs (rt1q.cuh)
     const int g = (L.ncl + K1Q_TC - 1) / K1Q_TC;
     if (L.has_y) {
-      if (rate) k1q_sat<true, true><<<g, K1Q_TC * 3, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
-      else k1q_sat<true, false><<<g, K1Q_TC * 3, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      if (rate) k1q_sat<true, true><<<g, K1Q_TC * 3, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, (long)L.ncv, h->vhq, h->fnq, h->phi, Sin, Fin, Sout, Fout);
+      else k1q_sat<true, false><<<g, K1Q_TC * 3, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, (long)L.ncv, h->vhq, h->fnq, h->phi, Sin, Fin, Sout, Fout);
     } else {
-      if (rate) k1q_sat<false, true><<<g, K1Q_TC * 2, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
-      else k1q_sat<false, false><<<g, K1Q_TC * 2, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, h->x, h->phi, Sin, Fin, Sout, Fout);
+      if (rate) k1q_sat<false, true><<<g, K1Q_TC * 2, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, (long)L.ncv, h->vhq, h->fnq, h->phi, Sin, Fin, Sout, Fout);
+      else k1q_sat<false, false><<<g, K1Q_TC * 2, 0, h->stream>>>(h->L1, h->qt, h->ph, h->sp, (long)L.ncv, h->vhq, h->fnq, h->phi, Sin, Fin, Sout, Fout);
     }
     return 0;
   }
@@ -1121,6 +1155,7 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
     if (h->L.has_y) k1_face_flux<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
     else k1_face_flux<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->L, h->rc, h->x, h->flux0);
   }
+  if (h->os == 1) RET_IF(launch_sat_pre(h));
   const int ode = h->d.substep_rule == IMPES_SUBSTEPS_SERIAL ? 1 : h->d.ode_solver_type;  // serial ignores -ode
   if (ode != 1 && ode != 2 && ode != 3 && ode != 4) {
     char b[128];
@@ -1141,7 +1176,8 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
           RET_IF(exchange_planes(h, S, true, true, h->nsl));
           RET_IF(launch_frac(h, S, h->F[h->scur]));
         } else {
-          RET_IF(exchange_planes(h, h->F[h->scur], true, true, h->nsl));
+          if (h->os == 1) RET_IF(exchange_planes_dofmajor(h, h->F[h->scur], h->nsl));   // F[m ncv + c]
+          else RET_IF(exchange_planes(h, h->F[h->scur], true, true, h->nsl));
         }
         RET_IF(launch_sat(h, false, S, Sn, h->F[h->scur], h->F[h->scur ^ 1]));
       } else {
@@ -1261,7 +1297,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup, h->accA, h->partial_u};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup, h->accA, h->partial_u, h->vhq, h->fnq};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   for (double* b : h->mg_bufs)
@@ -1644,6 +1680,13 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     RET_IF(dev_alloc(h, &h->rlam, (long)L.ncv * h->nqp));
     RET_IF(dev_alloc(h, &h->yup, (long)L.ncv * h->nup));
     RET_IF(dev_alloc(h, &h->accA, (long)L.nblk * BLK));
+    if (L.has_y) {
+      RET_IF(dev_alloc(h, &h->vhq, (long)L.ncv * SatQ<true>::ND * SatQ<true>::NVH));
+      RET_IF(dev_alloc(h, &h->fnq, (long)L.ncv * SatQ<true>::ND * SatQ<true>::NFP));
+    } else {
+      RET_IF(dev_alloc(h, &h->vhq, (long)L.ncv * SatQ<false>::ND * SatQ<false>::NVH));
+      RET_IF(dev_alloc(h, &h->fnq, (long)L.ncv * SatQ<false>::ND * SatQ<false>::NFP));
+    }
     CK(cudaFuncSetAttribute(k1q_apply_a<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
     CK(cudaFuncSetAttribute(k1q_apply_a<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
     h->sat_mode = 0;  // the DG-Q1 kernel always carries f(S)
@@ -2047,6 +2090,7 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
   h->profiling = false;
   if (kernel == IMPES_KERNEL_SAT_SUBSTEP && h->sat_mode == 0)  // f(S) is carried between sub-steps
     RET_IF(launch_frac(h, h->S[h->scur], h->F[h->scur]));
+  if (kernel == IMPES_KERNEL_SAT_SUBSTEP && h->os == 1) RET_IF(launch_sat_pre(h));
   for (int r = -2; r < reps; ++r) {  // 2 untimed warm-ups
     if (flush_l2) k_fill<<<h->num_sms * 4, 512, 0, h->stream>>>(h->flushbuf, h->flush_n, (double)r);
     CK(cudaEventRecord(e0, h->stream));

@@ -526,6 +526,13 @@ __global__ void __launch_bounds__(BLK) k1_face_flux(Lay1 L1, Lay L0, Rt1Const C,
 // same order (the ascending-column order of the assembled S): z-, y-, x- neighbour cells, in-cell partners with a
 // smaller, then larger index, x+, y+, z+ neighbour cells.
 constexpr int MGQ_T = 128;  // threads per CTA = 256 dofs (the canonical reduction block)
+#ifndef IMPES_MGQ_MINB
+#define IMPES_MGQ_MINB 4    // resident CTAs per SM of the plain sweep: the pair form needs ~108 registers; capped at
+                            // 64 (8 CTAs) it spilled 112 B per thread and the spill traffic made l1tex the top unit
+#endif
+#ifndef IMPES_MGQ_MINB2
+#define IMPES_MGQ_MINB2 4   // ... of the sweeps with fused prolongation / dot and of the restriction
+#endif
 
 struct double2v { double v0, v1; };
 __device__ __forceinline__ double2v ld2(const double* p) {
@@ -668,7 +675,7 @@ __device__ __forceinline__ double block_tree_256_pairs(double x0, double x1, dou
 // the CTA's 256 dofs -> partial_p[cta]); the last CTA adds tree(partial_u) (velocity part, from k_minres_b_dot) and
 // tree(partial_p) and writes the scalar.
 template <bool HY, bool PRO = false, bool DOT = false>
-__global__ void __launch_bounds__(MGQ_T, (PRO || DOT) ? 6 : 8) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
+__global__ void __launch_bounds__(MGQ_T, (PRO || DOT) ? IMPES_MGQ_MINB2 : IMPES_MGQ_MINB) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
                                                       const double* __restrict__ Dp, const double* __restrict__ rp,
                                                       const double* __restrict__ yin, double* __restrict__ yout,
                                                       double omega, int first, const MinresState* st,
@@ -733,7 +740,7 @@ __global__ void __launch_bounds__(MGQ_T, (PRO || DOT) ? 6 : 8) k1_mg_jacobi(Lay1
 
 // cell rhs = sum over the cell's dofs (local order) of the residual r - S y
 template <bool HY>
-__global__ void __launch_bounds__(MGQ_T, 6) k1_mg_restrict(Lay1 L, Rt1Const C, const double* __restrict__ T,
+__global__ void __launch_bounds__(MGQ_T, IMPES_MGQ_MINB2) k1_mg_restrict(Lay1 L, Rt1Const C, const double* __restrict__ T,
                                                         const double* __restrict__ Dp, const double* __restrict__ rp,
                                                         const double* __restrict__ y, double* __restrict__ rc,
                                                         const MinresState* st) {

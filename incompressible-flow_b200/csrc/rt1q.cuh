@@ -210,8 +210,12 @@ __global__ void __launch_bounds__(BLK) k1_schur_diag(Lay1 L, Rt1Const C, const d
 // (Round 1's version ran one thread per cell through all three directions: 128 registers + 676 B of spills,
 // scattered 8-byte loads of the 64 c_q -- 9 % of the HBM roofline.)
 // ---------------------------------------------------------------------------------------
-constexpr int K1Q_TC = 32;  // cells per CTA: one warp per direction (registers are split per SM sub-partition:
-                            // 3-warp CTAs at <= 96 registers keep 18 warps per SM resident, 6-warp CTAs at 112 only 12)
+#ifndef IMPES_K1Q_REGS
+#define IMPES_K1Q_REGS 128
+#endif
+constexpr int K1Q_TC = 32;  // cells per CTA: one warp per direction.  Register cap 128 (15 warps per SM): at 96 (18 warps)
+                            // the compiler reused one register pair for the four c_q loads of a quadrature line and
+                            // serialised LDS -> DMUL four times per iteration (ncu: short-scoreboard 1.7 per issue)
 
 template <bool HY>
 struct K1QS {
@@ -398,7 +402,7 @@ __device__ __forceinline__ void q_apply_dir(const Lay1& L, const Cell1& q, bool 
 }
 
 template <bool HY, bool DOT>
-__global__ void __launch_bounds__(K1QS<HY>::THREADS) __maxnreg__(HY ? 96 : 80)
+__global__ void __launch_bounds__(K1QS<HY>::THREADS) __maxnreg__(HY ? IMPES_K1Q_REGS : 80)
 k1q_apply_a(Lay1 L, Rt1Const C, QTab tb, const double* __restrict__ rlam, const double* __restrict__ Kx,
             const double* __restrict__ Ky, const double* __restrict__ Kz, double gx, double gy, double gz,
             const double* __restrict__ x, double* __restrict__ y, double* __restrict__ yup,
@@ -558,35 +562,135 @@ __device__ __forceinline__ double sat_source_at(const SatParam& sp, double px, d
           py <= sp.inj_c1 + sp.inj_h) ? sp.src : 0.;
 }
 
-// One (cell, direction) of a stage: rd[m] = this direction's part of (Kt F)_m for the cell's NSL dofs.
-// g: the cell's own F (shared memory).  ok = false: the lane shadows another cell (ragged last CTA).
+// The velocity is frozen during the sub-steps of a step [REF src/saturation_solver.cpp:74-92], so everything the
+// stage kernel needs from it is formed ONCE per step by k1q_sat_pre, in dof-major ("SoA") arrays over the cvec cell
+// index c (ghost planes included), so that the 32 cells of a warp read 32 consecutive doubles:
+//   vh[(dir NVH + 2 t + n) ncv + c]   v.e_dir at DG node n of line t (volume term)
+//   fn[(dir NFP + p) ncv + c]         w_p (v.n)(x_p) at the face-rule points of the cell's LOWER face in direction dir
+// (the upper face of a cell is the lower face of its upper neighbour -- the same RT1 face dofs, hence the same bits;
+// the top owned plane of a slab also fills the z-faces of the ghost plane above).  f(S) travels in the same layout:
+//   F[m ncv + c],  m = local DG dof.
+// The stage kernel then costs ~360 instead of ~520 fp64 instructions per (cell, direction) and every global access
+// of a warp is one contiguous 256-byte run (ncu on the cell-major form: l1tex data-pipe wavefronts 66-74 %, the top
+// unit, from the 64-byte-strided gathers of the neighbours' F and the stride-2 walks over the RT1 node grids).
+// Upwinding: DGTraceIntegrator's (a + b, b - a) with a = un/2, b = |un|/2 are exactly (un+, un-), so
+//   w (a + b) g1 - w (b - a) g2  ==  c * (c >= 0 ? g1 : g2),   c = w un     (same bits for finite g)
+template <bool HY>
+struct SatQ {
+  static constexpr int ND = HY ? 3 : 2;
+  static constexpr int NT = HY ? 4 : 2;    // lines per (cell, direction)
+  static constexpr int NFP = HY ? 9 : 2;   // face-rule points per face
+  static constexpr int NVH = 2 * NT;       // vhat values per (cell, direction)
+  static constexpr int THREADS = K1Q_TC * ND;
+};
+
 template <bool HY, int D>
-__device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const QTab& tb, const double* __restrict__ x,
-                                          const double* __restrict__ Fin, const double* g, double* rd) {
+__device__ __forceinline__ void q_sat_pre_dir(const Lay1& L, const Cell1& q, const QTab& tb, const double* __restrict__ x,
+                                              long ncv, double* __restrict__ vh, double* __restrict__ fn) {
   using R = QDir<HY, D>;
-  using Q = QD<HY>;
+  using SQ = SatQ<HY>;
   constexpr int NOE = R::no(R::E), NOF = R::no(R::F), NT = NOE * NOF;
-  constexpr int NFE = (R::E == 1 && !HY) ? 1 : Q::NF, NFF = (R::F == 1 && !HY) ? 1 : Q::NF;
-  constexpr int PS1 = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));
-  double ulo[NT], uhi[NT], umid[NT], gnl0[NT], gnl1[NT], gnh0[NT], gnh1[NT];
-  int cd = 0, nd = 1;
-  // ---- global loads first: RT1 dofs of the cell's lines, F of the two line neighbours
+  constexpr int NFE = (R::E == 1 && !HY) ? 1 : QD<HY>::NF, NFF = (R::F == 1 && !HY) ? 1 : QD<HY>::NF;
+  constexpr int DI = HY ? D : (D == 0 ? 0 : 1);
+  static_assert(NT == SQ::NT && NFE * NFF == SQ::NFP, "record sizes");
+  double ulo[NT], uhi[NT];
+  double* vo = vh + (long)DI * SQ::NVH * ncv + q.c;
 #pragma unroll
   for (int tf = 0; tf < NOF; ++tf)
 #pragma unroll
     for (int te = 0; te < NOE; ++te) {
       const Line1 l = line_of<HY, D>(L, q, te, tf);
       const int t = te + NOE * tf;
-      const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
-      cd = l.cd; nd = l.nd;
-      ulo[t] = x[l.base]; umid[t] = x[l.base + l.sd]; uhi[t] = x[l.base + 2 * l.sd];
-      const long nl = (long)(q.c - (l.cd > 0 ? l.cstride : 0)) * Q::NSL + lp;
-      const long nh = (long)(q.c + (l.cd + 1 < l.nd ? l.cstride : 0)) * Q::NSL + lp;
-      gnl0[t] = Fin[nl]; gnl1[t] = Fin[nl + PS1];
-      gnh0[t] = Fin[nh]; gnh1[t] = Fin[nh + PS1];
+      const double u0 = x[l.base], u1 = x[l.base + l.sd], u2 = x[l.base + 2 * l.sd];
+      ulo[t] = u0; uhi[t] = u2;
+      vo[(2 * t) * ncv] = tb.LC[0][0] * u0 + tb.LC[0][1] * u1 + tb.LC[0][2] * u2;
+      vo[(2 * t + 1) * ncv] = tb.LC[1][0] * u0 + tb.LC[1][1] * u1 + tb.LC[1][2] * u2;
     }
-  cp_async_wait<0>();
-  named_barrier_1<K1Q_TC * (HY ? 3 : 2)>();  // the staged F of the CTA's cells is in place
+  const bool top = D == 2 && q.kl == L.nzl - 1;   // slab top: the ghost plane's lower z-faces are this plane's upper ones
+  double* fo = fn + (long)DI * SQ::NFP * ncv + q.c;
+#pragma unroll
+  for (int qf = 0; qf < NFF; ++qf)
+#pragma unroll
+    for (int qe = 0; qe < NFE; ++qe) {
+      double unl = 0.0, unh = 0.0;
+#pragma unroll
+      for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+        for (int te = 0; te < NOE; ++te) {
+          const int t = te + NOE * tf;
+          // the same IEEE products as c_OOF3 (3-D) / the unrolled 2-D form of the stage kernel
+          const double oo = HY ? tb.OOF[qe][qf][t] : ((NFE == 1) ? 1.0 : tb.OF[qe][te]) * ((NFF == 1) ? 1.0 : tb.OF[qf][tf]);
+          unl = __fma_rn(ulo[t], oo, unl); unh = __fma_rn(uhi[t], oo, unh);
+        }
+      const double w = ((NFE == 1) ? 1.0 : tb.fw[qe]) * ((NFF == 1) ? 1.0 : tb.fw[qf]);
+      fo[(qe + NFE * qf) * ncv] = w * unl;
+      if (top) fo[(qe + NFE * qf) * ncv + L.plane] = w * unh;
+    }
+}
+template <bool HY>
+__global__ void __launch_bounds__(SatQ<HY>::THREADS) k1q_sat_pre(Lay1 L, QTab tb, const double* __restrict__ x, long ncv,
+                                                                 double* __restrict__ vh, double* __restrict__ fn) {
+  const int ci = threadIdx.x % K1Q_TC, dir = threadIdx.x / K1Q_TC;
+  const unsigned t = blockIdx.x * (unsigned)K1Q_TC + ci;
+  if (t >= (unsigned)L.ncl) return;
+  Cell1 q;
+  const unsigned r = fastdiv(t, L.fdx);
+  q.i = (int)(t - r * (unsigned)L.NX);
+  q.kl = (int)fastdiv(r, L.fdy);
+  q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
+  q.k = q.kl + L.zlo;
+  q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+  q.pb = L.off_p + q.c * L.npl;
+  q.ok = true;
+  if (dir == 0) q_sat_pre_dir<HY, 0>(L, q, tb, x, ncv, vh, fn);
+  else if (HY && dir == 1) { if constexpr (HY) q_sat_pre_dir<HY, 1>(L, q, tb, x, ncv, vh, fn); }
+  else q_sat_pre_dir<HY, 2>(L, q, tb, x, ncv, vh, fn);
+}
+
+// One (cell, direction) of a stage: rd[m] = this direction's part of (Kt F)_m for the cell's NSL dofs.
+// F, vh, fn: the dof-major arrays described above.  ok = false: the lane shadows another cell (ragged last CTA).
+template <bool HY, int D>
+__device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const QTab& tb, long ncv,
+                                          const double* __restrict__ F, const double* __restrict__ vh,
+                                          const double* __restrict__ fn, double* s_fn, double* rd) {
+  using R = QDir<HY, D>;
+  using Q = QD<HY>;
+  using SQ = SatQ<HY>;
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F), NT = NOE * NOF;
+  constexpr int NFE = (R::E == 1 && !HY) ? 1 : Q::NF, NFF = (R::F == 1 && !HY) ? 1 : Q::NF;
+  constexpr int PS1 = (D == 0) ? 1 : (D == 1 ? 2 : (HY ? 4 : 2));
+  constexpr int DI = HY ? D : (D == 0 ? 0 : 1);
+  // position of the cell along the direction and the cell stride to its neighbours
+  const int cd = D == 0 ? q.i : (D == 1 ? q.j : q.k), nd = D == 0 ? L.NX : (D == 1 ? L.NY : L.NZ);
+  const long cst = D == 0 ? 1 : (D == 1 ? L.NX : L.plane);
+  const bool lo = cd > 0, hi = cd + 1 < nd;
+  // ---- every global load of the prologue first (each one a contiguous run over the warp's cells)
+  const double* Fo = F + q.c;
+  const double* Fl = Fo - (lo ? cst : 0);   // clamped to the own cell where there is no neighbour (result unused)
+  const double* Fh = Fo + (hi ? cst : 0);
+  const double* vo = vh + (long)DI * SQ::NVH * ncv + q.c;
+  const double* fl_p = fn + (long)DI * SQ::NFP * ncv + q.c;
+  const double* fh_p = fl_p + cst;          // beyond the top boundary: a valid address whose value is not used
+  if constexpr (HY) {
+#pragma unroll
+    for (int p = 0; p < 9; ++p) {
+      cp_async8(s_fn + p * K1Q_TC, fl_p + p * ncv);
+      cp_async8(s_fn + (9 + p) * K1Q_TC, fh_p + p * ncv);
+    }
+    cp_async_commit();
+  }
+  double g0[NT], g1[NT], gnl0[NT], gnl1[NT], gnh0[NT], gnh1[NT], v0[NT], v1[NT];
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const int t = te + NOE * tf;
+      const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
+      g0[t] = Fo[lp * ncv]; g1[t] = Fo[(lp + PS1) * ncv];
+      gnl0[t] = Fl[lp * ncv]; gnl1[t] = Fl[(lp + PS1) * ncv];
+      gnh0[t] = Fh[lp * ncv]; gnh1[t] = Fh[(lp + PS1) * ncv];
+      v0[t] = vo[(2 * t) * ncv]; v1[t] = vo[(2 * t + 1) * ncv];
+    }
   double go0[NT], go1[NT], gn_lo[NT], gn_hi[NT];
 #pragma unroll
   for (int m = 0; m < Q::NSL; ++m) rd[m] = 0.0;
@@ -596,53 +700,44 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
     for (int te = 0; te < NOE; ++te) {
       const int t = te + NOE * tf;
       const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
-      const double u0 = ulo[t], u1 = umid[t], u2 = uhi[t];
-      const double g0 = g[lp], g1 = g[lp + PS1];
       // volume term: sum over the two DG nodes of the line of  w g vhat dpsi_i/dxi_d
-      const double vh0 = tb.LC[0][0] * u0 + tb.LC[0][1] * u1 + tb.LC[0][2] * u2;
-      const double vh1 = tb.LC[1][0] * u0 + tb.LC[1][1] * u1 + tb.LC[1][2] * u2;
-      const double vol = tb.wv * (g0 * vh0 + g1 * vh1);
+      const double vol = tb.wv * (g0[t] * v0[t] + g1[t] * v1[t]);
       rd[lp] += tb.dl[0] * vol;
       rd[lp + PS1] += tb.dl[1] * vol;
       // traces of g on the two faces: own side, and the neighbour's side
-      go0[t] = tb.E0[0] * g0 + tb.E0[1] * g1;
-      go1[t] = tb.E1[0] * g0 + tb.E1[1] * g1;
+      go0[t] = tb.E0[0] * g0[t] + tb.E0[1] * g1[t];
+      go1[t] = tb.E1[0] * g0[t] + tb.E1[1] * g1[t];
       gn_lo[t] = tb.E1[0] * gnl0[t] + tb.E1[1] * gnl1[t];   // lower cell, its xi_d = 1 face
       gn_hi[t] = tb.E0[0] * gnh0[t] + tb.E0[1] * gnh1[t];   // upper cell, its xi_d = 0 face
     }
   double cl[NT], ch[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) { cl[t] = 0.0; ch[t] = 0.0; }
-  // face quadrature: traces at the point (fma chains over the face's NT nodes), upwind flux, back to the nodes.
-  // 3-D: 9 points as a rolled loop (instruction-fetch friendly, like elem_apply); 2-D: 2 points, unrolled.
-  auto face_point = [&](const double (&oo)[NT], double w) {
-    double unl = 0.0, unh = 0.0, g1l = 0.0, g2l = 0.0, g1h = 0.0, g2h = 0.0;
+  // face quadrature: traces at the point (fma chains over the face's NT nodes), upwind flux, back to the nodes
+  auto face_point = [&](const double (&oo)[NT], double cfl, double cfh) {
+    double g1l = 0.0, g2l = 0.0, g1h = 0.0, g2h = 0.0;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      unl = __fma_rn(ulo[t], oo[t], unl); unh = __fma_rn(uhi[t], oo[t], unh);
       g1l = __fma_rn(gn_lo[t], oo[t], g1l); g2l = __fma_rn(go0[t], oo[t], g2l);   // lower face: element 1 = lower cell, 2 = this cell
       g1h = __fma_rn(go1[t], oo[t], g1h); g2h = __fma_rn(gn_hi[t], oo[t], g2h);   // upper face: element 1 = this cell
     }
-    {
-      const double a = 0.5 * unl, b = 0.5 * fabs(unl);
-      const double fl = (w * (a + b)) * g1l - (w * (b - a)) * g2l;
+    const double fl = cfl * (cfl >= 0.0 ? g1l : g2l);
+    const double fh = cfh * (cfh >= 0.0 ? g1h : g2h);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) cl[t] = __fma_rn(fl, oo[t], cl[t]);
-    }
-    {
-      const double a = 0.5 * unh, b = 0.5 * fabs(unh);
-      const double fh = (w * (a + b)) * g1h - (w * (b - a)) * g2h;
-#pragma unroll
-      for (int t = 0; t < NT; ++t) ch[t] = __fma_rn(fh, oo[t], ch[t]);
-    }
+    for (int t = 0; t < NT; ++t) { cl[t] = __fma_rn(fl, oo[t], cl[t]); ch[t] = __fma_rn(fh, oo[t], ch[t]); }
   };
   if constexpr (HY) {
+    // 9 points as a rolled loop (instruction-fetch friendly, like elem_apply).  The 18 face coefficients were sent on
+    // their way to the thread's own shared-memory slots (cp.async, s_fn[point][lane]) before the prologue's loads:
+    // their latency hides behind the prologue instead of stalling the loop (ncu: long-scoreboard at the first use of
+    // a register-prefetched row was a quarter of all warp-stall samples).
+    cp_async_wait<0>();
 #pragma unroll 1
     for (int p = 0; p < 9; ++p) {
       const int qf = p / 3, qe = p - 3 * qf;
       const double* o = c_OOF3[qe][qf];
       const double oo[NT] = {o[0], o[1], o[2], o[3]};
-      face_point(oo, c_WF3[qe][qf]);
+      face_point(oo, s_fn[p * K1Q_TC], s_fn[(9 + p) * K1Q_TC]);
     }
   } else {
 #pragma unroll
@@ -657,7 +752,7 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
             const double oe = (NFE == 1) ? 1.0 : tb.OF[qe][te], of = (NFF == 1) ? 1.0 : tb.OF[qf][tf];
             oo[te + NOE * tf] = oe * of;
           }
-        face_point(oo, ((NFE == 1) ? 1.0 : tb.fw[qe]) * ((NFF == 1) ? 1.0 : tb.fw[qf]));
+        face_point(oo, fl_p[(qe + NFE * qf) * ncv], fh_p[(qe + NFE * qf) * ncv]);
       }
   }
 #pragma unroll
@@ -666,46 +761,51 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
     for (int te = 0; te < NOE; ++te) {
       const int t = te + NOE * tf;
       const int lp = (D == 0) ? 2 * te + 2 * (HY ? 2 : 1) * tf : (D == 1 ? te + 4 * tf : te + 2 * tf);
-      if (cd > 0) {  // rows of element 2 of the lower face: + flux * psi_i(xi_d = 0)
+      if (lo) {  // rows of element 2 of the lower face: + flux * psi_i(xi_d = 0)
         rd[lp] += tb.E0[0] * cl[t];
         rd[lp + PS1] += tb.E0[1] * cl[t];
       }
-      if (cd + 1 < nd) {  // rows of element 1 of the upper face: - flux * psi_i(xi_d = 1)
+      if (hi) {  // rows of element 1 of the upper face: - flux * psi_i(xi_d = 1)
         rd[lp] -= tb.E1[0] * ch[t];
         rd[lp + PS1] -= tb.E1[1] * ch[t];
       }
     }
 }
 
-// One thread per (owned cell, direction) like K1 pass A: the CTA stages F of its K1Q_TC cells in shared memory, each
-// thread forms its direction's part of Kt F (volume term + both faces of the cell along that direction), the three
-// parts meet in shared memory as  r = (r_x + r_y) + r_z,  and the update runs one thread per DG dof (coalesced).
+// One thread per (owned cell, direction) like K1 pass A: each thread forms its direction's part of Kt F (volume term +
+// both faces of the cell along that direction) from coalesced loads, the three parts meet in shared memory as
+// r = (r_x + r_y) + r_z, and the update runs one thread per DG dof (S is cell-major like the host's vector: coalesced).
 // (Round 1's version: one thread per cell through all directions, 254 -> 128 registers with spills, 17 % of the HBM
 // roofline.)
+#ifndef IMPES_K1QS_REGS
+#define IMPES_K1QS_REGS 128
+#endif
 template <bool HY, bool RATE>
-__global__ void __launch_bounds__(K1Q_TC * (HY ? 3 : 2)) __maxnreg__(HY ? 96 : 80)
-k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x, const double* __restrict__ phi,
-        const double* __restrict__ Sin, const double* __restrict__ Fin, double* __restrict__ Sout,
-        double* __restrict__ Fout) {
+__global__ void __launch_bounds__(K1Q_TC * (HY ? 3 : 2)) __maxnreg__(HY ? IMPES_K1QS_REGS : 80)
+k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, long ncv, const double* __restrict__ vh, const double* __restrict__ fn,
+        const double* __restrict__ phi, const double* __restrict__ Sin, const double* __restrict__ Fin,
+        double* __restrict__ Sout, double* __restrict__ Fout) {
   using Q = QD<HY>;
-  constexpr int ND = HY ? 3 : 2, THREADS = K1Q_TC * ND, PS = Q::NSL + 1;
-  __shared__ double s_g[K1Q_TC * PS];        // F of the CTA's cells
-  __shared__ double s_r[ND * K1Q_TC * PS];   // per-direction parts of Kt F
+  using SQ = SatQ<HY>;
+  constexpr int ND = SQ::ND, THREADS = SQ::THREADS, PS = Q::NSL + 1;
+  __shared__ double s_r[ND * K1Q_TC * PS];         // per-direction parts of Kt F
+  __shared__ double s_f[HY ? ND * 18 * K1Q_TC : 1];   // 3-D: face coefficients, [direction][lower 9 | upper 9][lane]
   const int tid = threadIdx.x;
   const int ci = tid % K1Q_TC, dir = tid / K1Q_TC;
   const unsigned t0 = blockIdx.x * (unsigned)K1Q_TC;
   const unsigned nc = min((unsigned)K1Q_TC, (unsigned)L.ncl - t0);
-  const long sb0 = ((long)t0 + L.plane) * Q::NSL;   // first DG dof of the CTA's cells (cell-major, ghost plane below)
+  const long c0 = (long)t0 + L.plane;               // cvec index of the CTA's first cell (owned cells are contiguous)
+  const long sb0 = c0 * Q::NSL;                     // its first DG dof in the cell-major S
   constexpr int NIT = (K1Q_TC * Q::NSL + THREADS - 1) / THREADS;
+  // operands of the update pass (one DG dof per thread and pass): in flight during the flux computation
+  double phi_r[NIT], sin_r[NIT];
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const unsigned e = tid + it * THREADS;
-    if (e < nc * Q::NSL) {
-      const unsigned c = e / Q::NSL, m = e - c * Q::NSL;
-      cp_async8(s_g + c * PS + m, Fin + sb0 + e);
-    }
+    const bool in = e < nc * Q::NSL;
+    phi_r[it] = phi[c0 + (in ? e / Q::NSL : 0)];
+    sin_r[it] = RATE ? 0.0 : Sin[sb0 + (in ? e : 0)];
   }
-  cp_async_commit();
   Cell1 q;
   {
     q.ok = (unsigned)ci < nc;
@@ -718,20 +818,11 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x, con
     q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
     q.pb = L.off_p + q.c * L.npl;
   }
-  const double* g = s_g + (q.ok ? ci : 0) * PS;
   double* rd = s_r + (dir * K1Q_TC + ci) * PS;
-  if (dir == 0) q_sat_dir<HY, 0>(L, q, tb, x, Fin, g, rd);
-  else if (HY && dir == 1) q_sat_dir<HY, 1>(L, q, tb, x, Fin, g, rd);
-  else q_sat_dir<HY, 2>(L, q, tb, x, Fin, g, rd);
-  // operands of the update pass (one DG dof per thread and pass), all in flight before the barrier
-  double phi_r[NIT], sin_r[NIT];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const unsigned e = tid + it * THREADS;
-    const bool in = e < nc * Q::NSL;
-    phi_r[it] = phi[(long)t0 + L.plane + (in ? e / Q::NSL : 0)];
-    sin_r[it] = RATE ? 0.0 : Sin[sb0 + (in ? e : 0)];
-  }
+  double* sfn = s_f + (HY ? dir * 18 * K1Q_TC + ci : 0);
+  if (dir == 0) q_sat_dir<HY, 0>(L, q, tb, ncv, Fin, vh, fn, sfn, rd);
+  else if (HY && dir == 1) { if constexpr (HY) q_sat_dir<HY, 1>(L, q, tb, ncv, Fin, vh, fn, sfn, rd); }
+  else q_sat_dir<HY, 2>(L, q, tb, ncv, Fin, vh, fn, sfn, rd);
   __syncthreads();
   const double wm = sp.vol * tb.wv;
 #pragma unroll
@@ -768,17 +859,21 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, const double* __restrict__ x, con
         mobilities(ph, so, mw, mo);
         fo = div_rcp(mw, mw + mo);   // FS [REF src/saturation_solver.cpp:8-17]
       }
-      Fout[sb0 + e] = fo;
+      Fout[(long)m * ncv + c0 + c] = fo;   // dof-major
     }
   }
 }
 
 // f(S) over a flat dof range (ghost planes included)
-__global__ void __launch_bounds__(BLK) k_frac_flat(long n, Phys ph, int two_phase, const double* __restrict__ S,
+// S: cell-major (nsl dofs per cell); F: dof-major, F[m ncv + c] (the layout of the DG-Q1 stage kernel)
+__global__ void __launch_bounds__(BLK) k_frac_flat(long ncv, int nsl, Phys ph, int two_phase, const double* __restrict__ S,
                                                    double* __restrict__ F) {
+  const long n = ncv * nsl;
   for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
     const double s = S[i];
-    F[i] = two_phase ? frac_flow_of(ph, s) : s;
+    const long c = i / nsl;
+    const int m = (int)(i - c * nsl);
+    F[(long)m * ncv + c] = two_phase ? frac_flow_of(ph, s) : s;
   }
 }
 // guards over a flat owned dof range
