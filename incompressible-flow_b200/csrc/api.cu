@@ -473,15 +473,21 @@ int update_coeff(impes_ctx* h) {
   const Lay& L = h->L;
   RET_IF(exchange_planes(h, h->S[h->scur], true, true, h->nsl));
   if (h->os == 1) {  // S in DG-Q1: 1/lambda at the mass-rule points, diag(M) by quadrature, Schur diagonal
-    Scope sc(h, KI_COEFF, 3);
-    const int g = (int)((L.ncv + BLK - 1) / BLK);
+    const bool slab = L.nranks > 1;
+    Scope sc(h, KI_COEFF, slab ? 5 : 4);
+    const int g = (int)(((long)L.ncv * h->nqp + BLK - 1) / BLK);   // one thread per (cell, mass-rule point)
+    const int ga = (L.ncl + K1Q_TC - 1) / K1Q_TC, gs = (2 * L.plane + BLK - 1) / BLK;
     if (L.has_y) {
       k1q_rlam<true><<<g, BLK, 0, h->stream>>>(L, h->ph, h->qt, h->S[h->scur], h->rlam);
-      k1q_md<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], h->Md, h->T);
+      k1q_md_a<true><<<ga, K1QS<true>::THREADS, sizeof(double) * K1Q_TC * K1QS<true>::RS, h->stream>>>(h->L1, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], h->Md, h->T, h->yup);
+      k1q_md_b<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->Md, h->T, h->yup);
+      if (slab) k1q_md_slab<true><<<gs, BLK, 0, h->stream>>>(h->L1, h->qt, h->rlam, h->K[2], h->geo[2], h->Md, h->T);
       k1_schur_diag<true><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, h->Md);
     } else {
       k1q_rlam<false><<<g, BLK, 0, h->stream>>>(L, h->ph, h->qt, h->S[h->scur], h->rlam);
-      k1q_md<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], h->Md, h->T);
+      k1q_md_a<false><<<ga, K1QS<false>::THREADS, sizeof(double) * K1Q_TC * K1QS<false>::RS, h->stream>>>(h->L1, h->qt, h->rlam, h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], h->Md, h->T, h->yup);
+      k1q_md_b<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->Md, h->T, h->yup);
+      if (slab) k1q_md_slab<false><<<gs, BLK, 0, h->stream>>>(h->L1, h->qt, h->rlam, h->K[2], h->geo[2], h->Md, h->T);
       k1_schur_diag<false><<<h->grid_dofs1, BLK, 0, h->stream>>>(h->L1, h->rc, h->T, h->Md);
     }
   } else
@@ -765,7 +771,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
   double* qb = q1 ? y + h->L1.off_p : nullptr;
   double* qa = h->mg1_ya;
   const double* qD = q1 ? h->Md + h->L1.off_p : nullptr;
-  const int gq = q1 ? (int)(((long)L.ncl * h->L1.npl + BLK - 1) / BLK) : 0;  // one thread per L2 dof
+  const int gq = q1 ? (int)(((long)L.ncl * h->L1.npl + BLK - 1) / BLK) : 0;  // 256-dof blocks (one thread per pair of L2 dofs)
+  const int gdot = std::min(gq, h->num_sms * IMPES_MGQ_MINB2);               // resident grid of the sweep with the fused dot
   auto q1_smooth = [&](int sweeps, bool from_zero) -> int {
     for (int s = 0; s < sweeps; ++s) {
       double* in = (s & 1) ? qa : qb;
@@ -773,8 +780,13 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
       const int first = from_zero && s == 0;
       if (!first && multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
       Scope sc(h, first ? KI_MGQ_FIRST : KI_MGQ_JACOBI, 1);
-      if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
-      else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, first, st);
+      if (first) {  // owned L2 dofs = one contiguous range of the p-part (16-byte aligned: npl is even, parts are padded)
+        const long n2 = (long)L.ncl * h->L1.npl / 2;
+        const size_t o2 = qpe / 2;
+        k1_mg_first<<<h->num_sms * 8, BLK, 0, h->stream>>>(n2, reinterpret_cast<const double2*>(qD) + o2, reinterpret_cast<const double2*>(qr) + o2,
+                                                           reinterpret_cast<double2*>(out) + o2, h->mg_omega, st);
+      } else if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
+      else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
     }
     return 0;
   };
@@ -835,8 +847,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
     if (multi) RET_IF(mg_halo(h, mg[0].yb, (size_t)L.plane, L.nzl));
     {
       Scope sc(h, KI_MGQ_JACOBI, 1);
-      if (L.has_y) k1_mg_jacobi<true, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
-      else k1_mg_jacobi<false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, mg[0].yb, h->mg_cfac);
+      if (L.has_y) k1_mg_jacobi<true, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, (unsigned)gq, mg[0].yb, h->mg_cfac);
+      else k1_mg_jacobi<false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, (unsigned)gq, mg[0].yb, h->mg_cfac);
     }
     for (int s = 1; s < h->mg_nu; ++s) {
       double* in = (s & 1) ? qa : qb;
@@ -844,11 +856,11 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
       if (multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
       Scope sc(h, KI_MGQ_JACOBI, 1);
       if (dot && s + 1 == h->mg_nu) {  // last sweep: finishes beta^2 = <v0, P v0> (see k1_mg_jacobi<.., DOT>)
-        if (L.has_y) k1_mg_jacobi<true, false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
-        else k1_mg_jacobi<false, false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+        if (L.has_y) k1_mg_jacobi<true, false, true><<<gdot, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+        else k1_mg_jacobi<false, false, true><<<gdot, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
       } else {
-        if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
-        else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st);
+        if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
+        else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
       }
     }
   }
@@ -1504,6 +1516,13 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
       CK(cudaMemcpyToSymbol(c_OO3, t.OO, sizeof t.OO));
       CK(cudaMemcpyToSymbol(c_OOF3, t.OOF, sizeof t.OOF));
       CK(cudaMemcpyToSymbol(c_WF3, wf, sizeof wf));
+      double oosq[4][4][4];
+      for (int qe = 0; qe < 4; ++qe)
+        for (int qf = 0; qf < 4; ++qf)
+          for (int tf = 0; tf < 2; ++tf)
+            for (int te = 0; te < 2; ++te)
+              oosq[qe][qf][te + 2 * tf] = (t.O[qe][te] * t.O[qe][te]) * (t.O[qf][tf] * t.O[qf][tf]);
+      CK(cudaMemcpyToSymbol(c_OO3SQ, oosq, sizeof oosq));
     }
     h->nqp = d.dim == 3 ? 64 : 9;
     h->nup = d.dim == 3 ? 12 : 4;

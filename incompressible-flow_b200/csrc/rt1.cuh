@@ -545,10 +545,10 @@ struct Pair1 {
   int a1, a2, l0;  // transverse indices of the pair and local index of its first dof
 };
 template <bool HY>
-__device__ __forceinline__ Pair1 owned_pair1(const Lay1& L) {
+__device__ __forceinline__ Pair1 owned_pair1(const Lay1& L, unsigned blk) {
   constexpr int NG = HY ? 4 : 2, NPL = HY ? 8 : 4;
   Pair1 d;
-  const unsigned t = blockIdx.x * (unsigned)MGQ_T + threadIdx.x;
+  const unsigned t = blk * (unsigned)MGQ_T + threadIdx.x;
   const unsigned cell = t / NG, g = t % NG;
   d.a1 = HY ? (int)(g & 1) : 0;
   d.a2 = HY ? (int)(g >> 1) : (int)g;
@@ -678,44 +678,53 @@ template <bool HY, bool PRO = false, bool DOT = false>
 __global__ void __launch_bounds__(MGQ_T, (PRO || DOT) ? IMPES_MGQ_MINB2 : IMPES_MGQ_MINB) k1_mg_jacobi(Lay1 L, Rt1Const C, const double* __restrict__ T,
                                                       const double* __restrict__ Dp, const double* __restrict__ rp,
                                                       const double* __restrict__ yin, double* __restrict__ yout,
-                                                      double omega, int first, const MinresState* st,
+                                                      double omega, int first, const MinresState* st, unsigned nblk,
                                                       const double* __restrict__ ec = nullptr, double cfac = 0.0,
                                                       double* partial_p = nullptr, const double* partial_u = nullptr,
                                                       unsigned n_u_chunks = 0, double* out = nullptr,
                                                       unsigned* ticket = nullptr) {
   if (st && st->done) return;
-  const Pair1 d = owned_pair1<HY>(L);
-  const int p = d.q.pb + d.l0;
-  const double2v rv = ld2(rp + p), dd = ld2(Dp + p);
-  if (first) {
+  // DOT: nblk 256-dof blocks are walked by a grid of resident CTAs (block b -> partial_p[b]) so that the fence +
+  // ticket of the final reduction is paid once per CTA, not once per block (ncu, one CTA per block: barrier 2.9 and
+  // membar 0.5 stalls per issue, 365 us against 215 us for the plain sweep at 128^3); otherwise one block per CTA.
+  for (unsigned blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const Pair1 d = owned_pair1<HY>(L, blk);
+    const int p = d.q.pb + d.l0;
+    const double2v rv = ld2(rp + p), dd = ld2(Dp + p);
+    if (first) {   // kept for 2-D / callers without the streaming kernel k1_mg_first
+      if (d.q.ok) {
+        double2 o;
+        o.x = omega * div_rcp(rv.v0, dd.v0);   // same bits as `/`, half the instructions
+        o.y = omega * div_rcp(rv.v1, dd.v1);
+        *reinterpret_cast<double2*>(yout + p) = o;
+      }
+      continue;
+    }
+    double2v ys = ld2(yin + p);
+    if constexpr (PRO) {
+      const double e = cfac * ec[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)];
+      ys.v0 = ys.v0 + e; ys.v1 = ys.v1 + e;
+    }
+    double sum0, sum1;
+    q1_rows_pair<HY, PRO>(L, C, d, T, yin, ys.v0, ys.v1, ec, cfac, sum0, sum1);
+    const double sy0 = dd.v0 * ys.v0 + sum0, sy1 = dd.v1 * ys.v1 + sum1;
+    const double yn0 = ys.v0 + omega * div_rcp(rv.v0 - sy0, dd.v0), yn1 = ys.v1 + omega * div_rcp(rv.v1 - sy1, dd.v1);
     if (d.q.ok) {
       double2 o;
-      o.x = omega * div_rcp(rv.v0, dd.v0);   // same bits as `/`, half the instructions
-      o.y = omega * div_rcp(rv.v1, dd.v1);
+      o.x = yn0; o.y = yn1;
       *reinterpret_cast<double2*>(yout + p) = o;
     }
-    return;
-  }
-  double2v ys = ld2(yin + p);
-  if constexpr (PRO) {
-    const double e = cfac * ec[d.q.i + L.NX * (d.q.j + L.NY * d.q.kl)];
-    ys.v0 = ys.v0 + e; ys.v1 = ys.v1 + e;
-  }
-  double sum0, sum1;
-  q1_rows_pair<HY, PRO>(L, C, d, T, yin, ys.v0, ys.v1, ec, cfac, sum0, sum1);
-  const double sy0 = dd.v0 * ys.v0 + sum0, sy1 = dd.v1 * ys.v1 + sum1;
-  const double yn0 = ys.v0 + omega * div_rcp(rv.v0 - sy0, dd.v0), yn1 = ys.v1 + omega * div_rcp(rv.v1 - sy1, dd.v1);
-  if (d.q.ok) {
-    double2 o;
-    o.x = yn0; o.y = yn1;
-    *reinterpret_cast<double2*>(yout + p) = o;
+    if constexpr (DOT) {
+      __shared__ double smb[8];
+      const double s = block_tree_256_pairs(d.q.ok ? rv.v0 * yn0 : 0.0, d.q.ok ? rv.v1 * yn1 : 0.0, smb);
+      if (threadIdx.x == 0) partial_p[blk] = s;
+      __syncthreads();   // smb is reused by the next block
+    }
   }
   if constexpr (DOT) {
     __shared__ double sm[8];
     __shared__ int is_last;
-    const double s = block_tree_256_pairs(d.q.ok ? rv.v0 * yn0 : 0.0, d.q.ok ? rv.v1 * yn1 : 0.0, sm);
     if (threadIdx.x == 0) {
-      partial_p[blockIdx.x] = s;
       __threadfence();
       is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
@@ -725,7 +734,7 @@ __global__ void __launch_bounds__(MGQ_T, (PRO || DOT) ? IMPES_MGQ_MINB2 : IMPES_
       // thread t of the canonical 256-thread reduction block = value slots t (x0) and t + 128 (x1) here:
       // ordered sums of entries t, t + 256, ... like ordered_partial_sum, two slots per thread
       const double a0 = ordered_partial_sum_at(partial_u, n_u_chunks, threadIdx.x), a1 = ordered_partial_sum_at(partial_u, n_u_chunks, threadIdx.x + 128);
-      const double b0 = ordered_partial_sum_at(partial_p, gridDim.x, threadIdx.x), b1 = ordered_partial_sum_at(partial_p, gridDim.x, threadIdx.x + 128);
+      const double b0 = ordered_partial_sum_at(partial_p, nblk, threadIdx.x), b1 = ordered_partial_sum_at(partial_p, nblk, threadIdx.x + 128);
       __syncthreads();
       const double ta = block_tree_256_split(a0, a1, sm);
       __syncthreads();
@@ -738,6 +747,20 @@ __global__ void __launch_bounds__(MGQ_T, (PRO || DOT) ? IMPES_MGQ_MINB2 : IMPES_
   }
 }
 
+// first sweep from a zero initial guess: y = omega (r / D) over the owned L2 dofs, a contiguous range of the p-part
+// (the generic sweep kernel spends its few resident warps on index arithmetic: 0.51 of the HBM roofline for 3 streams)
+__global__ void __launch_bounds__(BLK) k1_mg_first(long n2, const double2* __restrict__ D, const double2* __restrict__ r,
+                                                   double2* __restrict__ y, double omega, const MinresState* st) {
+  if (st && st->done) return;
+  for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n2; i += (long)gridDim.x * BLK) {
+    const double2 rv = r[i], dd = D[i];
+    double2 o;
+    o.x = omega * div_rcp(rv.x, dd.x);
+    o.y = omega * div_rcp(rv.y, dd.y);
+    y[i] = o;
+  }
+}
+
 // cell rhs = sum over the cell's dofs (local order) of the residual r - S y
 template <bool HY>
 __global__ void __launch_bounds__(MGQ_T, IMPES_MGQ_MINB2) k1_mg_restrict(Lay1 L, Rt1Const C, const double* __restrict__ T,
@@ -746,7 +769,7 @@ __global__ void __launch_bounds__(MGQ_T, IMPES_MGQ_MINB2) k1_mg_restrict(Lay1 L,
                                                         const MinresState* st) {
   constexpr int NG = HY ? 4 : 2;
   if (st && st->done) return;
-  const Pair1 d = owned_pair1<HY>(L);
+  const Pair1 d = owned_pair1<HY>(L, blockIdx.x);
   const int p = d.q.pb + d.l0;
   const double2v ys = ld2(y + p), rv = ld2(rp + p), dd = ld2(Dp + p);
   double sum0, sum1;

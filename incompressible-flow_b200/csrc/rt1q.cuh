@@ -40,6 +40,7 @@ struct QTab {
 __constant__ double c_OO3[4][4][4];
 __constant__ double c_OOF3[3][3][4];
 __constant__ double c_WF3[3][3];   // fw[qe] * fw[qf] of the 3-D face rule
+__constant__ double c_OO3SQ[4][4][4];  // 3-D: (O[qe][te] O[qe][te]) * (O[qf][tf] O[qf][tf]) at [qe][qf][te + 2 tf] (k1q_md_a)
 
 template <bool HY>
 struct QD {
@@ -61,33 +62,33 @@ __device__ __forceinline__ double ob(const QTab& tb, int dir, int q, int t) { re
 // K4 (os = 1): w_q / lambda(S(x_q)) at the mass-rule points of every cell (ghost planes included)
 // CWVectorCoefficient::Eval with a DG-Q1 GridFunctionCoefficient [REF src/param.hpp:246-261]
 // ---------------------------------------------------------------------------------------
+// One thread per (cell, point): coalesced stores of the cell-major point array (the one-thread-per-cell form wrote 64
+// doubles per lane with a 512-byte stride between lanes).  Same sums in the same order as before.
 template <bool HY>
 __global__ void __launch_bounds__(BLK) k1q_rlam(Lay L, Phys ph, QTab tb, const double* __restrict__ S,
                                                 double* __restrict__ rlam) {
   using Q = QD<HY>;
-  const int c = blockIdx.x * BLK + threadIdx.x;
-  if (c >= L.ncv) return;
-  const int k = c / L.plane - 1 + L.zlo;
-  double* out = rlam + (long)c * Q::NQP;
-  if (k < 0 || k >= L.NZ) {
-    for (int q = 0; q < Q::NQP; ++q) out[q] = 0.0;
-    return;
+  __shared__ double s_O[4][2], s_gw[4];   // run-time point indices: shared-memory copies of the tables
+  if (threadIdx.x < 8) s_O[threadIdx.x >> 1][threadIdx.x & 1] = (threadIdx.x & 1) ? tb.O[threadIdx.x >> 1][1] : tb.O[threadIdx.x >> 1][0];
+  if (threadIdx.x >= 32 && threadIdx.x < 36) {
+    const int q = threadIdx.x - 32;
+    s_gw[q] = q == 0 ? tb.gw[0] : (q == 1 ? tb.gw[1] : (q == 2 ? tb.gw[2] : tb.gw[3]));
   }
-  double s[Q::NSL];
+  __syncthreads();
+  const long e = (long)blockIdx.x * BLK + threadIdx.x;
+  if (e >= (long)L.ncv * Q::NQP) return;
+  const int c = (int)(e / Q::NQP), q = (int)(e - (long)c * Q::NQP);
+  const int k = c / L.plane - 1 + L.zlo;
+  if (k < 0 || k >= L.NZ) { rlam[e] = 0.0; return; }
+  const int q0 = q % Q::NQ, q1 = (q / Q::NQ) % Q::NQY, q2 = q / (Q::NQ * Q::NQY);
+  double sq = 0.0;
 #pragma unroll
-  for (int m = 0; m < Q::NSL; ++m) s[m] = S[(long)c * Q::NSL + m];
-  for (int q2 = 0; q2 < Q::NQ; ++q2)
-    for (int q1 = 0; q1 < Q::NQY; ++q1)
-      for (int q0 = 0; q0 < Q::NQ; ++q0) {
-        double sq = 0.0;
-#pragma unroll
-        for (int m = 0; m < Q::NSL; ++m) {
-          const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
-          sq += s[m] * (tb.O[q0][m0] * ob<HY>(tb, 1, q1, m1) * tb.O[q2][m2]);
-        }
-        const double w = tb.gw[q0] * (HY ? tb.gw[q1] : 1.0) * tb.gw[q2];
-        out[q0 + Q::NQ * (q1 + Q::NQY * q2)] = w / lambda_of(ph, sq);
-      }
+  for (int m = 0; m < Q::NSL; ++m) {
+    const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
+    sq += S[(long)c * Q::NSL + m] * (s_O[q0][m0] * (HY ? s_O[q1][m1] : 1.0) * s_O[q2][m2]);
+  }
+  const double w = s_gw[q0] * (HY ? s_gw[q1] : 1.0) * s_gw[q2];
+  rlam[e] = w / lambda_of(ph, sq);
 }
 
 // transverse directions (e < f) of direction D and the stride of a mass-rule point index along each direction
@@ -543,6 +544,186 @@ __global__ void __launch_bounds__(BLK) k1q_apply_b(Lay1 L, const double* __restr
       }
     }
   }
+}
+
+// ---- the same diag(M) / T, two passes in the shape of K1 (k1q_apply_a / _b below).  k1q_md above walks 36 + 12 node
+// sums of 64 terms per thread straight from global memory with a 512-byte stride between lanes: 21.6 ms at 192^3,
+// ten K1 applications.  Here pass A runs one thread per (owned cell, direction), the c_q of the CTA's cells staged by
+// coalesced cp.async, ONE walk over the 64 points feeding the 12 node sums of the direction (each sum adds the same
+// terms  (c_q (C C)) ((Oe Oe)(Of Of))  in the same order qf, qe, qd as q_diag: same bits); it completes interior and
+// boundary nodes, leaves its own part on lower-face nodes and hands the upper-face part to the upper neighbour through
+// up[cell][dir][line] (the K1 scratch).  Pass B: md = lower cell's part + own part (q_md_dir's order), T = 1 / md.
+// Lower faces of a slab's bottom plane and the ghost node plane above its top plane involve ghost cells: k1q_md_slab
+// (the direct form, two cell planes only).
+template <bool HY, int D>
+__device__ __forceinline__ void q_md_a_dir(const Lay1& L, const Cell1& q, const QTab& tb, const double* rl,
+                                           const double* __restrict__ K, double geo, double* __restrict__ Md,
+                                           double* __restrict__ T, double* __restrict__ up) {
+  using R = QDir<HY, D>;
+  using Q = QD<HY>;
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F), NT = NOE * NOF;
+  constexpr int DI = HY ? D : (D == 0 ? 0 : 1);
+  double s[3][NT];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) s[i][t] = 0.0;
+  auto pair = [&](const double* rq, const double (&oo)[NT]) {
+#pragma unroll
+    for (int qd = 0; qd < Q::NQ; ++qd) {
+      const double c = rq[qd * R::sq(D)];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double ci = c * (tb.C[qd][i] * tb.C[qd][i]);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) s[i][t] += ci * oo[t];
+      }
+    }
+  };
+  if constexpr (HY) {
+#pragma unroll 1
+    for (int p = 0; p < 16; ++p) {   // qf outer, qe inner
+      const int qe = p & 3, qf = p >> 2;
+      const double* o = c_OO3SQ[qe][qf];
+      const double oo[NT] = {o[0], o[1], o[2], o[3]};
+      pair(rl + qe * R::sq(R::E) + qf * R::sq(R::F), oo);
+    }
+  } else {
+#pragma unroll
+    for (int qf = 0; qf < R::nq(R::F); ++qf)
+#pragma unroll
+      for (int qe = 0; qe < R::nq(R::E); ++qe) {
+        double oo[NT];
+#pragma unroll
+        for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+          for (int te = 0; te < NOE; ++te) {
+            const double oe = ob<HY>(tb, R::E, qe, te), of = ob<HY>(tb, R::F, qf, tf);
+            oo[te + NOE * tf] = (oe * oe) * (of * of);
+          }
+        pair(rl + qe * R::sq(R::E) + qf * R::sq(R::F), oo);
+      }
+  }
+  if (!q.ok) return;
+  const double sc = geo / K[q.c];
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      const int t = te + NOE * tf;
+      if (l.cd > 0) Md[l.base] = sc * s[0][t];   // own part; pass B / k1q_md_slab add the lower cell's
+      else { Md[l.base] = 1.0; T[l.base] = 0.0; }
+      const double md1 = sc * s[1][t];
+      Md[l.base + l.sd] = md1; T[l.base + l.sd] = 1.0 / md1;
+      if (l.cd + 1 == l.nd) { Md[l.base + 2 * l.sd] = 1.0; T[l.base + 2 * l.sd] = 0.0; }
+      else up[(long)q.c * Q::NUP + DI * Q::NL + t] = sc * s[2][t];
+    }
+}
+template <bool HY>
+__global__ void __launch_bounds__(K1QS<HY>::THREADS) __maxnreg__(HY ? 96 : 80)
+k1q_md_a(Lay1 L, QTab tb, const double* __restrict__ rlam, const double* __restrict__ Kx, const double* __restrict__ Ky,
+         const double* __restrict__ Kz, double gx, double gy, double gz, double* __restrict__ Md, double* __restrict__ T,
+         double* __restrict__ up) {
+  using Q = QD<HY>;
+  using S = K1QS<HY>;
+  extern __shared__ double k1q_sm[];
+  double* s_rl = k1q_sm;   // [TC][RS]
+  const int tid = threadIdx.x;
+  const int ci = tid % K1Q_TC, dir = tid / K1Q_TC;
+  const unsigned t0 = blockIdx.x * (unsigned)K1Q_TC;
+  const unsigned nc = min((unsigned)K1Q_TC, (unsigned)L.ncl - t0);
+  const double* g_rl = rlam + ((long)t0 + L.plane) * Q::NQP;
+  constexpr int NRL = (K1Q_TC * Q::NQP + S::THREADS - 1) / S::THREADS;
+#pragma unroll
+  for (int it = 0; it < NRL; ++it) {
+    const unsigned e = tid + it * S::THREADS;
+    if (e < nc * Q::NQP) {
+      const unsigned c = e / Q::NQP, qq = e - c * Q::NQP;
+      cp_async8(s_rl + c * S::RS + qq, g_rl + e);
+    }
+  }
+  cp_async_commit();
+  Cell1 q;
+  {
+    q.ok = (unsigned)ci < nc;
+    const unsigned tt = q.ok ? t0 + ci : t0;
+    const unsigned r = fastdiv(tt, L.fdx);
+    q.i = (int)(tt - r * (unsigned)L.NX);
+    q.kl = (int)fastdiv(r, L.fdy);
+    q.j = (int)(r - (unsigned)q.kl * (unsigned)L.NY);
+    q.k = q.kl + L.zlo;
+    q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+    q.pb = L.off_p + q.c * L.npl;
+  }
+  const double* rl = s_rl + (q.ok ? ci : 0) * S::RS;
+  cp_async_wait<0>();
+  __syncthreads();
+  if (dir == 0) q_md_a_dir<HY, 0>(L, q, tb, rl, Kx, gx, Md, T, up);
+  else if (HY && dir == 1) { if constexpr (HY) q_md_a_dir<HY, 1>(L, q, tb, rl, Ky, gy, Md, T, up); }
+  else q_md_a_dir<HY, 2>(L, q, tb, rl, Kz, gz, Md, T, up);
+}
+// pass B: lower-face nodes whose lower cell belongs to the slab
+template <bool HY, int D>
+__device__ __forceinline__ void q_md_b_dir(const Lay1& L, const Cell1& q, double* __restrict__ Md, double* __restrict__ T,
+                                           const double* __restrict__ up) {
+  using R = QDir<HY, D>;
+  using Q = QD<HY>;
+  constexpr int NOE = R::no(R::E), NOF = R::no(R::F);
+  constexpr int DI = HY ? D : (D == 0 ? 0 : 1);
+  if (D == 2 && q.kl == 0) return;   // the lower cell is a ghost (or absent): k1q_md_slab
+#pragma unroll
+  for (int tf = 0; tf < NOF; ++tf)
+#pragma unroll
+    for (int te = 0; te < NOE; ++te) {
+      const Line1 l = line_of<HY, D>(L, q, te, tf);
+      if (l.cd > 0) {
+        const double md = up[(long)(q.c - l.cstride) * Q::NUP + DI * Q::NL + te + NOE * tf] + Md[l.base];
+        Md[l.base] = md; T[l.base] = 1.0 / md;
+      }
+    }
+}
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1q_md_b(Lay1 L, double* __restrict__ Md, double* __restrict__ T,
+                                                const double* __restrict__ up) {
+  const Cell1 q = owned_cell1(L);
+  if (!q.ok) return;
+  q_md_b_dir<HY, 0>(L, q, Md, T, up);
+  if constexpr (HY) q_md_b_dir<HY, 1>(L, q, Md, T, up);
+  q_md_b_dir<HY, 2>(L, q, Md, T, up);
+}
+// z-face nodes shared with the neighbouring slabs (multi-GPU only): block 0.. of the grid = bottom owned plane (lower
+// face nodes), the second half = top owned plane (the ghost node plane above).  Direct form of q_md_dir.
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k1q_md_slab(Lay1 L, QTab tb, const double* __restrict__ rlam,
+                                                   const double* __restrict__ Kz, double gz, double* __restrict__ Md,
+                                                   double* __restrict__ T) {
+  using R = QDir<HY, 2>;
+  using Q = QD<HY>;
+  const int t = blockIdx.x * BLK + threadIdx.x;
+  if (t >= 2 * L.plane) return;
+  const int side = t / L.plane, ip = t - side * L.plane;
+  Cell1 q;
+  q.i = ip % L.NX; q.j = ip / L.NX; q.kl = side ? L.nzl - 1 : 0; q.k = q.kl + L.zlo;
+  q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
+  q.pb = L.off_p + q.c * L.npl; q.ok = true;
+  if (side == 0 && (q.k == 0 || (L.nzl == 1 && false))) return;
+  if (side == 1 && q.k + 1 >= L.NZ) return;
+  const double* rl = rlam + (long)q.c * Q::NQP;
+  const double sc = gz / Kz[q.c];
+  for (int tf = 0; tf < R::no(R::F); ++tf)
+    for (int te = 0; te < R::no(R::E); ++te) {
+      const Line1 l = line_of<HY, 2>(L, q, te, tf);
+      if (side == 0) {
+        const int cl = q.c - l.cstride;
+        const double md = (gz / Kz[cl]) * q_diag<HY, 2>(tb, rlam + (long)cl * Q::NQP, 2, te, tf) + sc * q_diag<HY, 2>(tb, rl, 0, te, tf);
+        Md[l.base] = md; T[l.base] = 1.0 / md;
+      } else {
+        const int cu = q.c + l.cstride;
+        const double md = sc * q_diag<HY, 2>(tb, rl, 2, te, tf) + (gz / Kz[cu]) * q_diag<HY, 2>(tb, rlam + (long)cu * Q::NQP, 0, te, tf);
+        Md[l.base + 2 * l.sd] = md; T[l.base + 2 * l.sd] = 1.0 / md;
+      }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
