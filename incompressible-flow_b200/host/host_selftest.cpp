@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <fstream>
+#include <sstream>
 #include <vector>
 
 #include "dofmap.hpp"
@@ -73,6 +75,42 @@ int main(int argc, char** argv) {
     std::remove(f32.c_str());
     std::remove(f64.c_str());
     std::cout << "ok binary_io" << std::endl;
+  }
+  {  // .vts writers [REF src/utilities.cpp:126-472]: the 2-D per-cell file byte for byte, the shapes of the others
+    auto slurp = [](const std::string& f) { std::ifstream in(f); std::stringstream ss; ss << in.rdbuf(); return ss.str(); };
+    auto count = [](const std::string& s, const std::string& w) { size_t n = 0; for (size_t p = s.find(w); p != std::string::npos; p = s.find(w, p + 1)) ++n; return n; };
+    const std::string f = tmp + "/impes_selftest.vts";
+    mfem::Vector c2(2); c2(0) = 0.25; c2(1) = 1.5;
+    write_vts_scalar_cells(f, "saturation", 4.0, 3.0, 2, 1, c2);
+    const std::string want =
+        "<?xml version=\"1.0\"?>\n<VTKFile type=\"StructuredGrid\" version=\"0.1\">\n"
+        "  <StructuredGrid WholeExtent=\"1 3 1 2 1 1\">\n    <Piece Extent=\"1 3 1 2 1 1\">\n"
+        "      <CellData Scalars=\"saturation\">\n"
+        "        <DataArray type=\"Float64\" Name=\"saturation\" format=\"ascii\" NumberOfComponents=\"1\">\n"
+        "0.25 1.5 \n        </DataArray>\n      </CellData>\n      <Points>\n"
+        "        <DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n"
+        "0 0 0.0 2 0 0.0 4 0 0.0 0 3 0.0 2 3 0.0 4 3 0.0 \n"
+        "        </DataArray>\n      </Points>\n    </Piece>\n  </StructuredGrid>\n</VTKFile>\n";
+    CHECK(slurp(f) == want);
+    mfem::Vector v3(3 * 3 * 2), w3(3 * 3 * 2), z3(3 * 3 * 2), c3(2 * 2 * 1);
+    for (int i = 0; i < 18; ++i) { v3(i) = 3.0; w3(i) = 4.0; z3(i) = 12.0; }
+    c3 = 0.5;
+    write_vts_vector(f, "velocity", 1.0, 1.0, 1.0, 2, 2, 1, v3, w3, z3);
+    std::string t = slurp(f);
+    CHECK(t.find("WholeExtent=\"1 3 1 3 1 2\"") != std::string::npos && t.find("Name=\"velocity_scalar_mag\"") != std::string::npos);
+    CHECK(count(t, "3 4 12 ") == 18 && count(t, "13 ") == 18);   // components, then |v| = 13 at every vertex
+    write_vts_scalar_cells(f, "pressure", 1.0, 1.0, 1.0, 2, 2, 1, c3);
+    t = slurp(f);
+    CHECK(t.find("<CellData Scalars=\"pressure\">") != std::string::npos && count(t, "0.5 ") >= 4);
+    mfem::Vector s2(6); s2 = 2.0;
+    write_vts_scalar(f, "saturation", 4.0, 3.0, 2, 1, s2);   // 2-D vertex files: y extent in the third slot
+    t = slurp(f);
+    CHECK(t.find("WholeExtent=\"1 3 1 1 1 2\"") != std::string::npos && t.find("<PointData Scalars=\"saturation\">") != std::string::npos);
+    write_vts_vector(f, "velocity", 4.0, 3.0, 2, 1, s2, s2);
+    t = slurp(f);
+    CHECK(count(t, "2 2 0.0 ") == 6 && t.find("_scalar_mag") == std::string::npos);
+    std::remove(f.c_str());
+    std::cout << "ok vts" << std::endl;
   }
   {  // init_arrays: constants, files, porosity floor [REF src/param.cpp:78-113]
     Param p;

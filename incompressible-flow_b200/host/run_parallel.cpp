@@ -5,7 +5,7 @@
 // data).  Process placement comes from the environment instead of MPI_Init:
 //   IMPES_RANK / IMPES_WORLD_SIZE (or torchrun's RANK / WORLD_SIZE), IMPES_NCCL_ID_FILE (bootstrap, solver_context.hpp);
 // the CUDA device is -device + the local rank (IMPES_LOCAL_RANK / LOCAL_RANK, default: the rank).
-// VisIt / .vts output is not reproduced (off the hot path); pressure and saturation per-cell .bin dumps are.
+// VisIt output is not reproduced (off the hot path); pressure and saturation per-cell .bin + .vts dumps are.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -51,11 +51,20 @@ void output_cells(const Param& p, const double* local, long n_local_dofs, int do
   const long ncl = n_local_dofs / dofs_per_cell;
   vector<float> cells(ncl);
   for (long c = 0; c < ncl; ++c) cells[c] = (float)local[c * dofs_per_cell + dofs_per_cell - 1];
+  // the .vts twin of the dump [REF src/utilities.cpp:587-630]: the float32 values the .bin holds, as cell data
+  auto write_vts = [&](const vector<float>& v) {
+    Vector x((int)v.size());
+    for (size_t c = 0; c < v.size(); ++c) x((int)c) = v[c];
+    const string fv = base.substr(0, base.size() - 4) + ".vts";
+    if (p.spacedim == 2) write_vts_scalar_cells(fv, name, p.sx, p.sy, p.nx, p.ny, x);
+    else write_vts_scalar_cells(fv, name, p.sx, p.sy, p.sz, p.nx, p.ny, p.nz, x);
+  };
   if (world == 1) {
     FILE* f = fopen(base.c_str(), "wb");
     MFEM_VERIFY(f, "cannot open " + base);
     fwrite(cells.data(), sizeof(float), ncl, f);
     fclose(f);
+    write_vts(cells);
     return;
   }
   const string part = base + ".part" + d2s(rank);
@@ -85,6 +94,7 @@ void output_cells(const Param& p, const double* local, long n_local_dofs, int do
   MFEM_VERIFY(f, "cannot open " + base);
   fwrite(all.data(), sizeof(float), all.size(), f);
   fclose(f);
+  write_vts(all);
 }
 }  // namespace
 

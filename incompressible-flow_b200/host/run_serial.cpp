@@ -43,13 +43,13 @@ void output_saturation_cells(const Param& p, const Vector& S_own, const DofMap& 
     map.to_native(S_own.GetData(), nat.data());
     S = nat.data();
   }
-  if (nsl == 1) {
-    write_binary(fname.c_str(), n, S);
-    return;
-  }
-  std::vector<double> in_cells(n);
-  for (int c = 0; c < n; ++c) in_cells[c] = S[(long)c * nsl + nsl - 1];
-  write_binary(fname.c_str(), n, in_cells.data());
+  Vector in_cells(n);
+  for (int c = 0; c < n; ++c) in_cells(c) = S[(long)c * nsl + nsl - 1];
+  write_binary(fname.c_str(), n, in_cells.GetData());
+  // the .vts twin [REF src/utilities.cpp:565-582]
+  const string fvts = fname.substr(0, fname.size() - 4) + ".vts";
+  if (p.spacedim == 2) write_vts_scalar_cells(fvts, "saturation", p.sx, p.sy, p.nx, p.ny, in_cells);
+  else write_vts_scalar_cells(fvts, "saturation", p.sx, p.sy, p.sz, p.nx, p.ny, p.nz, in_cells);
 }
 }  // namespace
 

@@ -10,6 +10,23 @@
 void read_binary(const char* filename, int n_values, double* values);
 void write_binary(const char* filename, int n_values, const double* values);
 
+// VTK StructuredGrid (.vts, ascii) writers of the reference, same signatures and file layout
+// [REF src/utilities.hpp:109-139] [REF src/utilities.cpp:126-472]: vertex-based vector / scalar fields
+// ((nx+1)(ny+1)(nz+1) values, x fastest) and per-cell scalars (nx ny nz values).  2-D files have extent 1 in z.
+namespace mfem { class Vector; }
+void write_vts_vector(const std::string& filename, const std::string& solname, double sx, double sy, double sz, int nx,
+                      int ny, int nz, const mfem::Vector& sol_x, const mfem::Vector& sol_y, const mfem::Vector& sol_z);
+void write_vts_vector(const std::string& filename, const std::string& solname, double sx, double sy, int nx, int ny,
+                      const mfem::Vector& sol_x, const mfem::Vector& sol_y);
+void write_vts_scalar(const std::string& filename, const std::string& solname, double sx, double sy, double sz, int nx,
+                      int ny, int nz, const mfem::Vector& sol);
+void write_vts_scalar(const std::string& filename, const std::string& solname, double sx, double sy, int nx, int ny,
+                      const mfem::Vector& sol);
+void write_vts_scalar_cells(const std::string& filename, const std::string& solname, double sx, double sy, double sz,
+                            int nx, int ny, int nz, const mfem::Vector& sol);
+void write_vts_scalar_cells(const std::string& filename, const std::string& solname, double sx, double sy, int nx,
+                            int ny, const mfem::Vector& sol);
+
 // number -> string with optional zero padding (file names "..._000003.bin") [REF src/utilities.hpp:29-62]
 template <typename T>
 inline std::string d2s(T data, bool scientific = false, int precision = 0, bool noperiod = false, int width = 0) {

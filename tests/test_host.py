@@ -21,7 +21,7 @@ def host_bins(native_lib):
 def test_host_selftest(host_bins, tmp_path):
     out = subprocess.run([host_bins[1], str(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    for name in ("defaults", "options", "binary_io", "init_arrays", "dofmap"):
+    for name in ("defaults", "options", "binary_io", "vts", "init_arrays", "dofmap"):
         assert f"ok {name}" in out.stdout
 
 
