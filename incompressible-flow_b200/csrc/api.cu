@@ -911,7 +911,7 @@ int minres_iteration(impes_ctx* h, double* u1, double* q, double* v0, double* v1
       const Lay1& Q = h->L1;
       const long pz = (long)Q.gz0 * Q.gz1;
       const long own_z0 = Q.off_z + 2 * pz, own_z1 = own_z0 + pz * (2 * Q.nzl + (Q.zhi == Q.NZ ? 1 : 0));
-      k_minres_b_dot<<<h->n_u_chunks_all, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, q, v0, v1, h->Md, q, h->scal + 0, st_cur,
+      k_minres_b_dot<<<h->n_u_chunks_all, MINRES_B_T, 0, h->stream>>>(h->vec_n, h->vec_offp, q, v0, v1, h->Md, q, h->scal + 0, st_cur,
                                                                (long)Q.off_z, own_z0, own_z1, (long)Q.off_p, h->partial_u);
     }
     RET_IF(schur_prec(h, v0, q, st_cur, true));
@@ -2122,7 +2122,7 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
       case IMPES_KERNEL_MINRES_UPDATE: {
         { Scope sc(h, KI_MINRES_B, 1);
         if (h->fold_dot)
-          k_minres_b_dot<<<h->n_u_chunks_all, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
+          k_minres_b_dot<<<h->n_u_chunks_all, MINRES_B_T, 0, h->stream>>>(h->vec_n, h->vec_offp, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,
                                                                    h->st + 2, 0L, 0L, 0L, 0L, h->partial_u);
         else
         k_minres_b<<<h->grid_vec, BLK, 0, h->stream>>>(h->vec_n, h->vec_offp, h->q, h->v0, h->v1, h->Md, h->q, h->scal + 2,

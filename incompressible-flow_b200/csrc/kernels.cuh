@@ -89,6 +89,26 @@ __device__ __forceinline__ double block_tree_256_split(double x0, double x1, dou
   return s;
 }
 
+// block_tree_256 over 256 values held two per thread by a 128-thread CTA (value 2t, 2t+1 in thread t): the same
+// butterfly (xor 16, 8, 4, 2, 1 over the VALUE index inside groups of 32) and the same ordered sum of the 8 group
+// results, hence the same bits.  Result valid in thread 0.  sm: 8 doubles.
+__device__ __forceinline__ double block_tree_256_pairs(double x0, double x1, double* sm) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {   // value-index xor 16, 8, 4, 2 = lane xor 8, 4, 2, 1
+    x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+    x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+  }
+  const double v = x0 + x1;           // value-index xor 1
+  if ((threadIdx.x & 15) == 0) sm[threadIdx.x >> 4] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[w];
+  }
+  return s;
+}
+
 // Block partial -> partial[blockIdx.x]; the last block to arrive adds all partials in index
 // order (thread t takes t, t+256, ...; then the same tree) and writes *out.  Deterministic:
 // which block is last does not matter.
@@ -382,11 +402,21 @@ __global__ void __launch_bounds__(BLK) k_minres_b(long n, long n_u, const double
                                                   const double* alpha_p, const MinresState* st) {
   if (st->done) return;
   const double alpha = *alpha_p, beta = st->beta, m0 = st->m0, m1 = st->m1;
-  for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
-    const double t = q_in[i] + (-beta) * (v0[i] * m0);
-    const double v = t + (-alpha) * (v1[i] * m1);
-    v0[i] = v;
-    if (i < n_u) q_out[i] = v / Md[i];
+  // two entries per thread and trip (n and n_u are multiples of 32)
+  for (long i = 2 * ((long)blockIdx.x * BLK + threadIdx.x); i < n; i += 2 * (long)gridDim.x * BLK) {
+    const double2 qi = *reinterpret_cast<const double2*>(q_in + i);
+    const double2 a = *reinterpret_cast<const double2*>(v0 + i), b = *reinterpret_cast<const double2*>(v1 + i);
+    double2 v;
+    const double t0 = qi.x + (-beta) * (a.x * m0), t1 = qi.y + (-beta) * (a.y * m0);
+    v.x = t0 + (-alpha) * (b.x * m1);
+    v.y = t1 + (-alpha) * (b.y * m1);
+    *reinterpret_cast<double2*>(v0 + i) = v;
+    if (i < n_u) {
+      const double2 md = *reinterpret_cast<const double2*>(Md + i);
+      double2 qv;
+      qv.x = v.x / md.x; qv.y = v.y / md.y;
+      *reinterpret_cast<double2*>(q_out + i) = qv;
+    }
   }
 }
 
@@ -398,32 +428,43 @@ __global__ void __launch_bounds__(BLK) k_minres_b(long n, long n_u, const double
 // Schur preconditioner (k1_mg_jacobi<.., DOT>).  Entries in [x0, x1) u [x2, x3) are ghost layers (stale on several
 // GPUs) and padding; they are updated like everything else but left out of the sum.
 constexpr int DOT_CHUNK = 16384;
-__global__ void __launch_bounds__(BLK) k_minres_b_dot(long n, long n_u, const double* q_in,
-                                                      double* __restrict__ v0, const double* __restrict__ v1,
-                                                      const double* __restrict__ Md, double* q_out,
-                                                      const double* alpha_p, const MinresState* st,
-                                                      long x0, long x1, long x2, long x3, double* __restrict__ partial_u) {
+constexpr int MINRES_B_T = 128;   // threads of a pass-B CTA: thread t owns slots 2t, 2t + 1 of the canonical 256-slot block,
+                                  // i.e. entries 2t + 256 k (+1) of its chunk -- one 16-byte access per vector and trip
+                                  // (the 8-byte form ran at 0.79 of the HBM roofline; pass C gained 11 % the same way)
+__global__ void __launch_bounds__(MINRES_B_T) k_minres_b_dot(long n, long n_u, const double* q_in,
+                                                             double* __restrict__ v0, const double* __restrict__ v1,
+                                                             const double* __restrict__ Md, double* q_out,
+                                                             const double* alpha_p, const MinresState* st,
+                                                             long x0, long x1, long x2, long x3, double* __restrict__ partial_u) {
   if (st->done) return;
   const double alpha = *alpha_p, beta = st->beta, m0 = st->m0, m1 = st->m1;
   const long base = (long)blockIdx.x * DOT_CHUNK;
-  double acc = 0.0;
+  double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 4
   for (int k = 0; k < DOT_CHUNK / BLK; ++k) {
-    const long i = base + threadIdx.x + k * BLK;
+    const long i = base + 2 * threadIdx.x + k * BLK;   // even; n and n_u are multiples of 32
     if (i < n) {
-      const double t = q_in[i] + (-beta) * (v0[i] * m0);
-      const double v = t + (-alpha) * (v1[i] * m1);
-      v0[i] = v;
+      const double2 qi = *reinterpret_cast<const double2*>(q_in + i);
+      const double2 a = *reinterpret_cast<const double2*>(v0 + i), b = *reinterpret_cast<const double2*>(v1 + i);
+      double2 v;
+      const double t0 = qi.x + (-beta) * (a.x * m0), t1 = qi.y + (-beta) * (a.y * m0);
+      v.x = t0 + (-alpha) * (b.x * m1);
+      v.y = t1 + (-alpha) * (b.y * m1);
+      *reinterpret_cast<double2*>(v0 + i) = v;
       if (i < n_u) {
-        const double qv = v / Md[i];
-        q_out[i] = qv;
-        const bool ghost = (i >= x0 && i < x1) || (i >= x2 && i < x3);
-        acc += ghost ? 0.0 : v * qv;
+        const double2 md = *reinterpret_cast<const double2*>(Md + i);
+        double2 qv;
+        qv.x = v.x / md.x; qv.y = v.y / md.y;
+        *reinterpret_cast<double2*>(q_out + i) = qv;
+        const bool g0 = (i >= x0 && i < x1) || (i >= x2 && i < x3);
+        const bool g1 = (i + 1 >= x0 && i + 1 < x1) || (i + 1 >= x2 && i + 1 < x3);
+        acc0 += g0 ? 0.0 : v.x * qv.x;
+        acc1 += g1 ? 0.0 : v.y * qv.y;
       }
     }
   }
-  __shared__ double sm[BLK / 32];
-  const double s = block_tree_256(acc, sm);
+  __shared__ double sm[8];
+  const double s = block_tree_256_pairs(acc0, acc1, sm);
   if (threadIdx.x == 0) partial_u[blockIdx.x] = s;
 }
 
@@ -455,12 +496,24 @@ __global__ void __launch_bounds__(BLK) k_minres_c(long n, double* __restrict__ w
   const double etan = -sigma1n * eta;
   const double m = 1.0 / beta;
   const double mu = st->mu;
-  for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
-    const double t = a * w0[i] + c * w1[i];
-    const double w = t + e * (LAZYU ? u1[i] * mu : u1[i]);
-    w0[i] = w;
-    x[i] += xf * w;
-    if (!LAZYU) q[i] *= m;
+  // two entries per thread and trip (16-byte accesses; n is a multiple of 32, the vectors are 256-byte aligned)
+  const long n2 = n >> 1;
+  double2* w0v = reinterpret_cast<double2*>(w0);
+  const double2* w1v = reinterpret_cast<const double2*>(w1);
+  const double2* u1v = reinterpret_cast<const double2*>(u1);
+  double2* xv = reinterpret_cast<double2*>(x);
+  double2* qv = reinterpret_cast<double2*>(q);
+#pragma unroll 2
+  for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n2; i += (long)gridDim.x * BLK) {
+    const double2 a0 = w0v[i], a1 = w1v[i], uu = u1v[i];
+    double2 xx = xv[i], w;
+    const double t0 = a * a0.x + c * a1.x, t1 = a * a0.y + c * a1.y;
+    w.x = t0 + e * (LAZYU ? uu.x * mu : uu.x);
+    w.y = t1 + e * (LAZYU ? uu.y * mu : uu.y);
+    w0v[i] = w;
+    xx.x += xf * w.x; xx.y += xf * w.y;
+    xv[i] = xx;
+    if (!LAZYU) { double2 qq = qv[i]; qq.x *= m; qq.y *= m; qv[i] = qq; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     MinresState s = *st;

@@ -645,26 +645,6 @@ __device__ __forceinline__ void q1_rows_pair(const Lay1& L, const Rt1Const& C, c
 #undef IMPES_Q1_ROW
 }
 
-// block_tree_256 over 256 values held two per thread by a 128-thread CTA (value 2t, 2t+1 in thread t): the same
-// butterfly (xor 16, 8, 4, 2, 1 over the VALUE index inside groups of 32) and the same ordered sum of the 8 group
-// results, hence the same bits.  Result valid in thread 0.  sm: 8 doubles.
-__device__ __forceinline__ double block_tree_256_pairs(double x0, double x1, double* sm) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {   // value-index xor 16, 8, 4, 2 = lane xor 8, 4, 2, 1
-    x0 += __shfl_xor_sync(0xffffffffu, x0, o);
-    x1 += __shfl_xor_sync(0xffffffffu, x1, o);
-  }
-  const double v = x0 + x1;           // value-index xor 1
-  if ((threadIdx.x & 15) == 0) sm[threadIdx.x >> 4] = v;
-  __syncthreads();
-  double s = 0.0;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += sm[w];
-  }
-  return s;
-}
-
 // One damped-Jacobi sweep on the Q1 level: first = 1: y_out = omega (r / D) (zero initial guess), else
 // y_out = y_in + omega ((r - S y_in) / D).
 // PRO: the first post-smoothing sweep with the prolongation fused in: yin is the iterate before
