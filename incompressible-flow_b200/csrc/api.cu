@@ -469,6 +469,9 @@ int allreduce_scalar(impes_ctx* h, double* p) {
 // ---- coefficient update (K4) -------------------------------------------------------------------
 int mg_gather(impes_ctx* h, double* full, size_t pe);
 MgLevel mg_view(const impes_ctx* h, const MgLevel& v);
+#ifndef IMPES_APPLYB_RESIDENT
+#define IMPES_APPLYB_RESIDENT 0   // 1: K1 pass B with the fused dot as a resident grid (measured: 2 % slower than one CTA per block)
+#endif
 int update_coeff(impes_ctx* h) {
   const Lay& L = h->L;
   RET_IF(exchange_planes(h, h->S[h->scur], true, true, h->nsl));
@@ -555,8 +558,8 @@ int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState*
     {
       Scope sc(h, KI_DARCY_Q1B, 1);
 #define KQB(HY, DOT)                                                                                               \
-  k1q_apply_b<HY, DOT><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, x, y, h->yup, h->accA, h->partial, h->scal + 0, \
-                                                             h->ticket, st)
+  k1q_apply_b<HY, DOT><<<(DOT && IMPES_APPLYB_RESIDENT) ? std::min(h->grid_cells, h->num_sms * 8) : h->grid_cells, BLK, 0, h->stream>>>( \
+      h->L1, x, y, h->yup, h->accA, h->partial, h->scal + 0, h->ticket, st, (unsigned)h->grid_cells)
       if (h->L.has_y) { if (dot) KQB(true, true); else KQB(true, false); }
       else { if (dot) KQB(false, true); else KQB(false, false); }
 #undef KQB

@@ -47,9 +47,9 @@ struct Cell1 {
   int i, j, kl, k, c, pb;  // c: cvec index (ghost plane below included), pb: index of the cell's first p dof
   bool ok;
 };
-__device__ __forceinline__ Cell1 owned_cell1(const Lay1& L) {
+__device__ __forceinline__ Cell1 owned_cell1_at(const Lay1& L, unsigned blk) {
   Cell1 q;
-  const unsigned t = blockIdx.x * (unsigned)BLK + threadIdx.x;
+  const unsigned t = blk * (unsigned)BLK + threadIdx.x;
   q.ok = t < (unsigned)L.ncl;
   const unsigned tt = q.ok ? t : 0u;
   const unsigned r = fastdiv(tt, L.fdx);
@@ -61,6 +61,7 @@ __device__ __forceinline__ Cell1 owned_cell1(const Lay1& L) {
   q.pb = L.off_p + q.c * L.npl;
   return q;
 }
+__device__ __forceinline__ Cell1 owned_cell1(const Lay1& L) { return owned_cell1_at(L, blockIdx.x); }
 
 // Line geometry of one (cell, direction, transverse pair): index of closed node 0, stride along the line,
 // position of the cell along the line, local index of the line's first pressure dof and the stride between

@@ -503,37 +503,46 @@ __device__ __forceinline__ void q_face_dir(const Lay1& L, const Cell1& q, const 
       }
     }
 }
+// DOT: the nblk 256-cell blocks are walked by a resident grid (block b -> partial[b], partial[nblk + b]) so that the
+// fence + ticket of the final reduction is paid once per CTA (ncu, one CTA per block: barrier 15.7 stalls per issue).
 template <bool HY, bool DOT>
 __global__ void __launch_bounds__(BLK) k1q_apply_b(Lay1 L, const double* __restrict__ x, double* __restrict__ y,
                                                    const double* __restrict__ yup, const double* __restrict__ accA,
                                                    double* partial, double* out, unsigned* ticket,
-                                                   const MinresState* st) {
+                                                   const MinresState* st, unsigned nblk) {
   if (st && st->done) return;
-  const Cell1 q = owned_cell1(L);
-  double acc = 0.0, accq = 0.0;
-  if (q.ok) {
-    const double mu = st ? st->mu : 1.0;
-    q_face_dir<HY, 0, DOT>(L, q, x, mu, y, yup, acc);
-    if constexpr (HY) q_face_dir<HY, 1, DOT>(L, q, x, mu, y, yup, acc);
-    q_face_dir<HY, 2, DOT>(L, q, x, mu, y, yup, acc);
-    if (DOT) accq = accA[blockIdx.x * (unsigned)BLK + threadIdx.x];
+  __shared__ double sm[BLK / 32];
+  for (unsigned blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const Cell1 q = owned_cell1_at(L, blk);
+    double acc = 0.0, accq = 0.0;
+    if (q.ok) {
+      const double mu = st ? st->mu : 1.0;
+      q_face_dir<HY, 0, DOT>(L, q, x, mu, y, yup, acc);
+      if constexpr (HY) q_face_dir<HY, 1, DOT>(L, q, x, mu, y, yup, acc);
+      q_face_dir<HY, 2, DOT>(L, q, x, mu, y, yup, acc);
+      if (DOT) accq = accA[blk * (unsigned)BLK + threadIdx.x];
+    }
+    if (DOT) {
+      const double sa = block_tree_256(accq, sm);
+      __syncthreads();
+      const double sb = block_tree_256(acc, sm);
+      if (threadIdx.x == 0) {
+        partial[blk] = sa;
+        partial[nblk + blk] = sb;
+      }
+      __syncthreads();   // sm is reused by the next block
+    }
   }
   if (DOT) {
-    __shared__ double sm[BLK / 32];
     __shared__ int is_last;
-    const double sa = block_tree_256(accq, sm);
-    __syncthreads();
-    const double sb = block_tree_256(acc, sm);
     if (threadIdx.x == 0) {
-      partial[blockIdx.x] = sa;
-      partial[gridDim.x + blockIdx.x] = sb;
       __threadfence();
       is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (is_last) {
       __threadfence();
-      const double a = ordered_partial_sum(partial, gridDim.x), b = ordered_partial_sum(partial + gridDim.x, gridDim.x);
+      const double a = ordered_partial_sum(partial, nblk), b = ordered_partial_sum(partial + nblk, nblk);
       __syncthreads();
       const double ta = block_tree_256(a, sm);
       __syncthreads();
