@@ -300,6 +300,8 @@ def rooflines_from_profile(kern, dim, ncl, ndof, peak, traffic, lazy_u=False):
             rec.update(B=int(b), gbs=rnd(b / (us * 1e-6) / 1e9, 4), frac=rnd(b / (us * 1e-6) / 1e9 / peak, 3))
             t = traffic.get(name)
             rec["traffic"] = int(t["bytes_per_cell"] * ncl) if t else None
+            if t and t.get("fp64_pipe_pct", 0) >= 25:   # fp64-pipe co-limited kernels: ncu's pipe utilisation beside the HBM view
+                rec["fp64_pipe_pct_ncu"] = t["fp64_pipe_pct"]
         out.append(rec)
     out.sort(key=lambda r: -r["share"])
     return out
@@ -500,6 +502,9 @@ def main():
         if roofline:
             for k in ("how", "peak_source", "traffic_source"):
                 full_note = roofline.pop(k, None)
+            if roofline["frac"] > 1.0:
+                roofline["note"] = ("peak = measured 1:1 copy bandwidth; this kernel reads 2 bytes per byte written and "
+                                    "moves exactly its algorithmic bytes (see traffic), so it can exceed the copy figure")
         # key order: the driver keeps the END of stdout, so the roofline records come last
         line = {
             "metric": "IMPES cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world,
@@ -509,8 +514,9 @@ def main():
             "iters_per_step": its, "steps_per_s": rnd(1e3 * args.steps / ms), "s_max": rnd(smax), "nonfinite": int(bad),
             "gpu_launches": int(launches), "extras": extras, "same_mesh": same, "parity": parity,
             "isolated_us_l2_flushed": iso, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
-            "rooflines": [[r["k"], r["share"], r["us"], r.get("frac")] for r in rl[:9]],
-            "rooflines_cols": "kernel, share of the profiled step, us per launch, algorithmic-bytes / time / HBM peak",
+            "rooflines": [[r["k"], r["share"], r["us"], r.get("frac"), r.get("fp64_pipe_pct_ncu")] for r in rl[:9]],
+            "rooflines_cols": "kernel, share of the profiled step, us per launch, algorithmic-bytes / time / HBM peak, "
+                              "fp64 pipe utilisation (%) from the committed ncu capture for the fp64-co-limited kernels",
             "roofline": roofline,
         }
         try:

@@ -52,6 +52,7 @@ def main():
             t = traffic.setdefault(variant, {"bytes": [], "us": [], "source": f"profiles/{tag}_ncu_launches.csv ({os.path.basename(rep)}, {ncell} cells)"})
             t["bytes"].append(b)
             t["us"].append(rec.get("gpu__time_duration.sum", 0))
+            t.setdefault("fp64", []).append(rec.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", 0))
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_launches.csv"), "w", newline="") as f:
         w = csv.writer(f)
@@ -62,7 +63,9 @@ def main():
     for variant, t in traffic.items():
         # keep the FULL variant of kernels that also have a cheap one (first jacobi sweep): the largest traffic
         b = max(t["bytes"])
-        table[variant] = {"bytes_per_cell": b / ncell, "us_at_profile": t["us"][t["bytes"].index(b)], "source": t["source"]}
+        i = t["bytes"].index(b)
+        table[variant] = {"bytes_per_cell": b / ncell, "us_at_profile": t["us"][i], "fp64_pipe_pct": round(t["fp64"][i], 1),
+                          "source": t["source"]}
     with open(os.path.join(ROOT, "profiles", f"{tag}_traffic_by_variant.json"), "w") as f:
         json.dump(table, f, indent=1)
     # names as bench.py's rooflines use them
@@ -77,7 +80,7 @@ def main():
             out[name] = by[name]
     if "k1q_apply_a" in by and "k1q_apply_b" in by:
         out["k1q_apply_a+b"] = {"bytes_per_cell": by["k1q_apply_a"]["bytes_per_cell"] + by["k1q_apply_b"]["bytes_per_cell"],
-                                "source": by["k1q_apply_a"]["source"]}
+                                "fp64_pipe_pct": by["k1q_apply_a"]["fp64_pipe_pct"], "source": by["k1q_apply_a"]["source"]}
     bk = [k for k in by if k.startswith("k_minres_b")]
     if bk and "k_minres_c" in by:
         out["k_minres_b+c"] = {"bytes_per_cell": by[bk[0]]["bytes_per_cell"] + by["k_minres_c"]["bytes_per_cell"],
