@@ -1069,13 +1069,15 @@ __global__ void __launch_bounds__(BLK) k_frac_flat(long ncv, int nsl, Phys ph, i
 // guards over a flat owned dof range
 __global__ void __launch_bounds__(BLK) k_guards_flat(long n, const double* __restrict__ S, unsigned long long* n_bad,
                                                      unsigned long long* max_bits) {
+  unsigned bad = 0;
+  unsigned long long key = 0ull;
   for (long i = (long)blockIdx.x * BLK + threadIdx.x; i < n; i += (long)gridDim.x * BLK) {
     const double s = S[i];
-    if (!isfinite(s)) { atomicAdd(n_bad, 1ull); continue; }
-    unsigned long long b = (unsigned long long)__double_as_longlong(s);
-    b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-    atomicMax(max_bits, b);
+    if (!isfinite(s)) { ++bad; continue; }
+    const unsigned long long b = guard_key(s);
+    key = b > key ? b : key;
   }
+  guard_commit(bad, key, n_bad, max_bits);
 }
 
 }  // namespace impes
