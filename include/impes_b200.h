@@ -263,6 +263,10 @@ int  impes_event_record(impes_handle h, int slot);
 int  impes_event_elapsed_ms(impes_handle h, int slot_from, int slot_to, double* ms);
 /* Number of kernels this handle has launched since creation. */
 int64_t impes_launch_count(impes_handle h);
+/* One line naming the kernel variants this handle selected at creation for its mesh and options (spaces, Schur
+ * preconditioner and which of its sweep kernels, multigrid levels, saturation kernel, CUDA graphs).  Returns the
+ * length of the full description; at most buflen - 1 characters are written. */
+int  impes_describe(impes_handle h, char* buf, int buflen);
 /* Device-side milliseconds spent per kernel class since the last reset when
  * profiling is on (impes_profile_enable(h,1)); used for the step breakdown. */
 int  impes_profile_enable(impes_handle h, int on);

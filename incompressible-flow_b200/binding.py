@@ -23,7 +23,7 @@ EXPORTS = [
     "impes_update_coefficients", "impes_darcy_apply", "impes_prec_apply", "impes_get_rhs",
     "impes_get_local_dims", "impes_pressure_solve_local", "impes_saturation_advance_local",
     "impes_set_field_local", "impes_get_field_local",
-    "impes_time_kernel", "impes_event_record", "impes_event_elapsed_ms", "impes_launch_count", "impes_profile_enable", "impes_profile_read",
+    "impes_time_kernel", "impes_event_record", "impes_event_elapsed_ms", "impes_launch_count", "impes_describe", "impes_profile_enable", "impes_profile_read",
     "impes_profile_read_kernels",
 ]
 
@@ -87,6 +87,7 @@ def load_library():
     L.impes_event_elapsed_ms.argtypes = [H, C.c_int, C.c_int, _dp]
     L.impes_launch_count.restype = C.c_int64
     L.impes_launch_count.argtypes = [H]
+    L.impes_describe.argtypes = [H, C.c_char_p, C.c_int]
     L.impes_profile_enable.argtypes = [H, C.c_int]
     L.impes_profile_read.argtypes = [H, _dp, C.POINTER(C.c_int64)]
     L.impes_profile_read_kernels.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_int64)]
@@ -264,6 +265,12 @@ class Solver:
 
     def launch_count(self):
         return int(self.L.impes_launch_count(self.h))
+
+    def describe(self):
+        """one line naming the kernel variants this handle selected (impes_describe)"""
+        buf = C.create_string_buffer(1024)
+        self.L.impes_describe(self.h, buf, 1024)
+        return buf.value.decode()
 
     def profile_enable(self, on=True):
         self._chk(self.L.impes_profile_enable(self.h, int(on)))

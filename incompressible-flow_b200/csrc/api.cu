@@ -81,7 +81,6 @@ struct impes_ctx {
   double* phi = nullptr;
   double* S[2] = {nullptr, nullptr};
   double* F[2] = {nullptr, nullptr};  // f(S) carried beside S (streaming K6)
-  int sat_mode = 0;                   // 0 streaming (fs array), 1 tiled, 2 simple
   int scur = 0;
   double* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // RK stage buffers (lazy)
   double* m[3] = {nullptr, nullptr, nullptr};
@@ -104,12 +103,9 @@ struct impes_ctx {
   // launch geometry
   int grid_cells = 0, grid_vec = 0, grid_sgs = 0, num_sms = 0;
   int sgs_mode = 2, sgs_threads = 256;  // 0 one CTA, 1 cluster, 2 cooperative grid
-  bool sat_simple = false;              // IMPES_SAT_SIMPLE=1: untiled K6 (A/B testing)
-  int sat_tz = 8;                       // planes marched per block in the tiled K6
   bool sgs_skew = false;                // stage-major (skewed) sweep available for this shape
   int sgs_ppt = 1;
   bool sgs_tma = false;                 // one-CTA TMA ring version (<= 1024 pencils)
-  bool sgs_flow = false;                // 2-D warp-dataflow version (no block barrier)
   int sgs_ns = 0;
   size_t sgs_smem = 0;
   SgsPack pack = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
@@ -672,9 +668,7 @@ int launch_sgs(impes_ctx* h, const double* r, double* y, int fwd, int bwd, const
   if (h->sgs_skew) {
     Scope sc(h, KI_SGS, 2 + (fwd ? 1 : 0));
     if (fwd) k_sgs_skew_in<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->pack, r, st);
-    if (h->sgs_flow)
-      k_sgs_flow2d<<<1, h->sgs_threads, h->sgs_smem, h->stream>>>(L, h->pack, T, y, fwd, bwd, st);
-    else if (h->sgs_tma)
+    if (h->sgs_tma)
       launch_sgs_tma(h, y, fwd, bwd, st);
     else if (h->sgs_mode == 0) RET_IF(launch_skew_sweep<0>(h, y, fwd, bwd, st));
     else RET_IF(launch_skew_sweep<1>(h, y, fwd, bwd, st));
@@ -1120,35 +1114,17 @@ int launch_sat(impes_ctx* h, bool rate, const double* Sin, double* Sout, const d
     }
     return 0;
   }
-  if (h->sat_mode == 0) {
-    if (rate) k_sat_stream<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
-    else k_sat_stream<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
-    return 0;
-  }
-  if (h->sat_mode == 2) {
-    if (rate) k_sat_substep<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Sout);
-    else k_sat_substep<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Sout);
-    return 0;
-  }
-  if (L.has_y) {
-    dim3 g((L.NX + 29) / 30, (L.NY + 5) / 6, (L.nzl + h->sat_tz - 1) / h->sat_tz);
-    if (rate) k_sat_tile<32, 8, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
-    else k_sat_tile<32, 8, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
-  } else {
-    dim3 g((L.NX + 253) / 254, 1, (L.nzl + h->sat_tz - 1) / h->sat_tz);
-    if (rate) k_sat_tile<256, 1, true><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
-    else k_sat_tile<256, 1, false><<<g, 256, 0, h->stream>>>(L, h->ph, h->sp, h->sat_tz, satv, h->phi, Sin, Sout);
-  }
+  // DG_0: streaming form, f(S) carried as a second resident array (round 1's tiled / untiled alternatives measured slower
+  // and were removed)
+  if (rate) k_sat_stream<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
+  else k_sat_stream<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->ph, h->sp, satv, h->phi, Sin, Fin, Sout, Fout);
   return 0;
 }
 
 int sat_rate(impes_ctx* h, double* Sin, double* out) {  // out = M_phi^-1 (Kt f(Sin) + b)
   RET_IF(exchange_planes(h, Sin, true, true, h->nsl));
-  if (h->sat_mode == 0) {
-    RET_IF(launch_frac(h, Sin, h->F[0]));
-    return launch_sat(h, true, Sin, out, h->F[0], nullptr);
-  }
-  return launch_sat(h, true, Sin, out);
+  RET_IF(launch_frac(h, Sin, h->F[0]));
+  return launch_sat(h, true, Sin, out, h->F[0], nullptr);
 }
 int axpby(impes_ctx* h, double a, const double* x, double b, const double* y, double* out) {
   Scope sc(h, KI_SAT_AUX, 1);
@@ -1185,20 +1161,15 @@ int saturation_device(impes_ctx* h, double global_dt, double dt, int* nsub) {
     double* S = h->S[h->scur];
     double* Sn = h->S[h->scur ^ 1];
     if (ode == 1) {
-      if (h->sat_mode == 0) {
-        // f(S) travels with S: F[scur] = f(S[scur]); only its ghost planes are exchanged per sub-step
-        if (ti == 1) {
-          RET_IF(exchange_planes(h, S, true, true, h->nsl));
-          RET_IF(launch_frac(h, S, h->F[h->scur]));
-        } else {
-          if (h->os == 1) RET_IF(exchange_planes_dofmajor(h, h->F[h->scur], h->nsl));   // F[m ncv + c]
-          else RET_IF(exchange_planes(h, h->F[h->scur], true, true, h->nsl));
-        }
-        RET_IF(launch_sat(h, false, S, Sn, h->F[h->scur], h->F[h->scur ^ 1]));
+      // f(S) travels with S: F[scur] = f(S[scur]); only its ghost planes are exchanged per sub-step
+      if (ti == 1) {
+        RET_IF(exchange_planes(h, S, true, true, h->nsl));
+        RET_IF(launch_frac(h, S, h->F[h->scur]));
       } else {
-        RET_IF(exchange_planes(h, S, true, true));
-        RET_IF(launch_sat(h, false, S, Sn));
+        if (h->os == 1) RET_IF(exchange_planes_dofmajor(h, h->F[h->scur], h->nsl));   // F[m ncv + c]
+        else RET_IF(exchange_planes(h, h->F[h->scur], true, true, h->nsl));
       }
+      RET_IF(launch_sat(h, false, S, Sn, h->F[h->scur], h->F[h->scur ^ 1]));
       h->scur ^= 1;
     } else if (ode == 2) {  // RK2Solver(a = 1)
       const double a = 1.0, bb = 0.5 / a;
@@ -1618,21 +1589,6 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
           CK(cudaFuncSetAttribute(k_sgs_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         }
       }
-      {
-        // warp-dataflow variant (no block barrier): bit-identical, but measured slower than the TMA ring
-        // kernel on B200 (485 vs 258 ns per stage on C2) -- opt-in only
-        bool flow = false;
-        if (const char* e = getenv("IMPES_SGS_FLOW")) flow = atoi(e) != 0 && !L.has_y && npair <= 512;
-        if (flow) {
-          h->sgs_flow = true;
-          h->sgs_tma = false;
-          h->sgs_mode = 0;
-          h->grid_sgs = 1;
-          h->sgs_threads = (int)((npair + 31) / 32 * 32);
-          h->sgs_smem = (size_t)(h->sgs_threads / 32) * FLOW_PD * FLOW_NOP * 32 * sizeof(double);
-          CK(cudaFuncSetAttribute(k_sgs_flow2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sgs_smem));
-        }
-      }
       RET_IF(dev_alloc(h, &h->pack_blk, nstage * h->pack.SS));
       RET_IF(dev_alloc(h, &h->pack.Yb, nstage * h->pack.NPs));
       h->pack.Rs = h->pack_blk;
@@ -1671,15 +1627,6 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     }
   }
 
-  {  // K6 tiling: enough blocks for >= 2 waves when the mesh allows it
-    if (const char* e = getenv("IMPES_SAT_SIMPLE")) h->sat_simple = atoi(e) != 0;
-    if (const char* e = getenv("IMPES_SAT_MODE")) h->sat_mode = atoi(e);
-    if (h->sat_simple) h->sat_mode = 2;
-    const long tiles = L.has_y ? (long)((L.NX + 29) / 30) * ((L.NY + 5) / 6) : (long)((L.NX + 253) / 254);
-    long tz = (tiles * L.nzl) / (2L * h->num_sms);
-    h->sat_tz = (int)std::max<long>(1, std::min<long>(16, tz));
-    if (const char* e = getenv("IMPES_SAT_TZ")) h->sat_tz = std::max(1, atoi(e));
-  }
   // device arrays
   const double* Kin[3] = {Kx, d.dim == 3 ? Ky : nullptr, d.dim == 3 ? Kz : Ky};
   for (int c = 0; c < 3; ++c) {
@@ -1711,7 +1658,6 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     }
     CK(cudaFuncSetAttribute(k1q_apply_a<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
     CK(cudaFuncSetAttribute(k1q_apply_a<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
-    h->sat_mode = 0;  // the DG-Q1 kernel always carries f(S)
     h->lazy_u = !getenv("IMPES_NO_LAZY_U");
   }
   double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
@@ -2110,7 +2056,7 @@ API int impes_time_kernel(impes_handle h, int kernel, int reps, int flush_l2, do
   CK(cudaEventCreate(&guard.b));
   cudaEvent_t e0 = guard.a, e1 = guard.b;
   h->profiling = false;
-  if (kernel == IMPES_KERNEL_SAT_SUBSTEP && h->sat_mode == 0)  // f(S) is carried between sub-steps
+  if (kernel == IMPES_KERNEL_SAT_SUBSTEP)  // f(S) is carried between sub-steps
     RET_IF(launch_frac(h, h->S[h->scur], h->F[h->scur]));
   if (kernel == IMPES_KERNEL_SAT_SUBSTEP && h->os == 1) RET_IF(launch_sat_pre(h));
   for (int r = -2; r < reps; ++r) {  // 2 untimed warm-ups
@@ -2181,6 +2127,35 @@ API int impes_event_elapsed_ms(impes_handle h, int a, int b, double* ms) {
 }
 
 API int64_t impes_launch_count(impes_handle h) { return h ? h->launches : 0; }
+
+API int impes_describe(impes_handle h, char* buf, int buflen) {
+  if (!h) return 0;
+  char b[512];
+  std::string s;
+  snprintf(b, sizeof b, "spaces RT%d/L2_%d/DG_%d, %d-D %dx%dx%d, slab %d of %d (planes %d..%d)", h->ord, h->ord, h->os, h->d.dim,
+           h->L.NX, h->L.NY, h->L.NZ, h->L.rank, h->L.nranks, h->L.zlo, h->L.zhi);
+  s = b;
+  if (h->d.schur_prec == IMPES_SCHUR_MG) {
+    snprintf(b, sizeof b, "; Schur: multigrid V(%d,%d), %d cell level(s)%s, replicated from level %d", h->mg_nu, h->mg_nu,
+             (int)h->mg.size(), h->ord == 1 ? " + L2-Q1 level" : "", h->mg_g > 100 ? -1 : h->mg_g);
+    s += b;
+  } else if (h->d.schur_prec == IMPES_SCHUR_SGS_LEX) {
+    const char* v = h->ord == 1 ? (h->sgs_mode == 2 ? "k1_sgs_wavefront<cooperative grid>" : h->sgs_mode == 1 ? "k1_sgs_wavefront<cluster>" : "k1_sgs_wavefront<one CTA>")
+                    : h->sgs_skew ? (h->sgs_tma ? "k_sgs_tma (one-CTA TMA ring)" : h->sgs_mode == 1 ? "k_sgs_skew<cluster>" : "k_sgs_skew<one CTA>")
+                    : (h->sgs_mode == 2 ? "k_sgs_wavefront<cooperative grid>" : h->sgs_mode == 1 ? "k_sgs_wavefront<cluster>" : "k_sgs_wavefront<one CTA>");
+    snprintf(b, sizeof b, "; Schur: lexicographic symmetric Gauss-Seidel, %s, %d CTA(s) x %d threads", v, h->grid_sgs, h->sgs_threads);
+    s += b;
+  } else {
+    s += "; Schur: Jacobi";
+  }
+  s += h->os == 1 ? "; K1 k1q_apply_a/_b; K6 k1q_sat" : (h->ord == 1 ? "; K1 k1_darcy_apply; K6 k_sat_stream" : "; K1 k_darcy_apply; K6 k_sat_stream");
+  s += h->use_graph ? "; MINRES iterations in CUDA graphs" : "; no CUDA graphs";
+  if (buf && buflen > 0) {
+    strncpy(buf, s.c_str(), (size_t)buflen - 1);
+    buf[buflen - 1] = 0;
+  }
+  return (int)s.size();
+}
 
 API int impes_profile_enable(impes_handle h, int on) {
   if (!h) return IMPES_ERR_BAD_ARG;

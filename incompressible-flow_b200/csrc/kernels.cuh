@@ -984,20 +984,7 @@ __global__ void __launch_bounds__(1024) k_sgs_tma(Lay L, SgsPack P, const double
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// K3 (warp-dataflow path, 2-D meshes, one CTA): no block barrier at all.  Pencil p = row k runs along x;
-// cell (i, p) is computed at stage d = i + p by lane p%32 of warp p/32.  It needs its own previous value
-// (register), the previous-stage value of pencil p-1 (forward) / p+1 (backward): a __shfl from the neighbouring
-// lane, or -- for the first / last lane of a warp -- a value the neighbouring warp left in a small shared ring,
-// guarded by that warp's progress counter.  Each warp streams through its own stage range at its own pace,
-// one stage behind its predecessor; operands (coalesced 256 B rows of the skewed block layout) are prefetched
-// PD stages ahead into a register ring.  Per-stage critical path: shuffle + 8 dependent fp64 ops.
-// Same per-cell arithmetic as every other variant (bit-identical result).
-// ---------------------------------------------------------------------------------------
-constexpr int FLOW_R = 32;   // depth of the cross-warp exchange rings (stages)
-constexpr int FLOW_PD = 6;   // operand prefetch distance (stages)
-constexpr int FLOW_NOP = 8;  // operand slots per stage and lane: R, D, rD, nx, nz, fx, fz, hz
-
+// small PTX helpers shared by the staged kernels
 __device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ void st_volatile_s32(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) {
@@ -1007,178 +994,6 @@ __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Dynamic shared memory: per-warp operand ring  opnd[warp][FLOW_PD][FLOW_NOP][32]  (each lane only ever reads
-// what it copied itself, so no cross-lane synchronisation is needed for it).
-__global__ void __launch_bounds__(512) k_sgs_flow2d(Lay L, SgsPack P, const double* __restrict__ T, double* y,
-                                                    int do_fwd, int do_bwd, const MinresState* st) {
-  if (st && st->done) return;
-  extern __shared__ __align__(16) double opnd_all[];
-  __shared__ double xr[2][17][FLOW_R];  // [dir][receiving warp][stage % R]
-  __shared__ int prog[2][18];           // [dir][warp + 1]: stages completed (index 0 / nw+1: sentinels)
-  const int NP = L.nzl, NX = L.NX, SS = P.SS, NPs = P.NPs;
-  const int nstage = NX + NP - 1;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (NP + 31) >> 5;
-  const int p = threadIdx.x;
-  const bool pv = p < NP;
-  const int k = p + L.zlo;
-  const bool ghost_lo = pv && p == 0 && k > 0;                  // multi-rank: row below lives on another GPU
-  const bool ghost_hi = pv && p + 1 == NP && k + 1 < L.NZ;      // multi-rank: row above lives on another GPU
-  double* yp = y + L.off_p;
-  double* opnd = opnd_all + (size_t)w * FLOW_PD * FLOW_NOP * 32 + lane;   // [u][op] at opnd[(u*NOP+op)*32]
-  // progress counters start at "everything outside my stage range is done": forward counts completed stages
-  // upwards from 0, backward counts them downwards from nstage-1
-  if (threadIdx.x < 18) {
-    const int t = threadIdx.x, wq = t - 1;
-    const bool sentinel = t == 0 || t >= nw + 1;
-    prog[0][t] = sentinel ? (1 << 30) : 32 * wq;
-    prog[1][t] = sentinel ? (1 << 30) : nstage - 1 - (min(32 * wq + 31, NP - 1) + NX - 1);
-  }
-  __syncthreads();
-  if (w >= nw) return;
-  const int d_lo = 32 * w, d_hi = min(32 * w + 31, NP - 1) + NX - 1;  // stage range in which this warp has work
-  const int pc = pv ? p : NP - 1;                                       // clamped pencil for address safety
-
-  if (do_fwd) {
-    const double* base = P.Rs + pc;
-    auto issue = [&](int u, int d) {  // operands of stage d -> ring position u (clamped: inactive lanes load junk)
-      const int dc = min(max(d, 0), nstage - 1);
-      const double* q = base + (size_t)dc * SS;
-      double* o = opnd + (size_t)u * FLOW_NOP * 32;
-      cp_async8(o + 0 * 32, q);
-      cp_async8(o + 1 * 32, q + NPs);
-      cp_async8(o + 2 * 32, q + 2 * NPs);
-      cp_async8(o + 3 * 32, q + 3 * NPs);
-      cp_async8(o + 4 * 32, q + 4 * NPs);
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int u = 0; u < FLOW_PD; ++u) issue(u, d_lo + u);
-    double yown = 0.0;  // value of this pencil at the previous stage
-    double* gout = P.Yf + p + (size_t)d_lo * SS;
-    for (int d0 = d_lo; d0 <= d_hi; d0 += FLOW_PD) {
-#pragma unroll
-      for (int u = 0; u < FLOW_PD; ++u) {
-        const int d = d0 + u;
-        if (d <= d_hi) {
-          const int i = d - p;
-          const bool act = pv && (unsigned)i < (unsigned)NX;
-          cp_async_wait<FLOW_PD - 1>();
-          const double* o = opnd + (size_t)u * FLOW_NOP * 32;
-          const double oR = o[0], oD = o[32], orD = o[64], onx = o[96], onz = o[128];
-          // wait until the warp below has finished stage d-1 (and the warp above has consumed the ring slot
-          // this stage overwrites)
-          if (w > 0 || w + 1 < nw) {
-            const int need_lo = d, need_hi = d - FLOW_R + 2;
-            while (true) {
-              const int a0 = lane == 0 ? ld_volatile_s32(&prog[0][w]) - need_lo
-                                       : (lane == 1 ? ld_volatile_s32(&prog[0][w + 2]) - need_hi : 0);
-              if (__all_sync(0xffffffffu, a0 >= 0)) break;
-            }
-            asm volatile("" ::: "memory");
-          }
-          double left = __shfl_up_sync(0xffffffffu, yown, 1);
-          if (lane == 0) left = w > 0 ? *reinterpret_cast<const volatile double*>(&xr[0][w][(d - 1) & (FLOW_R - 1)]) : 0.0;
-          if (ghost_lo && act) left = __ldcg(yp + ix_c(L, i, 0, 0));
-          double sum = left * onz;
-          sum += yown * onx;
-          const double v = div_exact(oR - sum, oD, orD);
-          if (act) {
-            yown = v;
-            *gout = v;
-          }
-          // value, then flag, by the same thread: shared-memory stores of one thread are observed in order
-          if (lane == 31) {
-            if (w + 1 < nw) *reinterpret_cast<volatile double*>(&xr[0][w + 1][d & (FLOW_R - 1)]) = v;
-            st_volatile_s32(&prog[0][w + 1], d + 1);
-          }
-          gout += SS;
-          issue(u, d + FLOW_PD);
-        }
-      }
-    }
-    cp_async_wait<0>();
-    if (lane == 31) st_volatile_s32(&prog[0][w + 1], 1 << 29);  // done: never block a neighbour again
-  }
-  if (do_bwd) {
-    // the forward results of all warps must be complete (and visible) before they are read as F rows
-    __threadfence();
-    asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
-    // operands of stage d: R, D, rD, nx, nz, fx = Yf(d-1,p), fz = Yf(d-1,p-1), hz = -Tz_lo(d+1,p+1);
-    // hx (upper x face of stage d) is nx of stage d+1: kept from the previous iteration
-    const double* base = P.Rs + pc;
-    auto issue = [&](int u, int d) {
-      const int dc = min(max(d, 0), nstage - 1);
-      const double* q = base + (size_t)dc * SS;
-      const double* f = base + (size_t)max(dc - 1, 0) * SS + 5 * NPs;
-      const double* hq = base + (size_t)min(dc + 1, nstage - 1) * SS + 4 * NPs + (pc + 1 < NP ? 1 : 0);
-      double* o = opnd + (size_t)u * FLOW_NOP * 32;
-      cp_async8(o + 0 * 32, q);
-      cp_async8(o + 1 * 32, q + NPs);
-      cp_async8(o + 2 * 32, q + 2 * NPs);
-      cp_async8(o + 3 * 32, q + 3 * NPs);
-      cp_async8(o + 4 * 32, q + 4 * NPs);
-      cp_async8(o + 5 * 32, f);
-      cp_async8(o + 6 * 32, f - (pc > 0 ? 1 : 0));
-      cp_async8(o + 7 * 32, hq);
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int u = 0; u < FLOW_PD; ++u) issue(u, d_hi - u);
-    double yown = 0.0, nx_prev = 0.0;  // stage d+1: own new value, own -Tx_lo
-    double* gout = P.Yb + p + (size_t)d_hi * NPs;
-    for (int d0 = d_hi; d0 >= d_lo; d0 -= FLOW_PD) {
-#pragma unroll
-      for (int u = 0; u < FLOW_PD; ++u) {
-        const int d = d0 - u;
-        if (d >= d_lo) {
-          const int i = d - p;
-          const bool act = pv && (unsigned)i < (unsigned)NX;
-          cp_async_wait<FLOW_PD - 1>();
-          const double* o = opnd + (size_t)u * FLOW_NOP * 32;
-          const double oR = o[0], oD = o[32], orD = o[64], onx = o[96], onz = o[128];
-          const double ofx = i > 0 ? o[160] : 0.0, ofz = p > 0 ? o[192] : 0.0;
-          double hz = (pv && p + 1 < NP) ? o[224] : 0.0;  // -Tz_lo of cell (i, p+1)
-          if (w > 0 || w + 1 < nw) {
-            // the warp above must have finished stage d+1: it counts completed stages downwards from nstage
-            const int need_hi = nstage - 1 - d, need_lo = need_hi - FLOW_R + 2;
-            while (true) {
-              const int a0 = lane == 0 ? ld_volatile_s32(&prog[1][w + 2]) - need_hi
-                                       : (lane == 1 ? ld_volatile_s32(&prog[1][w]) - need_lo : 0);
-              if (__all_sync(0xffffffffu, a0 >= 0)) break;
-            }
-            asm volatile("" ::: "memory");
-          }
-          double up = __shfl_down_sync(0xffffffffu, yown, 1);       // new value of pencil p+1 at stage d+1
-          if (lane == 31) up = w + 1 < nw ? *reinterpret_cast<const volatile double*>(&xr[1][w][(d + 1) & (FLOW_R - 1)]) : 0.0;
-          if (ghost_hi && act) {
-            up = __ldcg(yp + ix_c(L, i, 0, NP + 1));
-            hz = -T[ix_uz(L, i, 0, NP + 1)];
-          }
-          const double fz = (ghost_lo && act) ? __ldcg(yp + ix_c(L, i, 0, 0)) : ofz;
-          double sum = fz * onz;
-          sum += ofx * onx;
-          sum += yown * ((i + 1 < NX) ? nx_prev : 0.0);
-          sum += up * hz;
-          const double v = div_exact(oR - sum, oD, orD);
-          if (act) {
-            yown = v;
-            *gout = v;
-          }
-          nx_prev = onx;
-          if (lane == 0) {
-            if (w > 0) *reinterpret_cast<volatile double*>(&xr[1][w - 1][d & (FLOW_R - 1)]) = v;
-            st_volatile_s32(&prog[1][w + 1], nstage - d);
-          }
-          gout -= NPs;
-          issue(u, d - FLOW_PD);
-        }
-      }
-    }
-    cp_async_wait<0>();
-    if (lane == 0) st_volatile_s32(&prog[1][w + 1], 1 << 29);
-  }
-}
 
 // ---------------------------------------------------------------------------------------
 // K6: one forward-Euler sub-step  S <- S + dt M_phi^-1 (Kt f(S) + b), fused
@@ -1216,146 +1031,10 @@ __device__ __forceinline__ double sat_source(const SatParam& sp, int i, int j, i
   return 0.;
 }
 
-template <bool RATE>
-__global__ void __launch_bounds__(BLK) k_sat_substep(Lay L, Phys ph, SatParam sp, const double* __restrict__ u,
-                                                     const double* __restrict__ phi, const double* __restrict__ Sin,
-                                                     double* __restrict__ Sout) {
-  const CellIdx ci = owned_cell(L);
-  if (!ci.ok) return;
-  const int i = ci.i, j = ci.j, kl = ci.kl, k = ci.k, kk = kl + 1;
-  const long c = ix_c(L, i, j, kk);
-  const bool xl = i > 0, xh = i + 1 < L.NX, yl = L.has_y && j > 0, yh = L.has_y && j + 1 < L.NY, zl = k > 0,
-             zh = k + 1 < L.NZ;
-  // face fluxes in +d direction (RT0 dof = total flux through the face)
-  const double Fxl = xl ? u[ix_ux(L, i, j, kl)] : 0.0, Fxh = xh ? u[ix_ux(L, i + 1, j, kl)] : 0.0;
-  const double Fyl = yl ? u[ix_uy(L, i, j, kl)] : 0.0, Fyh = yh ? u[ix_uy(L, i, j + 1, kl)] : 0.0;
-  const double Fzl = zl ? u[ix_uz(L, i, j, kk)] : 0.0, Fzh = zh ? u[ix_uz(L, i, j, kk + 1)] : 0.0;
-#define FPOS(F) ((F) > 0.0 ? (F) : 0.0)
-#define FNEG(F) ((F) < 0.0 ? (F) : 0.0)
-#define GS(idx) (sp.two_phase ? frac_flow_of(ph, Sin[idx]) : Sin[idx])
-  double z = 0.0;
-  if (zl) z += FPOS(Fzl) * GS(c - L.plane);
-  if (yl) z += FPOS(Fyl) * GS(c - L.NX);
-  if (xl) z += FPOS(Fxl) * GS(c - 1);
-  {
-    double dg = 0.0;  // diagonal of Kt, accumulated in assembly (face-loop) order
-    if (xl) dg += FNEG(Fxl);
-    if (xh) dg += -FPOS(Fxh);
-    if (yl) dg += FNEG(Fyl);
-    if (yh) dg += -FPOS(Fyh);
-    if (zl) dg += FNEG(Fzl);
-    if (zh) dg += -FPOS(Fzh);
-    z += dg * GS(c);
-  }
-  if (xh) z += (-FNEG(Fxh)) * GS(c + 1);
-  if (yh) z += (-FNEG(Fyh)) * GS(c + L.NX);
-  if (zh) z += (-FNEG(Fzh)) * GS(c + L.plane);
-#undef FPOS
-#undef FNEG
-#undef GS
-  z += sat_source(sp, i, j, k) * sp.vol;  // z += b
-  double yv = z / (phi[c] * sp.vol);       // M_phi^-1 (diagonal)
-  if (RATE) {
-    Sout[c] = yv;
-  } else {
-    yv *= sp.dt;
-    Sout[c] = Sin[c] + yv;
-  }
-}
-
-// K6, tiled: same arithmetic per cell as k_sat_substep (bit-identical result), restructured for instruction
-// count: tiles overlap by one cell in x (and y), so EVERY thread evaluates f(S) exactly once per plane for its
-// own cell (no divergent halo work) and only the tile interior (TX-2) x (TY-2) updates; a block marches TZ
-// planes along z keeping f of its column for planes k-1, k, k+1 in registers; the x / y neighbours come from a
-// double-buffered shared tile (one barrier per plane).  f-evaluations per updated cell: ~1.6 instead of 7,
-// with one IEEE division each (the constant denominators use div_exact).  All addressing is incremental.
-template <int TX, int TY, bool RATE>
-__global__ void __launch_bounds__(TX* TY) k_sat_tile(Lay L, Phys ph, SatParam sp, int TZ, const double* __restrict__ u,
-                                                     const double* __restrict__ phi, const double* __restrict__ Sin,
-                                                     double* __restrict__ Sout) {
-  constexpr int OX = TX - 2, OY = TY > 1 ? TY - 2 : 1;
-  __shared__ double fs[2][TY][TX];
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int i = (int)blockIdx.x * OX + tx - 1;
-  const int j = TY > 1 ? (int)blockIdx.y * OY + ty - 1 : 0;
-  const int kl0 = blockIdx.z * TZ, kl1 = min(kl0 + TZ, L.nzl);
-  const bool in = i >= 0 && i < L.NX && j >= 0 && j < L.NY;                                  // cell exists
-  const bool upd = in && tx >= 1 && tx <= OX && (TY == 1 || (ty >= 1 && ty <= OY));          // tile interior
-  const bool xl = i > 0, xh = i + 1 < L.NX, yl = L.has_y && j > 0, yh = L.has_y && j + 1 < L.NY;
-#define GS(v) (sp.two_phase ? frac_flow_of(ph, (v)) : (v))
-  const long plane = L.plane;
-  const long c0 = ix_c(L, in ? i : 0, in ? j : 0, kl0 + 1);
-  const double* Sp = Sin + c0;
-  double f_lo = (in && kl0 + L.zlo > 0) ? GS(Sp[-plane]) : 0.0;
-  double s_c = in ? Sp[0] : 0.0;
-  double f_c = in ? GS(s_c) : 0.0;
-  // running pointers of this column (advance one plane per iteration)
-  const long sxp = (long)(L.NX + 1) * L.NY, syp = (long)L.NX * (L.NY + 1);
-  const double* uxp = u + ix_ux(L, in ? i : 0, in ? j : 0, kl0);
-  const double* uyp = u + (L.has_y ? ix_uy(L, in ? i : 0, in ? j : 0, kl0) : 0);
-  const double* uzp = u + ix_uz(L, in ? i : 0, in ? j : 0, kl0 + 1);
-  const double* php = phi + c0;
-  double* Op = Sout + c0;
-  // injection-box membership of the column (SaturationSourceCoefficient [REF src/param.hpp:382-406]);
-  // the plane-dependent part of the test is done per plane
-  const double px = (i + 0.5) * sp.hx, py = (j + 0.5) * sp.hy;
-  const bool col_in = sp.well_2d ? (fabs(px - sp.inj_c0) <= sp.inj_r)
-                                 : (fabs(px - sp.inj_c0) <= sp.inj_r && py >= sp.inj_c1 && py <= sp.inj_c1 + sp.inj_h);
-  const double zc = sp.well_2d ? sp.inj_c1 : sp.inj_c2;
-  int b = 0;
-  for (int kl = kl0; kl < kl1; ++kl) {
-    const int k = kl + L.zlo;
-    const bool zl = k > 0, zh = k + 1 < L.NZ;
-    const double s_hi = (in && zh) ? Sp[plane] : 0.0;
-    const double f_hi = (in && zh) ? GS(s_hi) : 0.0;
-    fs[b][ty][tx] = f_c;
-    __syncthreads();
-    if (upd) {
-      const double Fxl = xl ? uxp[0] : 0.0, Fxh = xh ? uxp[1] : 0.0;
-      const double Fyl = yl ? uyp[0] : 0.0, Fyh = yh ? uyp[L.NX] : 0.0;
-      const double Fzl = zl ? uzp[0] : 0.0, Fzh = zh ? uzp[plane] : 0.0;
-#define FPOS(F) ((F) > 0.0 ? (F) : 0.0)
-#define FNEG(F) ((F) < 0.0 ? (F) : 0.0)
-      double z = 0.0;
-      if (zl) z += FPOS(Fzl) * f_lo;
-      if (yl) z += FPOS(Fyl) * fs[b][TY > 1 ? ty - 1 : 0][tx];
-      if (xl) z += FPOS(Fxl) * fs[b][ty][tx - 1];
-      {
-        double dg = 0.0;
-        if (xl) dg += FNEG(Fxl);
-        if (xh) dg += -FPOS(Fxh);
-        if (yl) dg += FNEG(Fyl);
-        if (yh) dg += -FPOS(Fyh);
-        if (zl) dg += FNEG(Fzl);
-        if (zh) dg += -FPOS(Fzh);
-        z += dg * f_c;
-      }
-      if (xh) z += (-FNEG(Fxh)) * fs[b][ty][tx + 1];
-      if (yh) z += (-FNEG(Fyh)) * fs[b][TY > 1 ? ty + 1 : 0][tx];
-      if (zh) z += (-FNEG(Fzh)) * f_hi;
-#undef FPOS
-#undef FNEG
-      const double src = (col_in && fabs((k + 0.5) * sp.hz - zc) <= sp.inj_r) ? sp.src : 0.;
-      z += src * sp.vol;
-      double yv = z / (php[0] * sp.vol);
-      if (RATE) {
-        Op[0] = yv;
-      } else {
-        yv *= sp.dt;
-        Op[0] = s_c + yv;
-      }
-    }
-    b ^= 1;
-    f_lo = f_c; f_c = f_hi; s_c = s_hi;
-    Sp += plane; php += plane; Op += plane; uxp += sxp; uyp += syp; uzp += plane;
-  }
-#undef GS
-}
-
 // K6, streaming form (default): f(S) is carried as a second resident array.  A sub-step reads f through the
 // 7-point stencil (neighbours hit L1/L2), its own S, the face fluxes and phi, and writes S_new together with
 // f(S_new): exactly one fractional-flow evaluation per cell and step, no shared memory, no barrier.
-// Same per-cell arithmetic as k_sat_substep (bit-identical).  Actual traffic 64 B/cell-step in 3-D (reads fs,
+// Actual traffic 64 B/cell-step in 3-D (reads fs,
 // S, 3 fluxes, phi; writes S, fs) against 48 B algorithmic.
 __global__ void __launch_bounds__(BLK) k_frac_flow(Lay L, Phys ph, int two_phase, const double* __restrict__ S,
                                                    double* __restrict__ F) {

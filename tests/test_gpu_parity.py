@@ -252,3 +252,17 @@ def test_graph_and_direct_paths_agree(pkg, orc, native_lib, monkeypatch):
     xd, std = s2.pressure_solve(S)
     s2.close()
     assert stg.iterations == std.iterations and np.array_equal(xg, xd)
+
+
+@pytest.mark.gpu
+def test_describe_names_the_selected_variants(pkg):
+    """impes_describe: which sweep kernel / multigrid set-up a handle chose for its mesh."""
+    from incompressible_flow_b200 import abi, workloads
+    d, Kx, Ky, Kz, phi = workloads.build(dim=2, nx=24, ny=20, K="lognormal")
+    with pkg.Solver(d, Kx, Ky, Kz, phi) as s:
+        t = s.describe()
+        assert "RT0/L2_0/DG_0" in t and "Gauss-Seidel" in t and "k_sgs" in t
+    d, Kx, Ky, Kz, phi = workloads.build(dim=3, nx=8, ny=8, nz=8, K="lognormal", order=1, order_s=1, schur_prec=abi.SCHUR_MG)
+    with pkg.Solver(d, Kx, Ky, Kz, phi) as s:
+        t = s.describe()
+        assert "RT1/L2_1/DG_1" in t and "multigrid V(2,2)" in t and "L2-Q1 level" in t and "k1q_sat" in t
