@@ -120,7 +120,14 @@ struct impes_ctx {
   std::vector<double*> mg_bufs;
   int mg_g = 1 << 30;            // first replicated level (multi-GPU): levels < mg_g are slab-distributed
   std::vector<int> mg_goff, mg_gcnt;  // plane offset / count of every rank's part of level mg_g
-  double mg_omega = 0.8, mg_cfac = 2.0;
+  double mg_omega = 0.8, mg_cfac = 2.0;  // damping of the coarsest level's sweeps; coarse-correction factor between cell levels
+  // Damping per smoothing sweep of a side: a 2-step (Chebyshev-like) Richardson iteration on D^-1 S with roots 1/1.4 and
+  // 1/0.55; pre-smoothing runs the sequence forwards, post-smoothing backwards (the V-cycle stays symmetric).  Against
+  // 0.8 throughout: 43 -> 35 MINRES iterations on the C5 family.  mg_cfacq: over-correction of the cell-wise constant
+  // prolongation onto the L2-Q1 level.  (The CPU checker restates the same constants.)
+  double mg_om[2] = {1.4, 0.55}, mg_cfacq = 2.5;
+  double om_pre(int s) const { return mg_om[s & 1]; }
+  double om_post(int s, int sweeps) const { return mg_om[(sweeps - 1 - s) & 1]; }
   int mg_nu = 2, mg_coarse_sweeps = 16;
   long long graph_launches = 0;
   long long graph_prof_n[KC_N] = {0};
@@ -775,15 +782,16 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
       double* in = (s & 1) ? qa : qb;
       double* out = (s & 1) ? qb : qa;
       const int first = from_zero && s == 0;
+      const double om = from_zero ? h->om_pre(s) : h->om_post(s, sweeps);
       if (!first && multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
       Scope sc(h, first ? KI_MGQ_FIRST : KI_MGQ_JACOBI, 1);
       if (first) {  // owned L2 dofs = one contiguous range of the p-part (16-byte aligned: npl is even, parts are padded)
         const long n2 = (long)L.ncl * h->L1.npl / 2;
         const size_t o2 = qpe / 2;
         k1_mg_first<<<h->num_sms * 8, BLK, 0, h->stream>>>(n2, reinterpret_cast<const double2*>(qD) + o2, reinterpret_cast<const double2*>(qr) + o2,
-                                                           reinterpret_cast<double2*>(out) + o2, h->mg_omega, st);
-      } else if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
-      else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
+                                                           reinterpret_cast<double2*>(out) + o2, om, st);
+      } else if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, om, 0, st, (unsigned)gq);
+      else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, om, 0, st, (unsigned)gq);
     }
     return 0;
   };
@@ -802,7 +810,8 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
       const bool first = from_zero && s == 0;
       if (!first && dist(l)) RET_IF(mg_halo(h, in, (size_t)v.nx * v.ny, v.nz));
       Scope sc(h, KI_MG_CELL, 1);
-      k_mg_jacobi<<<grid_of(v), MG_B, 0, h->stream>>>(v, v.r, in, out, h->mg_omega, first, st);
+      const double om = sweeps > 8 ? h->mg_omega : (from_zero ? h->om_pre(s) : h->om_post(s, sweeps));  // > 8: the coarsest level
+      k_mg_jacobi<<<grid_of(v), MG_B, 0, h->stream>>>(v, v.r, in, out, om, first, st);
     }
     return 0;
   };
@@ -844,20 +853,21 @@ int mg_vcycle(impes_ctx* h, const double* r, double* y, const MinresState* st, b
     if (multi) RET_IF(mg_halo(h, mg[0].yb, (size_t)L.plane, L.nzl));
     {
       Scope sc(h, KI_MGQ_JACOBI, 1);
-      if (L.has_y) k1_mg_jacobi<true, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, (unsigned)gq, mg[0].yb, h->mg_cfac);
-      else k1_mg_jacobi<false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->mg_omega, 0, st, (unsigned)gq, mg[0].yb, h->mg_cfac);
+      if (L.has_y) k1_mg_jacobi<true, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->om_post(0, h->mg_nu), 0, st, (unsigned)gq, mg[0].yb, h->mg_cfacq);
+      else k1_mg_jacobi<false, true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, qb, qa, h->om_post(0, h->mg_nu), 0, st, (unsigned)gq, mg[0].yb, h->mg_cfacq);
     }
     for (int s = 1; s < h->mg_nu; ++s) {
       double* in = (s & 1) ? qa : qb;
       double* out = (s & 1) ? qb : qa;
       if (multi) RET_IF(mg_halo(h, in + qpe, qpe, L.nzl));
       Scope sc(h, KI_MGQ_JACOBI, 1);
+      const double om = h->om_post(s, h->mg_nu);
       if (dot && s + 1 == h->mg_nu) {  // last sweep: finishes beta^2 = <v0, P v0> (see k1_mg_jacobi<.., DOT>)
-        if (L.has_y) k1_mg_jacobi<true, false, true><<<gdot, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
-        else k1_mg_jacobi<false, false, true><<<gdot, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+        if (L.has_y) k1_mg_jacobi<true, false, true><<<gdot, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, om, 0, st, (unsigned)gq, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
+        else k1_mg_jacobi<false, false, true><<<gdot, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, om, 0, st, (unsigned)gq, nullptr, 0.0, h->partial, h->partial_u, (unsigned)h->n_u_chunks, h->scal + 1, h->ticket);
       } else {
-        if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
-        else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, h->mg_omega, 0, st, (unsigned)gq);
+        if (L.has_y) k1_mg_jacobi<true><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, om, 0, st, (unsigned)gq);
+        else k1_mg_jacobi<false><<<gq, MGQ_T, 0, h->stream>>>(h->L1, h->rc, h->T, qD, qr, in, out, om, 0, st, (unsigned)gq);
       }
     }
   }
@@ -1668,7 +1678,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     h->launches++;
   }
   if (d.schur_prec == IMPES_SCHUR_MG) {
-    if (d.mg_smooth > 0) h->mg_nu = (d.mg_smooth + 1) / 2 * 2;  // even sweep counts (see mg_vcycle)
+    if (d.mg_smooth > 0) h->mg_nu = std::min(8, (d.mg_smooth + 1) / 2 * 2);  // even sweep counts (see mg_vcycle), at most 8
     const bool multi = L.nranks > 1;
     h->mg_g = multi ? mg_m : (1 << 30);
     if (h->ord == 1) {  // second iterate buffer of the Q1 level, p-part layout with ghost planes
