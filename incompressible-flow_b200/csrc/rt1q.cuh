@@ -214,6 +214,9 @@ __global__ void __launch_bounds__(BLK) k1_schur_diag(Lay1 L, Rt1Const C, const d
 #ifndef IMPES_K1Q_REGS
 #define IMPES_K1Q_REGS 128
 #endif
+#ifndef IMPES_K1Q_UNROLL
+#define IMPES_K1Q_UNROLL 1   // point pairs per trip of elem_apply's quadrature loop
+#endif
 constexpr int K1Q_TC = 32;  // cells per CTA: one warp per direction.  Register cap 128 (15 warps per SM): at 96 (18 warps)
                             // the compiler reused one register pair for the four c_q loads of a quadrature line and
                             // serialised LDS -> DMUL four times per iteration (ncu: short-scoreboard 1.7 per issue)
@@ -237,8 +240,15 @@ __device__ __forceinline__ void elem_apply(const QTab& tb, const double* rl, con
 #pragma unroll
   for (int n = 0; n < 12; ++n) yl[n] = 0.0;
   if constexpr (HY) {
+#if IMPES_K1Q_UNROLL > 1
+#pragma unroll 1
+    for (int pp = 0; pp < 16; pp += IMPES_K1Q_UNROLL)
+#pragma unroll
+    for (int p = pp; p < pp + IMPES_K1Q_UNROLL; ++p) {
+#else
 #pragma unroll 1
     for (int p = 0; p < 16; ++p) {
+#endif
       const int qe = p & 3, qf = p >> 2;
       const double* oo = c_OO3[qe][qf];
       const double o0 = oo[0], o1 = oo[1], o2 = oo[2], o3 = oo[3];
@@ -765,6 +775,9 @@ __device__ __forceinline__ double sat_source_at(const SatParam& sp, double px, d
 // unit, from the 64-byte-strided gathers of the neighbours' F and the stride-2 walks over the RT1 node grids).
 // Upwinding: DGTraceIntegrator's (a + b, b - a) with a = un/2, b = |un|/2 are exactly (un+, un-), so
 //   w (a + b) g1 - w (b - a) g2  ==  c * (c >= 0 ? g1 : g2),   c = w un     (same bits for finite g)
+#ifndef IMPES_K1QS_UNROLL3
+#define IMPES_K1QS_UNROLL3 1   // 1: face loop as 3 rolled rows of 3 unrolled points (-2 % in the step); 0: 9 rolled points; 2: fully unrolled (+6 %)
+#endif
 template <bool HY>
 struct SatQ {
   static constexpr int ND = HY ? 3 : 2;
@@ -922,6 +935,21 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
     // their latency hides behind the prologue instead of stalling the loop (ncu: long-scoreboard at the first use of
     // a register-prefetched row was a quarter of all warp-stall samples).
     cp_async_wait<0>();
+#if IMPES_K1QS_UNROLL3
+#if IMPES_K1QS_UNROLL3 == 2
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+    for (int qf = 0; qf < 3; ++qf) {   // rows of three points: the loop overhead (uniform address arithmetic) is paid per row
+#pragma unroll
+      for (int qe = 0; qe < 3; ++qe) {
+        const double* o = c_OOF3[qe][qf];
+        const double oo[NT] = {o[0], o[1], o[2], o[3]};
+        face_point(oo, s_fn[(qe + 3 * qf) * K1Q_TC], s_fn[(9 + qe + 3 * qf) * K1Q_TC]);
+      }
+    }
+#else
 #pragma unroll 1
     for (int p = 0; p < 9; ++p) {
       const int qf = p / 3, qe = p - 3 * qf;
@@ -929,6 +957,7 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
       const double oo[NT] = {o[0], o[1], o[2], o[3]};
       face_point(oo, s_fn[p * K1Q_TC], s_fn[(9 + p) * K1Q_TC]);
     }
+#endif
   } else {
 #pragma unroll
     for (int qf = 0; qf < NFF; ++qf)
@@ -970,6 +999,7 @@ __device__ __forceinline__ void q_sat_dir(const Lay1& L, const Cell1& q, const Q
 #ifndef IMPES_K1QS_REGS
 #define IMPES_K1QS_REGS 128
 #endif
+
 template <bool HY, bool RATE>
 __global__ void __launch_bounds__(K1Q_TC * (HY ? 3 : 2)) __maxnreg__(HY ? IMPES_K1QS_REGS : 80)
 k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, long ncv, const double* __restrict__ vh, const double* __restrict__ fn,
