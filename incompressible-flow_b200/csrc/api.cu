@@ -1538,6 +1538,18 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
             sp.bj0, sp.bj1);
       range(L.NZ, [&](int q) { return fabs((q + 0.5) * sp.hz - sp.inj_c2) <= sp.inj_r; }, sp.bk0, sp.bk1);
     }
+    // DG-Q1 nodes (1/2 -+ 1/(2 sqrt 3) inside the cell): cells with a node inside, per axis (k1q_sat skips the source
+    // evaluation everywhere else)
+    const double g1 = 0.5 / sqrt(3.0), sn[2] = {0.5 - g1, 0.5 + g1};
+    auto any = [&](auto pred) { return [=](int q) { return pred((q + sn[0])) || pred((q + sn[1])); }; };
+    range(L.NX, any([&](double t) { return fabs(t * sp.hx - sp.inj_c0) <= sp.inj_r; }), sp.ni0, sp.ni1);
+    if (d.dim == 2) {
+      sp.nj0 = 0; sp.nj1 = 0;
+      range(L.NZ, any([&](double t) { return fabs(t * sp.hz - sp.inj_c1) <= sp.inj_r; }), sp.nk0, sp.nk1);
+    } else {
+      range(L.NY, any([&](double t) { const double py = t * sp.hy; return py >= sp.inj_c1 && py <= sp.inj_c1 + sp.inj_h; }), sp.nj0, sp.nj1);
+      range(L.NZ, any([&](double t) { return fabs(t * sp.hz - sp.inj_c2) <= sp.inj_r; }), sp.nk0, sp.nk1);
+    }
   }
 
   h->grid_cells = L.nblk;

@@ -1011,6 +1011,9 @@ struct SatParam {
   // the same box as inclusive INTERNAL cell-index ranges (cell centres tested on the host with the formulas of
   // sat_source; membership is monotone along each axis); empty box: lo > hi
   int bi0, bi1, bj0, bj1, bk0, bk1;
+  // DG-Q1: inclusive cell-index ranges of the cells with at least one DG node inside the box (per-axis predicates at
+  // the node positions (i + sn) h, evaluated on the host with the kernel's expression); empty: lo > hi
+  int ni0, ni1, nj0, nj1, nk0, nk1;
 };
 __device__ __forceinline__ double sat_source_box(const SatParam& sp, int i, int j, int k) {
   return (i >= sp.bi0 && i <= sp.bi1 && j >= sp.bj0 && j <= sp.bj1 && k >= sp.bk0 && k <= sp.bk1) ? sp.src : 0.;

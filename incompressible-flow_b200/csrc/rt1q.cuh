@@ -1010,6 +1010,7 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, long ncv, const double* __restric
   constexpr int ND = SQ::ND, THREADS = SQ::THREADS, PS = Q::NSL + 1;
   __shared__ double s_r[ND * K1Q_TC * PS];         // per-direction parts of Kt F
   __shared__ double s_f[HY ? ND * 18 * K1Q_TC : 1];   // 3-D: face coefficients, [direction][lower 9 | upper 9][lane]
+  __shared__ int s_src[K1Q_TC];                       // cell may hold a DG node inside the injection box
   const int tid = threadIdx.x;
   const int ci = tid % K1Q_TC, dir = tid / K1Q_TC;
   const unsigned t0 = blockIdx.x * (unsigned)K1Q_TC;
@@ -1038,6 +1039,8 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, long ncv, const double* __restric
     q.c = q.i + L.NX * (q.j + L.NY * (q.kl + 1));
     q.pb = L.off_p + q.c * L.npl;
   }
+  if (dir == 0)
+    s_src[ci] = q.i >= sp.ni0 && q.i <= sp.ni1 && q.j >= sp.nj0 && q.j <= sp.nj1 && q.k >= sp.nk0 && q.k <= sp.nk1;
   double* rd = s_r + (dir * K1Q_TC + ci) * PS;
   double* sfn = s_f + (HY ? dir * 18 * K1Q_TC + ci : 0);
   if (dir == 0) q_sat_dir<HY, 0>(L, q, tb, ncv, Fin, vh, fn, sfn, rd);
@@ -1050,19 +1053,22 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, long ncv, const double* __restric
     const unsigned e = tid + it * THREADS;
     if (e >= nc * Q::NSL) break;
     const unsigned c = e / Q::NSL, m = e - c * Q::NSL;
-    const unsigned tt = t0 + c;
-    const unsigned rr = fastdiv(tt, L.fdx);
-    const int i = (int)(tt - rr * (unsigned)L.NX);
-    const int kl = (int)fastdiv(rr, L.fdy);
-    const int j = (int)(rr - (unsigned)kl * (unsigned)L.NY);
-    const int k = kl + L.zlo;
     const double ra = s_r[c * PS + m], rb = s_r[(K1Q_TC + c) * PS + m];
     const double r = HY ? (ra + rb) + s_r[(2 * K1Q_TC + c) * PS + m] : ra + rb;
-    const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
-    // run-time node index: selects instead of indexing the kernel parameter (which would be copied to local memory)
-    const double px = (i + (m0 ? tb.sn[1] : tb.sn[0])) * sp.hx, py = (j + (m1 ? tb.sn[1] : tb.sn[0])) * sp.hy,
-                 pz = (k + (m2 ? tb.sn[1] : tb.sn[0])) * sp.hz;
-    const double z = r + sat_source_at(sp, px, py, pz) * wm;
+    double z = r;
+    if (s_src[c]) {   // rare: only cells at the injection well evaluate the source at their nodes
+      const unsigned tt = t0 + c;
+      const unsigned rr = fastdiv(tt, L.fdx);
+      const int i = (int)(tt - rr * (unsigned)L.NX);
+      const int kl = (int)fastdiv(rr, L.fdy);
+      const int j = (int)(rr - (unsigned)kl * (unsigned)L.NY);
+      const int k = kl + L.zlo;
+      const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
+      // run-time node index: selects instead of indexing the kernel parameter (which would be copied to local memory)
+      const double px = (i + (m0 ? tb.sn[1] : tb.sn[0])) * sp.hx, py = (j + (m1 ? tb.sn[1] : tb.sn[0])) * sp.hy,
+                   pz = (k + (m2 ? tb.sn[1] : tb.sn[0])) * sp.hz;
+      z = r + sat_source_at(sp, px, py, pz) * wm;
+    }
     const double mphi = phi_r[it] * wm;
     double yv = div_rcp(z, mphi);   // same bits as `/` (kernels.cuh), without the call into the division subroutine
     double so;
