@@ -44,6 +44,7 @@
  *
  * Supported spaces (anything else: impes_create -> IMPES_ERR_UNSUPPORTED):
  *   order_v/order_p/order_s = 0/0/0   RT0 / P0 / P0
+ *                             0/0/1   RT0 / P0 / DG-Q1
  *                             1/1/0   RT1 / L2-Q1 / DG_0   (the reference's defaults [REF src/param.cpp:43])
  *                             1/1/1   RT1 / L2-Q1 / DG-Q1  (BASELINE config C5)
  */

@@ -60,10 +60,11 @@ struct impes_ctx {
   int grid_dofs1 = 0;    // blocks of 256 L2 dofs (ord == 1: K1, dot, Q1 multigrid level run one thread per dof)
   int vec_n = 0, vec_offp = 0;  // length and p-offset of a Darcy-sized device vector in the active layout
   double* flux0 = nullptr;      // ord == 1: face fluxes of x in the RT0 dvec layout (input of K6)
+  double* aq = nullptr;         // ord == 0, os == 1: RT0 element-block entries (k0q_coeff)
   double* vhq = nullptr;        // os == 1: per-step velocity records of the DG-Q1 stage kernel (k1q_sat_pre)
   double* fnq = nullptr;
   double* mg1_ya = nullptr;     // ord == 1: second iterate buffer of the Q1 multigrid level (p-part)
-  int os = 0, nsl = 1;          // saturation order (DG_os) and dofs per cell; os == 1 needs ord == 1 (rt1q.cuh)
+  int os = 0, nsl = 1;          // saturation order (DG_os) and dofs per cell (rt1q.cuh)
   QTab qt;
   double* rlam = nullptr;       // os == 1: w_q / lambda(S(x_q)) at the mass-rule points, ncv x NQP
   double* yup = nullptr;        // os == 1: upper-face-node element contributions of K1 pass A, ncv x NUP
@@ -478,6 +479,14 @@ MgLevel mg_view(const impes_ctx* h, const MgLevel& v);
 int update_coeff(impes_ctx* h) {
   const Lay& L = h->L;
   RET_IF(exchange_planes(h, h->S[h->scur], true, true, h->nsl));
+  if (h->os == 1 && h->ord == 0) {  // RT0 with S in DG-Q1: element-block entries by quadrature, then the RT0 face coefficients
+    Scope sc(h, KI_COEFF, 2);
+    const int g = (int)((L.ncv + BLK - 1) / BLK);
+    double* a = h->aq;
+    if (L.has_y) k0q_coeff<true><<<g, BLK, 0, h->stream>>>(L, h->ph, h->qt, h->S[h->scur], h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], a);
+    else k0q_coeff<false><<<g, BLK, 0, h->stream>>>(L, h->ph, h->qt, h->S[h->scur], h->K[0], h->K[1], h->K[2], h->geo[0], h->geo[1], h->geo[2], a);
+    k_face_coeff<true><<<h->grid_cells, BLK, 0, h->stream>>>(L, a, a + 3L * L.ncv, a + 6L * L.ncv, h->Md, h->T);
+  } else
   if (h->os == 1) {  // S in DG-Q1: 1/lambda at the mass-rule points, diag(M) by quadrature, Schur diagonal
     const bool slab = L.nranks > 1;
     Scope sc(h, KI_COEFF, slab ? 5 : 4);
@@ -506,7 +515,7 @@ int update_coeff(impes_ctx* h) {
       if (L.has_y) k1_node_coeff<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->m[0], h->m[1], h->m[2], h->Md, h->T);
       else k1_node_coeff<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L1, h->rc, h->m[0], h->m[1], h->m[2], h->Md, h->T);
     } else {
-      k_face_coeff<<<h->grid_cells, BLK, 0, h->stream>>>(L, h->m[0], h->m[1], h->m[2], h->Md, h->T);
+      k_face_coeff<false><<<h->grid_cells, BLK, 0, h->stream>>>(L, h->m[0], h->m[1], h->m[2], h->Md, h->T);
     }
   }
   if (h->sgs_skew) {
@@ -545,7 +554,7 @@ int update_coeff(impes_ctx* h) {
 
 // ---- K1 ----------------------------------------------------------------------------------------
 int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState* st) {
-  if (h->os == 1) {  // variable coefficient inside the cells: element products (A), then face-node completion (B)
+  if (h->os == 1 && h->ord == 1) {  // variable coefficient inside the cells: element products (A), then face-node completion (B)
     RET_IF(halo_darcy1(h, x));
     {
       Scope sc(h, KI_DARCY_Q1A, 1);
@@ -588,7 +597,11 @@ int darcy_apply(impes_ctx* h, double* x, double* y, bool dot, const MinresState*
   RET_IF(halo_darcy(h, x));
   {
     Scope sc(h, KI_DARCY_RT0, 1);
-    if (dot)
+    if (h->os == 1) {  // DG-Q1 coefficient: the same kernel with the element-block entries of k0q_coeff
+      const double *ax = h->aq, *ay = h->aq + 3L * h->L.ncv, *az = h->aq + 6L * h->L.ncv;
+      if (dot) k_darcy_apply<true, true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, ax, ay, az, x, y, h->partial, h->scal + 0, h->ticket, st);
+      else k_darcy_apply<false, true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, ax, ay, az, x, y, h->partial, h->scal + 0, h->ticket, st);
+    } else if (dot)
       k_darcy_apply<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->m[0], h->m[1], h->m[2], x, y, h->partial,
                                                                 h->scal + 0, h->ticket, st);
     else
@@ -1100,6 +1113,11 @@ int launch_frac(impes_ctx* h, const double* S, double* F) {
 // os == 1: velocity records of the stage kernel from the RT1 dofs in h->x (once per step: the velocity is frozen)
 int launch_sat_pre(impes_ctx* h) {
   Scope sc(h, KI_SAT_AUX, 1);
+  if (h->ord == 0) {  // records from the RT0 face fluxes
+    if (h->L.has_y) k0q_sat_pre<true><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->qt, h->x, (long)h->L.ncv, h->vhq, h->fnq);
+    else k0q_sat_pre<false><<<h->grid_cells, BLK, 0, h->stream>>>(h->L, h->qt, h->x, (long)h->L.ncv, h->vhq, h->fnq);
+    return 0;
+  }
   const int g = (h->L.ncl + K1Q_TC - 1) / K1Q_TC;
   if (h->L.has_y) k1q_sat_pre<true><<<g, SatQ<true>::THREADS, 0, h->stream>>>(h->L1, h->qt, h->x, (long)h->L.ncv, h->vhq, h->fnq);
   else k1q_sat_pre<false><<<g, SatQ<false>::THREADS, 0, h->stream>>>(h->L1, h->qt, h->x, (long)h->L.ncv, h->vhq, h->fnq);
@@ -1293,7 +1311,7 @@ API void impes_destroy(impes_handle h) {
   if (h->comm) h->nccl.CommDestroy(h->comm);
   double* ptrs[] = {h->K[0], h->K[1], h->K[2], h->phi, h->S[0], h->S[1], h->F[0], h->F[1], h->stage[0], h->stage[1], h->stage[2],
                     h->stage[3], h->m[0], h->m[1], h->m[2], h->Md, h->T, h->rhs, h->x, h->v0, h->v1, h->w0, h->w1,
-                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup, h->accA, h->partial_u, h->vhq, h->fnq};
+                    h->q, h->u1, h->tmpv, h->partial, h->scal, h->flushbuf, h->pack_blk, h->pack.Yb, h->flux0, h->mg1_ya, h->rlam, h->yup, h->accA, h->partial_u, h->vhq, h->fnq, h->aq};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   for (double* b : h->mg_bufs)
@@ -1317,9 +1335,10 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   if (d.order_v == 0 && d.order_p == 0 && d.order_s == 0) h->ord = 0;
   else if (d.order_v == 1 && d.order_p == 1 && d.order_s == 0) h->ord = 1;
   else if (d.order_v == 1 && d.order_p == 1 && d.order_s == 1) { h->ord = 1; h->os = 1; }
+  else if (d.order_v == 0 && d.order_p == 0 && d.order_s == 1) { h->ord = 0; h->os = 1; }
   else {
-    h->err = "GPU path implements -ov 0 -op 0 -os 0 (RT0/P0/P0), -ov 1 -op 1 -os 0 (RT1/Q1/P0, the reference default) "
-             "and -ov 1 -op 1 -os 1 (RT1/Q1/DG-Q1)";
+    h->err = "GPU path implements -ov 0 -op 0 -os 0 (RT0/P0/P0), -ov 0 -op 0 -os 1 (RT0/P0/DG-Q1), -ov 1 -op 1 -os 0 "
+             "(RT1/Q1/P0, the reference default) and -ov 1 -op 1 -os 1 (RT1/Q1/DG-Q1)";
     return IMPES_ERR_UNSUPPORTED;
   }
   h->nsl = h->os == 1 ? (d.dim == 3 ? 8 : 4) : 1;
@@ -1448,6 +1467,14 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     h->rc.wflux = wt;
     h->grid_dofs1 = (int)(((long)L.ncl * Q.npl + BLK - 1) / BLK);
   }
+  if (h->os == 1 && h->ord == 0) {  // k1q_sat walks the cells through a Lay1: only its cell-index fields are used
+    Lay1& Q = h->L1;
+    memset(&Q, 0, sizeof Q);
+    Q.fdx = L.fdx; Q.fdy = L.fdy;
+    Q.NX = L.NX; Q.NY = L.NY; Q.NZ = L.NZ; Q.has_y = L.has_y; Q.oy = L.has_y ? 2 : 1; Q.npl = 1;
+    Q.zlo = L.zlo; Q.zhi = L.zhi; Q.nzl = L.nzl; Q.rank = L.rank; Q.nranks = L.nranks;
+    Q.plane = L.plane; Q.ncl = L.ncl; Q.nblk = L.nblk;
+  }
   if (h->os == 1) {  // quadrature and basis tables of rt1q.cuh
     QTab& t = h->qt;
     memset(&t, 0, sizeof t);
@@ -1464,6 +1491,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     };
     gauss(nq, gx, gwt);
     gauss(nf, fx, t.fw);
+    gauss(d.dim == 3 ? 3 : 2, t.x0, t.gw0);   // RT0 mass rule (-ov 0 -os 1)
     const double g1 = 0.5 / sqrt(3.0), on[2] = {0.5 - g1, 0.5 + g1}, cn[3] = {0.0, 0.5, 1.0};
     auto lagr = [](const double* nodes, int nn, int a, double x) {
       double v = 1.0;
@@ -1477,6 +1505,8 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     }
     for (int q = 0; q < nf; ++q)
       for (int a = 0; a < 2; ++a) t.OF[q][a] = lagr(on, 2, a, fx[q]);
+    for (int q = 0; q < (d.dim == 3 ? 3 : 2); ++q)
+      for (int a = 0; a < 2; ++a) t.O0[q][a] = lagr(on, 2, a, t.x0[q]);
     for (int a = 0; a < 2; ++a) {
       for (int i = 0; i < 3; ++i) t.LC[a][i] = lagr(cn, 3, i, on[a]);
       t.E0[a] = lagr(on, 2, a, 0.0);
@@ -1668,9 +1698,13 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
   RET_IF(dev_alloc(h, &h->F[0], (long)L.ncv * h->nsl));
   RET_IF(dev_alloc(h, &h->F[1], (long)L.ncv * h->nsl));
   if (h->os == 1) {
-    RET_IF(dev_alloc(h, &h->rlam, (long)L.ncv * h->nqp));
-    RET_IF(dev_alloc(h, &h->yup, (long)L.ncv * h->nup));
-    RET_IF(dev_alloc(h, &h->accA, (long)L.nblk * BLK));
+    if (h->ord == 1) {
+      RET_IF(dev_alloc(h, &h->rlam, (long)L.ncv * h->nqp));
+      RET_IF(dev_alloc(h, &h->yup, (long)L.ncv * h->nup));
+      RET_IF(dev_alloc(h, &h->accA, (long)L.nblk * BLK));
+    } else {
+      RET_IF(dev_alloc(h, &h->aq, 9L * L.ncv));   // RT0: entries of the 2x2 element blocks, [3 dir + {00,01,11}][ncv]
+    }
     if (L.has_y) {
       RET_IF(dev_alloc(h, &h->vhq, (long)L.ncv * SatQ<true>::ND * SatQ<true>::NVH));
       RET_IF(dev_alloc(h, &h->fnq, (long)L.ncv * SatQ<true>::ND * SatQ<true>::NFP));
@@ -1680,7 +1714,7 @@ static int create_impl(impes_ctx* h, const double* Kx, const double* Ky, const d
     }
     CK(cudaFuncSetAttribute(k1q_apply_a<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
     CK(cudaFuncSetAttribute(k1q_apply_a<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * K1QS<true>::SMEM_DOUBLES)));
-    h->lazy_u = !getenv("IMPES_NO_LAZY_U");
+    h->lazy_u = h->ord == 1 && !getenv("IMPES_NO_LAZY_U");   // K1 of the RT1 / DG-Q1 path applies the lazy scaling of u
   }
   double** vecs[] = {&h->Md, &h->T, &h->rhs, &h->x, &h->v0, &h->v1, &h->w0, &h->w1, &h->q, &h->u1, &h->tmpv};
   for (double** v : vecs) RET_IF(dev_alloc(h, v, h->vec_n));
@@ -2170,7 +2204,8 @@ API int impes_describe(impes_handle h, char* buf, int buflen) {
   } else {
     s += "; Schur: Jacobi";
   }
-  s += h->os == 1 ? "; K1 k1q_apply_a/_b; K6 k1q_sat" : (h->ord == 1 ? "; K1 k1_darcy_apply; K6 k_sat_stream" : "; K1 k_darcy_apply; K6 k_sat_stream");
+  s += h->os == 1 ? (h->ord == 1 ? "; K1 k1q_apply_a/_b; K6 k1q_sat" : "; K1 k_darcy_apply<VAR>; K6 k1q_sat (records from RT0 fluxes)")
+                  : (h->ord == 1 ? "; K1 k1_darcy_apply; K6 k_sat_stream" : "; K1 k_darcy_apply; K6 k_sat_stream");
   s += h->use_graph ? "; MINRES iterations in CUDA graphs" : "; no CUDA graphs";
   if (buf && buflen > 0) {
     strncpy(buf, s.c_str(), (size_t)buflen - 1);

@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(BLK) k_cell_coeff(Lay L, Phys ph, const double
 // diag(M) on owned faces (1 on boundary faces: eliminated rows [REF src/pressure_solver.cpp:56-60]),
 // T_f = 1/diag(M)_f on interior faces (0 on boundary faces), and the diagonal of
 // S = B diag(M)^-1 B^T  [REF src/pressure_solver.cpp:76-81] stored in the p-part of Md.
+// VAR (S in DG-Q1, k0q_coeff): mx / my / mz point at three arrays each, [a00 | a01 | a11] with stride ncv -- the entries of
+// the 2x2 element block of the direction; diag(M)_f = a11(lower cell) + a00(upper cell).
+template <bool VAR>
 __global__ void __launch_bounds__(BLK) k_face_coeff(Lay L, const double* __restrict__ mx, const double* __restrict__ my,
                                                     const double* __restrict__ mz, double* __restrict__ Md,
                                                     double* __restrict__ T) {
@@ -247,40 +250,41 @@ __global__ void __launch_bounds__(BLK) k_face_coeff(Lay L, const double* __restr
   if (!ci.ok) return;
   const int i = ci.i, j = ci.j, kl = ci.kl, k = ci.k, kk = kl + 1;
   const long c = ix_c(L, i, j, kk);
+  const long n2 = 2L * L.ncv;   // VAR: offset of a11
   double D = 0.0;
   {  // x
     const long f = ix_ux(L, i, j, kl);
     if (i > 0) {
-      const double md = mx[c - 1] * THIRD + mx[c] * THIRD;
+      const double md = VAR ? mx[n2 + c - 1] + mx[c] : mx[c - 1] * THIRD + mx[c] * THIRD;
       const double t = 1.0 / md;
       Md[f] = md; T[f] = t; D += t;
     } else { Md[f] = 1.0; T[f] = 0.0; }
     if (i < L.NX - 1) {
-      const double md = mx[c] * THIRD + mx[c + 1] * THIRD;
+      const double md = VAR ? mx[n2 + c] + mx[c + 1] : mx[c] * THIRD + mx[c + 1] * THIRD;
       D += 1.0 / md;
     } else { Md[f + 1] = 1.0; T[f + 1] = 0.0; }
   }
   if (L.has_y) {
     const long f = ix_uy(L, i, j, kl);
     if (j > 0) {
-      const double md = my[c - L.NX] * THIRD + my[c] * THIRD;
+      const double md = VAR ? my[n2 + c - L.NX] + my[c] : my[c - L.NX] * THIRD + my[c] * THIRD;
       const double t = 1.0 / md;
       Md[f] = md; T[f] = t; D += t;
     } else { Md[f] = 1.0; T[f] = 0.0; }
     if (j < L.NY - 1) {
-      const double md = my[c] * THIRD + my[c + L.NX] * THIRD;
+      const double md = VAR ? my[n2 + c] + my[c + L.NX] : my[c] * THIRD + my[c + L.NX] * THIRD;
       D += 1.0 / md;
     } else { Md[f + L.NX] = 1.0; T[f + L.NX] = 0.0; }
   }
   {  // z
     const long f = ix_uz(L, i, j, kk);
     if (k > 0) {
-      const double md = mz[c - L.plane] * THIRD + mz[c] * THIRD;
+      const double md = VAR ? mz[n2 + c - L.plane] + mz[c] : mz[c - L.plane] * THIRD + mz[c] * THIRD;
       const double t = 1.0 / md;
       Md[f] = md; T[f] = t; D += t;
     } else { Md[f] = 1.0; T[f] = 0.0; }
     if (k < L.NZ - 1) {
-      const double md = mz[c] * THIRD + mz[c + L.plane] * THIRD;
+      const double md = VAR ? mz[n2 + c] + mz[c + L.plane] : mz[c] * THIRD + mz[c + L.plane] * THIRD;
       const double t = 1.0 / md;
       D += t;
       if (k == L.zhi - 1) T[f + L.plane] = t;  // ghost-above face plane: needed by the Schur sweeps
@@ -299,14 +303,16 @@ __global__ void __launch_bounds__(BLK) k_face_coeff(Lay L, const double* __restr
 // One direction of the RT0 apply for one cell, branch-free: the loads were issued by the caller (clamped where the
 // neighbour does not exist), skipped CSR entries become `+ 0.0` (bit-identical partial sums).
 //   lo / lo2: the lower face is interior / the lower cell's lower face is interior; hi: the upper face is interior
+//   cm / cd / cu: the row's coefficients of the lower face of the lower cell, the face itself, the upper face
+//   (constant coefficient in the cell: (mL/6), (mL/3 + mR/3), (mR/6); DG-Q1 coefficient: a01(L), a11(L) + a00(R), a01(R))
 template <bool DOT>
-__device__ __forceinline__ void rt0_dir(bool lo, bool lo2, bool hi, double mL, double mR, double xm, double xf,
+__device__ __forceinline__ void rt0_dir(bool lo, bool lo2, bool hi, double cm, double cd, double cu, double xm, double xf,
                                         double xf1, double pc, double pm, double& yf, double& yb, double& yp,
                                         double& acc) {
   double s = 0.0;
-  s += lo2 ? (mL * SIXTH) * xm : 0.0;
-  s += (mL * THIRD + mR * THIRD) * xf;
-  s += hi ? (mR * SIXTH) * xf1 : 0.0;
+  s += lo2 ? cm * xm : 0.0;
+  s += cd * xf;
+  s += hi ? cu * xf1 : 0.0;
   yf = lo ? s + (pc - pm) : xf;  // eliminated boundary row: identity
   if (DOT) acc += xf * yf;
   yp += lo ? xf : 0.0;
@@ -318,7 +324,8 @@ __device__ __forceinline__ void rt0_dir(bool lo, bool lo2, bool hi, double mL, d
   }
 }
 
-template <bool DOT>
+// VAR: see k_face_coeff
+template <bool DOT, bool VAR = false>
 __global__ void __launch_bounds__(BLK) k_darcy_apply(Lay L, const double* __restrict__ mx,
                                                      const double* __restrict__ my, const double* __restrict__ mz,
                                                      const double* __restrict__ x, double* __restrict__ y,
@@ -342,21 +349,38 @@ __global__ void __launch_bounds__(BLK) k_darcy_apply(Lay L, const double* __rest
     const double xxf = x[fx], xxf1 = x[fx + 1], xxm = x[xl ? fx - 1 : fx];
     const double xyf = x[fy], xyf1 = x[L.has_y ? fy + L.NX : fy], xym = x[(L.has_y && yl) ? fy - L.NX : fy];
     const double xzf = x[fz], xzf1 = x[fz + L.plane], xzm = x[zl ? fz - L.plane : fz];
-    const double mxR = mx[c], mxL = mx[xl ? c - 1 : c];
-    const double mzR = mz[c], mzL = mz[zl ? c - L.plane : c];
-    double myR = 0.0, myL = 0.0;
-    if (L.has_y) { myR = my[c]; myL = my[yl ? c - L.NX : c]; }
+    // row coefficients (lower neighbour's face, the face, upper face) per direction
+    double cxm, cxd, cxu, czm, czd, czu, cym = 0.0, cyd = 0.0, cyu = 0.0;
+    if constexpr (VAR) {
+      const long n1 = L.ncv, n2 = 2L * L.ncv;
+      const int cxl = xl ? c - 1 : c, czl = zl ? c - L.plane : c;
+      cxm = mx[n1 + cxl]; cxd = mx[n2 + cxl] + mx[c]; cxu = mx[n1 + c];
+      czm = mz[n1 + czl]; czd = mz[n2 + czl] + mz[c]; czu = mz[n1 + c];
+      if (L.has_y) {
+        const int cyl = yl ? c - L.NX : c;
+        cym = my[n1 + cyl]; cyd = my[n2 + cyl] + my[c]; cyu = my[n1 + c];
+      }
+    } else {
+      const double mxR = mx[c], mxL = mx[xl ? c - 1 : c];
+      const double mzR = mz[c], mzL = mz[zl ? c - L.plane : c];
+      cxm = mxL * SIXTH; cxd = mxL * THIRD + mxR * THIRD; cxu = mxR * SIXTH;
+      czm = mzL * SIXTH; czd = mzL * THIRD + mzR * THIRD; czu = mzR * SIXTH;
+      if (L.has_y) {
+        const double myR = my[c], myL = my[yl ? c - L.NX : c];
+        cym = myL * SIXTH; cyd = myL * THIRD + myR * THIRD; cyu = myR * SIXTH;
+      }
+    }
     // ---- compute phase
     double yp = 0.0, yf, yb;
-    rt0_dir<DOT>(xl, xl2, xh, mxL, mxR, xxm, xxf, xxf1, pc, pxm, yf, yb, yp, acc);
+    rt0_dir<DOT>(xl, xl2, xh, cxm, cxd, cxu, xxm, xxf, xxf1, pc, pxm, yf, yb, yp, acc);
     y[fx] = yf;
     if (!xh) y[fx + 1] = yb;
     if (L.has_y) {
-      rt0_dir<DOT>(yl, yl2, yh, myL, myR, xym, xyf, xyf1, pc, pym, yf, yb, yp, acc);
+      rt0_dir<DOT>(yl, yl2, yh, cym, cyd, cyu, xym, xyf, xyf1, pc, pym, yf, yb, yp, acc);
       y[fy] = yf;
       if (!yh) y[fy + L.NX] = yb;
     }
-    rt0_dir<DOT>(zl, zl2, zh, mzL, mzR, xzm, xzf, xzf1, pc, pzm, yf, yb, yp, acc);
+    rt0_dir<DOT>(zl, zl2, zh, czm, czd, czu, xzm, xzf, xzf1, pc, pzm, yf, yb, yp, acc);
     y[fz] = yf;
     if (!zh) y[fz + L.plane] = yb;
     y[ip] = yp;

@@ -33,6 +33,8 @@ struct QTab {
   double wv;         // weight of a DG node in the collocated rule: (1/2)^dim
   double OO[4][4][4];  // 3-D: O[qe][te] * O[qf][tf] at [qe][qf][te + 2 tf] (host-computed: the same IEEE products)
   double OOF[3][3][4]; // 3-D: OF[qe][te] * OF[qf][tf] at [qe][qf][te + 2 tf]
+  // RT0 velocity with S in DG-Q1 (-ov 0 -op 0 -os 1): mass rule of order OrderW + 2 = 3 points (3-D) / 2 points (2-D)
+  double x0[3], gw0[3], O0[3][2];   // points on [0,1], weights, DG basis at the points
 };
 
 // 3-D products of the transverse open bases (QTab::OO / QTab::OOF) in constant memory: the rolled quadrature loops
@@ -1086,6 +1088,97 @@ k1q_sat(Lay1 L, QTab tb, Phys ph, SatParam sp, long ncv, const double* __restric
         fo = div_rcp(mw, mw + mo);   // FS [REF src/saturation_solver.cpp:8-17]
       }
       Fout[(long)m * ncv + c0 + c] = fo;   // dof-major
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// -ov 0 -op 0 -os 1: RT0 / P0 velocity-pressure with the saturation in DG-Q1.  The RT0 mass block of a direction is
+// the 2x2 matrix  (geo_d / K_d) sum_q (w_q / lambda(S(x_q))) phi_i(xi_d) phi_j(xi_d),  phi = (1 - xi, xi), with the
+// rule of VectorFEMassIntegrator for RT0 (order OrderW + 2 el.order [MFEM-recall]: 3^3 / 2^2 points).  K4 stores its
+// three entries per cell and direction, a[(3 dir + {00, 01, 11}) ncv + c]; K1 and the face coefficients are the RT0
+// kernels with those entries in place of m/3, m/6 (kernels.cuh, VAR); K6 is k1q_sat fed with records formed from the
+// RT0 face fluxes (an RT0 field is the RT1 field whose four face nodes carry the face value and whose interior nodes
+// interpolate linearly).
+// ---------------------------------------------------------------------------------------
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k0q_coeff(Lay L, Phys ph, QTab tb, const double* __restrict__ S,
+                                                 const double* __restrict__ Kx, const double* __restrict__ Ky,
+                                                 const double* __restrict__ Kz, double gx, double gy, double gz,
+                                                 double* __restrict__ a) {
+  constexpr int NQ = HY ? 3 : 2, NQY = HY ? NQ : 1, NSL = HY ? 8 : 4;
+  const long c = (long)blockIdx.x * BLK + threadIdx.x;
+  if (c >= L.ncv) return;
+  const long n = L.ncv;
+  const int k = (int)(c / L.plane) - 1 + L.zlo;
+  if (k < 0 || k >= L.NZ) {
+    for (int e = 0; e < 9; ++e) a[e * n + c] = 0.0;
+    return;
+  }
+  double s[NSL];
+#pragma unroll
+  for (int m = 0; m < NSL; ++m) s[m] = S[c * NSL + m];
+  double ax[3] = {0.0, 0.0, 0.0}, ay[3] = {0.0, 0.0, 0.0}, az[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int q2 = 0; q2 < NQ; ++q2)
+#pragma unroll
+    for (int q1 = 0; q1 < NQY; ++q1)
+#pragma unroll
+      for (int q0 = 0; q0 < NQ; ++q0) {
+        double sq = 0.0;
+#pragma unroll
+        for (int m = 0; m < NSL; ++m) {
+          const int m0 = m & 1, m1 = HY ? (m >> 1) & 1 : 0, m2 = m >> (HY ? 2 : 1);
+          sq += s[m] * (tb.O0[q0][m0] * (HY ? tb.O0[q1][m1] : 1.0) * tb.O0[q2][m2]);
+        }
+        const double w = tb.gw0[q0] * (HY ? tb.gw0[q1] : 1.0) * tb.gw0[q2];
+        const double cq = w / lambda_of(ph, sq);
+        const double x0 = tb.x0[q0], x1 = HY ? tb.x0[q1] : 0.0, x2 = tb.x0[q2];
+        ax[0] += cq * ((1.0 - x0) * (1.0 - x0)); ax[1] += cq * ((1.0 - x0) * x0); ax[2] += cq * (x0 * x0);
+        if (HY) { ay[0] += cq * ((1.0 - x1) * (1.0 - x1)); ay[1] += cq * ((1.0 - x1) * x1); ay[2] += cq * (x1 * x1); }
+        az[0] += cq * ((1.0 - x2) * (1.0 - x2)); az[1] += cq * ((1.0 - x2) * x2); az[2] += cq * (x2 * x2);
+      }
+  const double fx = gx / Kx[c], fz = gz / Kz[c];
+#pragma unroll
+  for (int e = 0; e < 3; ++e) { a[e * n + c] = fx * ax[e]; a[(6 + e) * n + c] = fz * az[e]; }
+  if (HY) {
+    const double fy = gy / Ky[c];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) a[(3 + e) * n + c] = fy * ay[e];
+  }
+}
+
+// K6 records (see k1q_sat_pre) from the RT0 face fluxes u (dvec layout of kernels.cuh): along a direction the normal
+// component is (1 - xi) u_lo + xi u_hi for all NT lines; at a face point it is the face value (the transverse open
+// basis sums to one).
+template <bool HY>
+__global__ void __launch_bounds__(BLK) k0q_sat_pre(Lay L, QTab tb, const double* __restrict__ u, long ncv,
+                                                   double* __restrict__ vh, double* __restrict__ fn) {
+  using SQ = SatQ<HY>;
+  const CellIdx ci = owned_cell(L);
+  if (!ci.ok) return;
+  const int i = ci.i, j = ci.j, kl = ci.kl, kk = kl + 1;
+  const long c = ix_c(L, i, j, kk);
+  const int fx = ix_ux(L, i, j, kl), fz = ix_uz(L, i, j, kk);
+  const double lo[3] = {u[fx], HY ? u[ix_uy(L, i, j, kl)] : 0.0, u[fz]};
+  const double hi[3] = {u[fx + 1], HY ? u[ix_uy(L, i, j, kl) + L.NX] : 0.0, u[fz + L.plane]};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (!HY && d == 1) continue;
+    const int di = HY ? d : (d == 0 ? 0 : 1);
+    const double v0 = (1.0 - tb.sn[0]) * lo[d] + tb.sn[0] * hi[d], v1 = (1.0 - tb.sn[1]) * lo[d] + tb.sn[1] * hi[d];
+#pragma unroll
+    for (int t = 0; t < SQ::NT; ++t) {
+      vh[((long)di * SQ::NVH + 2 * t) * ncv + c] = v0;
+      vh[((long)di * SQ::NVH + 2 * t + 1) * ncv + c] = v1;
+    }
+    const bool top = d == 2 && kl == L.nzl - 1;
+#pragma unroll
+    for (int p = 0; p < SQ::NFP; ++p) {
+      const int qe = HY ? p % 3 : p, qf = HY ? p / 3 : 0;
+      const double w = HY ? tb.fw[qe] * tb.fw[qf] : tb.fw[qe];
+      fn[((long)di * SQ::NFP + p) * ncv + c] = w * lo[d];
+      if (top) fn[((long)di * SQ::NFP + p) * ncv + c + L.plane] = w * hi[d];
     }
   }
 }

@@ -95,4 +95,4 @@ def owned_ranges(dim, nx, ny, nz, rank, world, order=0, slab=None, order_s=0):
         darcy.append((nvx + py * lo, nvx + py * hi))
     darcy.append((nvx + nvy + plane * lo, nvx + nvy + plane * (hi + top)))
     darcy.append((nv + plane * lo, nv + plane * hi))
-    return darcy, [(plane * lo, plane * hi)]
+    return darcy, [(plane * nsl * lo, plane * nsl * hi)]

@@ -148,7 +148,7 @@ def test_driver_run_dgq1(pkg, orc, host_bins, tmp_path, dim):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("spaces", ["0 0 0", "1 1 0", "1 1 1"])
+@pytest.mark.parametrize("spaces", ["0 0 0", "0 0 1", "1 1 0", "1 1 1"])
 def test_driver_with_foreign_dof_numbering(host_bins, tmp_path, spaces):
     """The reference hands the solvers vectors in MFEM's numbering (RT dofs by mesh entity, face dofs oriented by the
     face's first element).  IMPES_COMPAT_SCRAMBLE makes the MFEM shim number its spaces with a random permutation and

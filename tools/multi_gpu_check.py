@@ -45,10 +45,16 @@ CASES = [
     (dict(dim=3, nx=6, ny=5, nz=9), 11, abi.SCHUR_SGS_LEX),  # 11 = RT1/Q1 with DG-Q1 saturation (-os 1): tolerance parity
     (dict(dim=3, nx=8, ny=6, nz=16), 11, abi.SCHUR_MG),
     (dict(dim=2, nx=16, ny=24), 11, abi.SCHUR_MG),
+    (dict(dim=3, nx=8, ny=6, nz=16), 10, abi.SCHUR_MG),      # 10 = RT0/P0 with DG-Q1 saturation: tolerance parity (assembled oracle)
+    (dict(dim=2, nx=9, ny=11), 10, abi.SCHUR_SGS_LEX),
 ]
+ONLY = os.environ.get("MGPU_ONLY")   # development: run only the cases with this order code
 for cfg, order, prec in CASES:
-    order_s = 1 if order == 11 else 0
-    order = 1 if order == 11 else order
+    if ONLY and str(order) != ONLY:
+        continue
+    order_s = 1 if order in (10, 11) else 0
+    arith = 0 if order == 10 else 1   # no canonical mirror for RT0 / DG-Q1: the assembled formulation
+    order = {11: 1, 10: 0}.get(order, order)
     nlay = cfg["nz"] if cfg["dim"] == 3 else cfg["ny"]
     if nlay < world or (prec == abi.SCHUR_MG and nlay < 2 * world):
         continue
@@ -90,8 +96,8 @@ for cfg, order, prec in CASES:
         orc = load_oracle()
         d1 = workloads.build(K="lognormal", order=order, order_s=order_s, schur_prec=prec, **cfg)[0]
         o = orc.Oracle(d1, Kx, Ky, Kz, phi)
-        o.set_arith(1)
-        o.set_threads_det(8)
+        o.set_arith(arith)
+        if arith: o.set_threads_det(8)
         o.update_coefficients(S)
         same = np.array_equal if order_s == 0 else (lambda a, b: rel(a, b) < 1e-12)   # -os 1: round-off parity
         e1 = same(yg, o.darcy_apply(x))
@@ -108,7 +114,7 @@ for cfg, order, prec in CASES:
         ok = ok and good
         print(f"{cfg} order={order} os={order_s} prec={'MG' if prec else 'SGS'} world={world} slab={(s.dims.slab_lo, s.dims.slab_hi)}: "
               f"K1 bit-exact={e1} prec bit-exact={e2} sat bit-exact={e3} "
-              f"iters gpu={st.iterations} oracle={sto.iterations} rel_u={ex:.2e} guards={(bad, mx) == (bo, mo)} local-api={loc_ok} -> {'OK' if good else 'FAIL'}",
+              f"iters gpu={st.iterations} oracle={sto.iterations} rel_u={ex:.2e} rel_S={rel(Sg, So):.2e} guards={(bad, mx) == (bo, mo)} local-api={loc_ok} -> {'OK' if good else 'FAIL'}",
               flush=True)
     s.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
