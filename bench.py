@@ -502,6 +502,12 @@ def main():
         if roofline:
             for k in ("how", "peak_source", "traffic_source"):
                 full_note = roofline.pop(k, None)
+            top = next((r for r in rl if r["k"] == roofline["kernel"]), {})
+            if top.get("fp64_pipe_pct_ncu"):
+                roofline["fp64_pipe_pct_ncu"] = top["fp64_pipe_pct_ncu"]
+                roofline["note"] = ("fp64-pipe / issue co-limited kernel (ncu: fp64 pipe utilisation beside, DRAM < 50 %); its DRAM "
+                                    "traffic exceeds the algorithmic bytes where per-step records trade bytes for fp64 work "
+                                    "(DESIGN.md section 4)")
             if roofline["frac"] > 1.0:
                 roofline["note"] = ("peak = measured 1:1 copy bandwidth; this kernel reads 2 bytes per byte written and "
                                     "moves exactly its algorithmic bytes (see traffic), so it can exceed the copy figure")
