@@ -167,3 +167,26 @@ def test_rt1_multigrid_mode_bit_exact(pkg, orc, native_lib, cfg):
     assert rel(xg[:o.nv], xr[:o.nv]) < 1e-4
     if n > 1000:
         assert stg.iterations < str_.iterations
+
+
+@pytest.mark.parametrize("sweeps", [4, 5])
+def test_rt1_multigrid_other_sweep_counts_bit_exact(pkg, orc, native_lib, sweeps):
+    """-mg-smooth: other (rounded-up-to-even) sweep counts run the damping sequence 1.4, 0.55, 1.4, 0.55, ... forwards
+    before and backwards after the coarse correction; same bits as the oracle's restatement, still a symmetric
+    preconditioner (MINRES converges)."""
+    from incompressible_flow_b200 import abi
+    d, o, s, n = make(pkg, orc, dict(dim=3, nx=6, ny=5, nz=4), schur_prec=abi.SCHUR_MG, mg_smooth=sweeps)
+    o.set_arith(1)
+    rng = np.random.default_rng(22)
+    S = rng.uniform(0.0, 0.9, n)
+    x = rng.standard_normal(o.nv + o.np_)
+    y = rng.standard_normal(o.nv + o.np_)
+    s.update_coefficients(S)
+    o.update_coefficients(S)
+    px, py = s.prec_apply(x), s.prec_apply(y)
+    assert np.array_equal(px, o.prec_apply(x))
+    assert abs(y @ px - x @ py) < 1e-10 * abs(y @ px)
+    xo, sto, _ = o.pressure_solve(S)
+    xg, stg = s.pressure_solve(S)
+    assert stg.converged == 1 and stg.iterations == sto.iterations and np.array_equal(xg, xo)
+    s.close()
