@@ -84,6 +84,34 @@ def test_slab_ranges_balanced(pkg):
     assert r[0][0] == 0 and r[-1][1] == 85 and all(r[i][1] == r[i + 1][0] for i in range(7))
 
 
+@pytest.mark.parametrize("dim,n,order,order_s", [(2, (6, 9, 1), 0, 0), (3, (4, 3, 8), 0, 1), (2, (5, 8, 1), 0, 1),
+                                                 (3, (3, 4, 6), 1, 0), (3, (3, 4, 6), 1, 1), (2, (5, 8, 1), 1, 1)])
+def test_owned_ranges_tile_the_vectors(pkg, dim, n, order, order_s):
+    """The slabs' owned index ranges are disjoint and cover the Darcy vector and the saturation vector of every space
+    triple (DG-Q1 saturation: 2^dim dofs per cell whatever the velocity order)."""
+    nx, ny, nz = n
+    world = 3
+    ncell = nx * ny * (nz if dim == 3 else 1)
+    ns = ncell * (2 ** dim if order_s else 1)
+    if order == 0:
+        nv = (nx + 1) * ny * (nz if dim == 3 else 1) + nx * (ny + 1) * (nz if dim == 3 else 1) + (nx * ny * (nz + 1) if dim == 3 else 0)
+        npr = ncell
+    else:
+        if dim == 2:
+            nv = (2 * nx + 1) * 2 * ny + 2 * nx * (2 * ny + 1)
+        else:
+            nv = (2 * nx + 1) * 2 * ny * 2 * nz + 2 * nx * (2 * ny + 1) * 2 * nz + 2 * nx * 2 * ny * (2 * nz + 1)
+        npr = ncell * 2 ** dim
+    cov_x, cov_s = np.zeros(nv + npr, int), np.zeros(ns, int)
+    for r in range(world):
+        dx, ds = pkg.partition.owned_ranges(dim, nx, ny, nz, r, world, order=order, order_s=order_s)
+        for a, b in dx:
+            cov_x[a:b] += 1
+        for a, b in ds:
+            cov_s[a:b] += 1
+    assert np.all(cov_x == 1) and np.all(cov_s == 1)
+
+
 def test_slab_ranges_multigrid_aligned(pkg):
     """Multi-GPU multigrid mode: slabs in units of 2^g layers, g = the first replicated level (aggregates of the
     distributed levels never straddle GPUs); small levels run replicated instead of exchanging halos."""
