@@ -74,6 +74,15 @@ int main(int argc, char** argv) {
     CHECK(d2s(7, 0, 0, 0, 6) == "000007" && d2s(3) == "3");
     std::remove(f32.c_str());
     std::remove(f64.c_str());
+    // array helpers [REF src/utilities.cpp:14-122]
+    const double v[5] = {0.5, -2.0, 3.25, 1.0, 3.0};
+    double lo, hi, le[5], ge[5];
+    get_minmax(v, 5, lo, hi);
+    CHECK(lo == -2.0 && hi == 3.25 && get_max(v, 5) == 3.25 && std::fabs(to_radians(180.0) - 3.141592653589793) < 1e-15);
+    get_LE(v, 5, 1.0, le);
+    get_GE(v, 5, 1.0, ge);
+    const double want_le[5] = {0.5, -2.0, 1.0, 1.0, 1.0}, want_ge[5] = {1.0, 1.0, 3.25, 1.0, 3.0};
+    for (int i = 0; i < 5; ++i) CHECK(le[i] == want_le[i] && ge[i] == want_ge[i]);
     std::cout << "ok binary_io" << std::endl;
   }
   {  // .vts writers [REF src/utilities.cpp:126-472]: the 2-D per-cell file byte for byte, the shapes of the others

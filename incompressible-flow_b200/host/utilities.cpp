@@ -47,6 +47,27 @@ void write_binary(const char* filename, int n_values, const double* values) {
   out.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)n_values * sizeof(float));
 }
 
+double to_radians(double x) { return x * 3.14159265358979323846 / 180.0; }
+double get_max(const double* a, int n_elements) {
+  double lo, hi;
+  get_minmax(a, n_elements, lo, hi);
+  return hi;
+}
+void get_minmax(const double* a, int n_elements, double& min_val, double& max_val) {
+  MFEM_VERIFY(n_elements > 0, "empty array");
+  min_val = max_val = a[0];
+  for (int i = 1; i < n_elements; ++i) {
+    if (a[i] < min_val) min_val = a[i];
+    if (a[i] > max_val) max_val = a[i];
+  }
+}
+// one clip routine behind the reference's pair: keep the values on the `keep_below` side of the bound
+static void clip(const double* a, int n, double bound, bool keep_below, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = ((a[i] <= bound) == keep_below || a[i] == bound) ? a[i] : bound;
+}
+void get_LE(const double* a, int n_elements, double LE_value, double* a_LE) { clip(a, n_elements, LE_value, true, a_LE); }
+void get_GE(const double* a, int n_elements, double GE_value, double* a_GE) { clip(a, n_elements, GE_value, false, a_GE); }
+
 // ---- .vts ------------------------------------------------------------------------------------------------
 // One table-driven emitter behind the six reference signatures.  A file = header, one data section (PointData
 // for vertex fields, CellData for per-cell fields), the vertex coordinates (the last vertex of every direction is

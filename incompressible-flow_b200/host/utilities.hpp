@@ -10,6 +10,14 @@
 void read_binary(const char* filename, int n_values, double* values);
 void write_binary(const char* filename, int n_values, const double* values);
 
+// small array helpers of the reference [REF src/utilities.hpp:64-94]: degrees -> radians, maximum, minimum and maximum,
+// clipping from above (get_LE: min(a, bound)) and from below (get_GE: max(a, bound))
+double to_radians(double x);
+double get_max(const double* a, int n_elements);
+void get_minmax(const double* a, int n_elements, double& min_val, double& max_val);
+void get_LE(const double* a, int n_elements, double LE_value, double* a_LE);
+void get_GE(const double* a, int n_elements, double GE_value, double* a_GE);
+
 // VTK StructuredGrid (.vts, ascii) writers of the reference, same signatures and file layout
 // [REF src/utilities.hpp:109-139] [REF src/utilities.cpp:126-472]: vertex-based vector / scalar fields
 // ((nx+1)(ny+1)(nz+1) values, x fastest) and per-cell scalars (nx ny nz values).  2-D files have extent 1 in z.
